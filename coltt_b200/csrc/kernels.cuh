@@ -1,0 +1,79 @@
+// kernels.cuh — parameter blocks and launchers of the CUDA kernels (internal header).
+#pragma once
+#include "common.cuh"
+
+namespace coltt {
+
+enum { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_F8C = 2 };
+__host__ __device__ inline uint32_t elem_size(int e) { return e == ELEM_F32 ? 4u : (e == ELEM_F16 ? 2u : 1u); }
+
+// ---- prep.cu ---------------------------------------------------------------------------
+struct PrepParams {
+  const float* in;        // [n][in_stride] un-normalized fp32 (device)
+  size_t n;
+  uint32_t in_stride;     // floats
+  uint32_t dim;
+  uint32_t smem_stride;   // floats per warp scratch (>= dim)
+  int normalize;          // cosine
+  uint8_t* rows_out;      // nullable: stored rows [slot][row_stride bytes]
+  uint32_t row_stride;
+  const uint32_t* slots;  // nullable: destination slot per input row
+  uint32_t slot_base;     // when slots == nullptr: slot = slot_base + i
+  float* norm2_out;       // nullable
+  int norm2_by_slot;      // index norm2_out by slot (rows) or by i (queries)
+  float* deq_out;         // nullable: fp32 copy of the stored (dequantized) values [n][deq_stride], zero padded
+  uint32_t deq_stride;
+  __half* f16_out;        // nullable: fp16 copy [n][f16_stride], zero padded
+  uint32_t f16_stride;
+};
+int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream);
+
+// ---- flat_scan.cu (K1 exact-order scan + K3 gather front-end) ---------------------------
+struct ScanParams {
+  const uint8_t* rows;      // [slot][row_stride]
+  uint32_t row_stride;      // bytes (multiple of 16)
+  uint32_t dim;
+  uint32_t n_items;         // rows scanned: n_rows, or n_subset with `subset`
+  const uint32_t* subset;   // nullable: slots to gather
+  const float* row_norm2;   // [slot]
+  const uint64_t* ids;      // [slot]
+  const float* queries;     // [nq][q_stride] dequantized fp32, zero padded to q_stride
+  const float* q_norm2;     // [nq]
+  uint32_t q_stride;        // floats, multiple of 8
+  uint32_t nq;
+  uint32_t k;
+  int nearest;              // select mode
+  int metric;
+  Hit* warp_lists;          // scratch [gridDim.x*W][nq][k] best-first
+  Hit* cta_lists;           // out     [gridDim.x][nq][k]  best-first
+  int* cta_counts;          // out     [gridDim.x][nq]
+  uint32_t chunk_bytes;     // bytes of one row copied per pipeline stage (multiple of 128)
+  uint32_t n_stages;        // stages per warp
+};
+struct ScanPlan {
+  int grid_x, grid_y, warps, qt;
+  uint32_t chunk_bytes, n_stages;
+  size_t smem_bytes;
+  size_t warp_list_bytes, cta_list_bytes, cta_count_bytes;
+};
+// Chooses tile/pipeline shape for (elem, dim, nq, k, n_items); no device work.
+int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items, uint32_t nq, uint32_t k, int n_sms,
+                   ScanPlan* plan);
+int launch_flat_scan(const ScanParams& p, const ScanPlan& plan, int elem, cudaStream_t stream);
+
+// ---- topk_merge.cu (K5) -----------------------------------------------------------------
+struct MergeParams {
+  const Hit* lists;          // [n_lists][nq][k_in]
+  const int* counts;         // [n_lists][nq]
+  int n_lists;
+  uint32_t nq;
+  uint32_t k_in;
+  uint32_t k;
+  int nearest;
+  int in_best_first;         // 1: lists are best-first (internal); 0: lists are in T order (public)
+  Hit* out;                  // [nq][k] in T order (ascending score, NaN last, then id)
+  int* out_counts;           // [nq]
+};
+int launch_merge_topk(const MergeParams& p, cudaStream_t stream);
+
+}  // namespace coltt

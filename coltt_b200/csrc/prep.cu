@@ -1,0 +1,116 @@
+// prep.cu — ingest / query preparation: Normalize -> Lower -> AVX-order ||x||^2, on the GPU.
+//
+// Reference path being replaced (per vector, on the CPU):
+//   edge.Normalize                    edge/vectorstore.go:173-189  (sequential f32 sum, sqrt via f64, f32 divide)
+//   Quantization.Lower                edge/{f16,bf16,f8}_quantization.go  -> pkg/compresshelper
+//   ||x||^2 in the cosine kernel      pkg/distance/simd/cpp/avx.cpp:51-75 (recomputed per distance call there;
+//                                     here computed once per row at ingest, same lane order, 4 B/row)
+// One warp per vector.  The Normalize sum is inherently sequential (its rounding sequence is
+// part of the parity contract), so lane 0 walks the row out of shared memory; everything
+// else is lane-parallel.  HBM traffic: reads dim*4 B, writes dim*elem B (+ optional fp32/fp16
+// query copies) per vector — an ingest-time cost, not on the search path.
+#include "kernels.cuh"
+#include "store.h"
+
+namespace coltt {
+
+template <int ELEM>
+__global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t dim = p.dim;
+  float* x = smem_f + (size_t)warp * p.smem_stride;
+
+  for (size_t i = (size_t)blockIdx.x * warps_per_block + warp; i < p.n; i += (size_t)gridDim.x * warps_per_block) {
+    const float* src = p.in + i * (size_t)p.in_stride;
+    for (uint32_t d = lane; d < dim; d += 32) x[d] = src[d];
+    __syncwarp();
+
+    if (p.normalize) {
+      float norm = 0.0f;
+      if (lane == 0) {
+        // edge/vectorstore.go:176-178: for i := range v { norm += v[i] * v[i] }  (unfused, in order)
+        for (uint32_t d = 0; d < dim; d++) norm = add_rn(norm, mul_rn(x[d], x[d]));
+      }
+      norm = __shfl_sync(0xffffffffu, norm, 0);
+      if (norm == 0.0f) {
+        for (uint32_t d = lane; d < dim; d += 32) x[d] = 0.0f;  // :179-181 zero vector stays zero
+      } else {
+        float nrm = sqrt_via_f64(norm);                            // :183
+        for (uint32_t d = lane; d < dim; d += 32) x[d] = __fdiv_rn(x[d], nrm);  // :184-186
+      }
+      __syncwarp();
+    }
+
+    // Lower + write the stored row; keep the dequantized value in smem for the norm pass.
+    const size_t slot = p.slots ? (size_t)p.slots[i] : (size_t)p.slot_base + i;
+    uint8_t* row = p.rows_out ? p.rows_out + slot * (size_t)p.row_stride : nullptr;
+    for (uint32_t d = lane; d < dim; d += 32) {
+      float v = x[d];
+      if (ELEM == ELEM_F32) {
+        if (row) reinterpret_cast<float*>(row)[d] = v;
+      } else if (ELEM == ELEM_F16) {
+        // compresshelper.Fromfloat32 (float16.go:124,274-321): IEEE RNE incl. subnormals and
+        // overflow->inf == __float2half_rn for every non-NaN input (tests/test_gpu_codec.py).
+        __half h = __float2half_rn(v);
+        if (row) reinterpret_cast<__half*>(row)[d] = h;
+        v = __half2float(h);  // Float16.Float32 (float16.go:184,237-270), exact
+      } else {
+        uint8_t c = f8_compat_encode(__float_as_uint(v));   // F8Fromfloat32 (float8.go:120,270-313)
+        if (row) row[d] = c;
+        v = __uint_as_float(f8_compat_decode_bits(c));       // Float8.Float32 (float8.go:180,233-266)
+      }
+      x[d] = v;
+    }
+    // zero the padding of the stored row so bulk copies of whole 16-byte units are defined
+    if (row) {
+      const uint32_t es = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
+      for (uint32_t b = dim * es + lane; b < p.row_stride; b += 32) row[b] = 0;
+    }
+    __syncwarp();
+
+    // ||x||^2 exactly as cosine_similarity_dot_norm accumulates it for one operand
+    // (avx.cpp:57-63 lanes, :3-8 tree, :68-72 scalar tail).
+    float acc = 0.0f;
+    const uint32_t full = (dim / 8) * 8;
+    if (lane < 8)
+      for (uint32_t d = lane; d < full; d += 8) acc = add_rn(acc, mul_rn(x[d], x[d]));
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));  // (l0+l1) (l2+l3) (l4+l5) (l6+l7)
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));  // (l0+l1)+(l2+l3), (l4+l5)+(l6+l7)
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));  // sum of both halves
+    if (lane == 0) {
+      for (uint32_t d = full; d < dim; d++) acc = add_rn(acc, mul_rn(x[d], x[d]));
+      if (p.norm2_out) p.norm2_out[p.norm2_by_slot ? slot : i] = acc;
+    }
+    if (p.deq_out) {
+      float* dq = p.deq_out + i * (size_t)p.deq_stride;
+      for (uint32_t d = lane; d < p.deq_stride; d += 32) dq[d] = d < dim ? x[d] : 0.0f;
+    }
+    if (p.f16_out) {
+      __half* hq = p.f16_out + i * (size_t)p.f16_stride;
+      for (uint32_t d = lane; d < p.f16_stride; d += 32) hq[d] = d < dim ? __float2half_rn(x[d]) : __half(0);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream) {
+  if (p.n == 0) return COLTT_OK;
+  // warps per block bounded by shared memory: one fp32 copy of the vector per warp
+  const size_t per_warp = (size_t)p.smem_stride * sizeof(float);
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  if (per_warp * warps > 227 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "dim too large for the ingest kernel");
+  const size_t smem = per_warp * warps;
+  const size_t blocks_needed = (p.n + warps - 1) / warps;
+  const int grid = (int)(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
+  auto k = elem == ELEM_F32 ? prep_rows_kernel<ELEM_F32> : (elem == ELEM_F16 ? prep_rows_kernel<ELEM_F16> : prep_rows_kernel<ELEM_F8C>);
+  COLTT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, warps * 32, smem, stream>>>(p);
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  return COLTT_OK;
+}
+
+}  // namespace coltt

@@ -1,0 +1,607 @@
+// store.cu — host side of one edge FLAT collection on one GPU, and its C-ABI.
+//
+// Mirrors the reference's `vectorspace` implementations (edge/vectorstore.go:30-49):
+//   ChangedVertex            -> coltt_b200_store_upsert      (none_vectorstore.go:66-103)
+//   RemoveVertex             -> coltt_b200_store_remove      (none_vectorstore.go:105-127)
+//   VertexSearch             -> coltt_b200_store_search      (none_vectorstore.go:129-180)
+//   FilterableVertexSearch   -> coltt_b200_store_search_subset (none_vectorstore.go:182-253)
+//   SaveVertex / LoadVertex  -> coltt_b200_store_export/import (none_vectorstore.go:308-516)
+// Data layout in HBM (one allocation each, grown geometrically):
+//   rows   [capacity][row_stride]  row-major, element = fp32 / fp16 / f8-compat code,
+//                                   row_stride = dim*elem rounded up to 16 B (bulk-copy unit)
+//   norm2  [capacity] fp32          ||row||^2 in the AVX lane order (prep.cu)
+//   ids    [capacity] u64           slot -> id (ids are sparse snowflakes, edge/id_generator.go)
+// Rows are dense: remove moves the last row into the hole.  The id -> slot map lives on the
+// host (the Go side owns metadata and filters; it hands ids across the boundary).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "store.h"
+
+namespace coltt {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+int sm100_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; i++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ok++;
+  }
+  return ok;
+}
+
+int require_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(COLTT_ERR_NO_DEVICE, "no CUDA device visible: libcoltt_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(COLTT_ERR_INVALID, "bad device ordinal");
+  cudaDeviceProp pr;
+  COLTT_CUDA(cudaGetDeviceProperties(&pr, device));
+  if (pr.major != 10) return fail(COLTT_ERR_NO_DEVICE, std::string("device is not sm_100 (Blackwell B200): ") + pr.name);
+  return COLTT_OK;
+}
+
+int DeviceBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return COLTT_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return fail(COLTT_ERR_NOMEM, "cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+    }
+    want = bytes;
+  }
+  cap = want;
+  return COLTT_OK;
+}
+DeviceBuf::~DeviceBuf() {
+  if (p) cudaFree(p);
+}
+int PinnedBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return COLTT_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+    return fail(COLTT_ERR_NOMEM, "cudaMallocHost failed");
+  }
+  cap = bytes;
+  return COLTT_OK;
+}
+PinnedBuf::~PinnedBuf() {
+  if (p) cudaFreeHost(p);
+}
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+SearchCtx::~SearchCtx() {
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  if (done) cudaEventDestroy(done);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+__global__ void scatter_ids_kernel(const uint64_t* src, const uint32_t* slots, uint64_t* dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[slots[i]] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+Store::~Store() {
+  cudaSetDevice(device);
+  pool.clear();
+  if (d_rows) cudaFree(d_rows);
+  if (d_norm2) cudaFree(d_norm2);
+  if (d_ids) cudaFree(d_ids);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int Store::create(const coltt_store_cfg* cfg, Store** out) {
+  if (!cfg || !out) return fail(COLTT_ERR_INVALID, "null argument");
+  if (cfg->dim == 0) return fail(COLTT_ERR_INVALID, "dim must be > 0");
+  if (cfg->metric != COLTT_COSINE && cfg->metric != COLTT_EUCLIDEAN) return fail(COLTT_ERR_INVALID, "bad metric");
+  int elem;
+  switch (cfg->quant) {
+    case COLTT_QUANT_NONE: elem = ELEM_F32; break;
+    case COLTT_QUANT_F16:
+    case COLTT_QUANT_BF16: elem = ELEM_F16; break;  // the reference's bf16 IS binary16
+    case COLTT_QUANT_F8: elem = ELEM_F8C; break;
+    case COLTT_QUANT_F8_E4M3: return fail(COLTT_ERR_UNSUPPORTED, "F8_E4M3 store not built yet");
+    default: return fail(COLTT_ERR_INVALID, "not support quantization type");  // edge/vectorstore.go:78
+  }
+  int rc = require_device(cfg->device);
+  if (rc) return rc;
+  COLTT_CUDA(cudaSetDevice(cfg->device));
+  std::unique_ptr<Store> s(new Store());
+  s->cfg = *cfg;
+  s->device = cfg->device;
+  s->elem = elem;
+  s->dim = cfg->dim;
+  s->row_stride = (cfg->dim * elem_size(elem) + 15) / 16 * 16;
+  cudaDeviceProp pr;
+  COLTT_CUDA(cudaGetDeviceProperties(&pr, cfg->device));
+  s->n_sms = pr.multiProcessorCount;
+  COLTT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (cfg->capacity_hint) {
+    rc = s->reserve(cfg->capacity_hint);
+    if (rc) return rc;
+  }
+  *out = s.release();
+  return COLTT_OK;
+}
+
+int Store::reserve(size_t rows) {
+  if (rows <= capacity) return COLTT_OK;
+  if (rows > 0xfffffff0ull) return fail(COLTT_ERR_UNSUPPORTED, "more than 2^32 rows per GPU shard");
+  size_t nc = std::max<size_t>(rows, std::max<size_t>(capacity * 2, 1024));
+  uint8_t* nr = nullptr;
+  float* nn = nullptr;
+  uint64_t* ni = nullptr;
+  auto try_alloc = [&](size_t c) {
+    nr = nullptr; nn = nullptr; ni = nullptr;
+    if (cudaMalloc(&nr, c * row_stride) == cudaSuccess && cudaMalloc(&nn, c * 4) == cudaSuccess &&
+        cudaMalloc(&ni, c * 8) == cudaSuccess)
+      return true;
+    cudaGetLastError();
+    if (nr) cudaFree(nr);
+    if (nn) cudaFree(nn);
+    if (ni) cudaFree(ni);
+    return false;
+  };
+  if (!try_alloc(nc)) {
+    nc = rows;  // geometric growth did not fit: retry with the exact size
+    if (!try_alloc(nc)) return fail(COLTT_ERR_NOMEM, "out of device memory growing the store");
+  }
+  if (n_rows) {
+    COLTT_CUDA(cudaMemcpyAsync(nr, d_rows, n_rows * row_stride, cudaMemcpyDeviceToDevice, stream));
+    COLTT_CUDA(cudaMemcpyAsync(nn, d_norm2, n_rows * 4, cudaMemcpyDeviceToDevice, stream));
+    COLTT_CUDA(cudaMemcpyAsync(ni, d_ids, n_rows * 8, cudaMemcpyDeviceToDevice, stream));
+    COLTT_CUDA(cudaStreamSynchronize(stream));
+  }
+  if (d_rows) cudaFree(d_rows);
+  if (d_norm2) cudaFree(d_norm2);
+  if (d_ids) cudaFree(d_ids);
+  d_rows = nr;
+  d_norm2 = nn;
+  d_ids = ni;
+  capacity = nc;
+  return COLTT_OK;
+}
+
+// ChangedVertex, batched.  Duplicate ids inside one batch: the last one wins, as n sequential
+// ChangedVertex calls would leave it.
+int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
+  if (n == 0) return COLTT_OK;
+  if (!ids || !vecs) return fail(COLTT_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(mu);
+  COLTT_CUDA(cudaSetDevice(device));
+  std::unordered_map<uint64_t, size_t> last;
+  last.reserve(n * 2);
+  for (size_t i = 0; i < n; i++) last[ids[i]] = i;
+  std::vector<uint32_t> src_idx, slots;
+  std::vector<uint64_t> uids;
+  src_idx.reserve(last.size()); slots.reserve(last.size()); uids.reserve(last.size());
+  size_t new_rows = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (last[ids[i]] != i) continue;
+    auto it = id2slot.find(ids[i]);
+    uint32_t slot = it != id2slot.end() ? it->second : (uint32_t)(n_rows + new_rows++);
+    src_idx.push_back((uint32_t)i); slots.push_back(slot); uids.push_back(ids[i]);
+  }
+  int rc = reserve(n_rows + new_rows);
+  if (rc) return rc;
+  const size_t m = src_idx.size();
+  const size_t chunk = std::max<size_t>(1, std::min<size_t>(m, (64u << 20) / ((size_t)dim * 4)));
+  rc = up_in.ensure(chunk * dim * 4); if (rc) return rc;
+  rc = up_slots.ensure(chunk * 4); if (rc) return rc;
+  rc = up_ids.ensure(chunk * 8); if (rc) return rc;
+  rc = up_pinned.ensure(chunk * dim * 4); if (rc) return rc;
+  for (size_t base = 0; base < m; base += chunk) {
+    const size_t c = std::min(chunk, m - base);
+    float* stage = (float*)up_pinned.p;
+    for (size_t j = 0; j < c; j++) std::memcpy(stage + j * dim, vecs + (size_t)src_idx[base + j] * dim, (size_t)dim * 4);
+    COLTT_CUDA(cudaMemcpyAsync(up_in.p, stage, c * dim * 4, cudaMemcpyHostToDevice, stream));
+    COLTT_CUDA(cudaMemcpyAsync(up_slots.p, slots.data() + base, c * 4, cudaMemcpyHostToDevice, stream));
+    COLTT_CUDA(cudaMemcpyAsync(up_ids.p, uids.data() + base, c * 8, cudaMemcpyHostToDevice, stream));
+    PrepParams pp{};
+    pp.in = (const float*)up_in.p; pp.n = c; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
+    pp.normalize = cfg.metric == COLTT_COSINE;  // `if vertex.distance.Type() == T_COSINE` (none_vectorstore.go:96-98)
+    pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slots = (const uint32_t*)up_slots.p;
+    pp.norm2_out = d_norm2; pp.norm2_by_slot = 1;
+    rc = launch_prep_rows(pp, elem, stream);
+    if (rc) return rc;
+    scatter_ids_kernel<<<(unsigned)((c + 255) / 256), 256, 0, stream>>>((const uint64_t*)up_ids.p, (const uint32_t*)up_slots.p, d_ids, c);
+    COLTT_CUDA(cudaGetLastError());
+    COLTT_CUDA(cudaStreamSynchronize(stream));  // staging buffers are reused by the next chunk
+  }
+  h_ids.resize(n_rows + new_rows);
+  for (size_t j = 0; j < m; j++) {
+    id2slot[uids[j]] = slots[j];
+    h_ids[slots[j]] = uids[j];
+  }
+  n_rows += new_rows;
+  return COLTT_OK;
+}
+
+int Store::remove(const uint64_t* ids, size_t n) {
+  if (n == 0) return COLTT_OK;
+  if (!ids) return fail(COLTT_ERR_INVALID, "null argument");
+  std::unique_lock<std::shared_mutex> lk(mu);
+  COLTT_CUDA(cudaSetDevice(device));
+  for (size_t i = 0; i < n; i++) {
+    auto it = id2slot.find(ids[i]);
+    if (it == id2slot.end()) continue;  // Go's delete() on a missing key is a no-op
+    const uint32_t s = it->second;
+    const uint32_t lastslot = (uint32_t)(n_rows - 1);
+    id2slot.erase(it);
+    if (s != lastslot) {
+      COLTT_CUDA(cudaMemcpyAsync(d_rows + (size_t)s * row_stride, d_rows + (size_t)lastslot * row_stride, row_stride, cudaMemcpyDeviceToDevice, stream));
+      COLTT_CUDA(cudaMemcpyAsync(d_norm2 + s, d_norm2 + lastslot, 4, cudaMemcpyDeviceToDevice, stream));
+      COLTT_CUDA(cudaMemcpyAsync(d_ids + s, d_ids + lastslot, 8, cudaMemcpyDeviceToDevice, stream));
+      h_ids[s] = h_ids[lastslot];
+      id2slot[h_ids[s]] = s;
+    }
+    h_ids.pop_back();
+    n_rows--;
+  }
+  COLTT_CUDA(cudaStreamSynchronize(stream));
+  return COLTT_OK;
+}
+
+// Scratch affinity: work enqueued on one stream may reuse the scratch last used on the same
+// stream (stream order protects it); otherwise take a context whose last use has completed.
+std::unique_ptr<SearchCtx> Store::acquire_ctx(cudaStream_t user_stream) {
+  {
+    std::lock_guard<std::mutex> g(pool_mu);
+    for (size_t i = 0; i < pool.size(); i++) {
+      SearchCtx& c = *pool[i];
+      const bool same = user_stream && c.used && c.last_stream == user_stream;
+      if (same || !c.used || cudaEventQuery(c.done) == cudaSuccess) {
+        auto out = std::move(pool[i]);
+        pool.erase(pool.begin() + i);
+        return out;
+      }
+    }
+    cudaGetLastError();  // cudaErrorNotReady from the queries above is not an error
+  }
+  std::unique_ptr<SearchCtx> c(new SearchCtx());
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  for (auto& e : c->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return c;
+}
+void Store::release_ctx(std::unique_ptr<SearchCtx> c) {
+  std::lock_guard<std::mutex> g(pool_mu);
+  if (c->have_times) { last_ms[0] = c->ms[0]; last_ms[1] = c->ms[1]; last_ms[2] = c->ms[2]; last_ms[3] = c->ms[3]; }
+  pool.push_back(std::move(c));
+}
+
+// The device part of a search: everything enqueued on `st`; queries and outputs on the device.
+// Caller holds the shared lock.
+int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int select_mode,
+                          int math_mode, const uint32_t* d_subset, size_t n_subset, Hit* d_out, int* d_counts,
+                          bool timed) {
+  if (k <= 0) return fail(COLTT_ERR_INVALID, "top-k must be positive");
+  if (select_mode != COLTT_SELECT_COMPAT && select_mode != COLTT_SELECT_NEAREST) return fail(COLTT_ERR_INVALID, "bad select mode");
+  if (math_mode != COLTT_MATH_EXACT && math_mode != COLTT_MATH_FAST) return fail(COLTT_ERR_INVALID, "bad math mode");
+  const size_t n_items = d_subset ? n_subset : n_rows;
+  const int nearest = select_mode == COLTT_SELECT_NEAREST;
+  const uint32_t q_stride = (dim + 7) / 8 * 8;
+  int rc;
+  if (n_items == 0) {
+    COLTT_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(int), st));
+    if (timed) for (auto& e : c.ev) cudaEventRecord(e, st);
+    return COLTT_OK;
+  }
+  const uint32_t k_eff = (uint32_t)std::min<size_t>((size_t)k, n_items);  // lists never hold more than n_items
+  // query batches bounded by list scratch
+  ScanPlan plan;
+  size_t qb = nq;
+  for (;;) {
+    rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_items, (uint32_t)qb, k_eff, n_sms, &plan);
+    if (rc) return rc;
+    if (plan.warp_list_bytes <= (512u << 20) || qb <= 8) break;
+    qb = std::max<size_t>(8, qb / 2);
+  }
+  rc = c.q_deq.ensure(nq * q_stride * 4); if (rc) return rc;
+  rc = c.q_n2.ensure(nq * 4); if (rc) return rc;
+  rc = c.warp_lists.ensure(plan.warp_list_bytes); if (rc) return rc;
+  rc = c.cta_lists.ensure(plan.cta_list_bytes); if (rc) return rc;
+  rc = c.cta_counts.ensure(plan.cta_count_bytes); if (rc) return rc;
+
+  if (timed) cudaEventRecord(c.ev[0], st);
+  // Normalize(target) + Lower(target): *_vectorstore.go:131-139
+  PrepParams pp{};
+  pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
+  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
+  pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
+  rc = launch_prep_rows(pp, elem, st);
+  if (rc) return rc;
+  if (timed) cudaEventRecord(c.ev[1], st);
+
+  for (size_t q0 = 0; q0 < nq; q0 += qb) {
+    const size_t nqb = std::min(qb, nq - q0);
+    if (nqb != qb) {
+      rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_items, (uint32_t)nqb, k_eff, n_sms, &plan);
+      if (rc) return rc;
+    }
+    ScanParams sp{};
+    sp.rows = d_rows; sp.row_stride = row_stride; sp.dim = dim; sp.n_items = (uint32_t)n_items; sp.subset = d_subset;
+    sp.row_norm2 = d_norm2; sp.ids = d_ids;
+    sp.queries = (const float*)c.q_deq.p + q0 * q_stride; sp.q_norm2 = (const float*)c.q_n2.p + q0; sp.q_stride = q_stride;
+    sp.nq = (uint32_t)nqb; sp.k = k_eff; sp.nearest = nearest; sp.metric = cfg.metric;
+    sp.warp_lists = (Hit*)c.warp_lists.p; sp.cta_lists = (Hit*)c.cta_lists.p; sp.cta_counts = (int*)c.cta_counts.p;
+    rc = launch_flat_scan(sp, plan, elem, st);
+    if (rc) return rc;
+    if (timed && q0 + qb >= nq) cudaEventRecord(c.ev[2], st);
+    MergeParams mp{};
+    mp.lists = (const Hit*)c.cta_lists.p; mp.counts = (const int*)c.cta_counts.p; mp.n_lists = plan.grid_x;
+    mp.nq = (uint32_t)nqb; mp.k_in = k_eff; mp.k = k_eff; mp.nearest = nearest; mp.in_best_first = 1;
+    mp.out = d_out + q0 * (size_t)k; mp.out_counts = d_counts + q0;
+    if (k_eff != (uint32_t)k) {
+      // rows of the public output are k wide; merge into a compact scratch then spread
+      rc = c.tmp_out.ensure(nqb * k_eff * sizeof(Hit)); if (rc) return rc;
+      mp.out = (Hit*)c.tmp_out.p;
+      rc = launch_merge_topk(mp, st); if (rc) return rc;
+      COLTT_CUDA(cudaMemcpy2DAsync(d_out + q0 * (size_t)k, (size_t)k * sizeof(Hit), c.tmp_out.p, (size_t)k_eff * sizeof(Hit),
+                                   (size_t)k_eff * sizeof(Hit), nqb, cudaMemcpyDeviceToDevice, st));
+    } else {
+      rc = launch_merge_topk(mp, st); if (rc) return rc;
+    }
+  }
+  if (timed) cudaEventRecord(c.ev[3], st);
+  (void)math_mode;  // COLTT_MATH_FAST is routed to the tcgen05 filter in gemm_filter.cu once built
+  return COLTT_OK;
+}
+
+int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids, size_t n_cand, bool use_subset, int k,
+                       int select_mode, int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (nq == 0) return COLTT_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return fail(COLTT_ERR_INVALID, "null argument");
+  if (k <= 0) return fail(COLTT_ERR_INVALID, "top-k must be positive");
+  std::shared_lock<std::shared_mutex> lk(mu);
+  COLTT_CUDA(cudaSetDevice(device));
+  auto ctx = acquire_ctx(nullptr);
+  if (!ctx) return fail(COLTT_ERR_CUDA, "could not create a search context");
+  struct Rel { Store* s; std::unique_ptr<SearchCtx>* c; ~Rel() { s->release_ctx(std::move(*c)); } } rel{this, &ctx};
+  SearchCtx& c = *ctx;
+  cudaStream_t st = c.stream;
+  int rc;
+  // candidate ids -> slots (the Go map lookup `if node, ok := vertices[shard][uid]; ok`,
+  // none_vectorstore.go:203); unknown and repeated ids are dropped
+  size_t n_sub = 0;
+  if (use_subset) {
+    std::vector<uint32_t> slots;
+    slots.reserve(n_cand);
+    for (size_t i = 0; i < n_cand; i++) {
+      auto it = id2slot.find(cand_ids[i]);
+      if (it != id2slot.end()) slots.push_back(it->second);
+    }
+    std::sort(slots.begin(), slots.end());
+    slots.erase(std::unique(slots.begin(), slots.end()), slots.end());
+    n_sub = slots.size();
+    rc = c.subset.ensure(std::max<size_t>(n_sub, 1) * 4); if (rc) return rc;
+    if (n_sub) COLTT_CUDA(cudaMemcpyAsync(c.subset.p, slots.data(), n_sub * 4, cudaMemcpyHostToDevice, st));
+    COLTT_CUDA(cudaStreamSynchronize(st));  // `slots` is pageable and goes out of scope
+  }
+  rc = c.q_in.ensure(nq * dim * 4); if (rc) return rc;
+  rc = c.out.ensure(nq * (size_t)k * sizeof(Hit)); if (rc) return rc;
+  rc = c.counts.ensure(nq * 4); if (rc) return rc;
+  rc = c.h_q.ensure(nq * dim * 4); if (rc) return rc;
+  rc = c.h_out.ensure(nq * (size_t)k * sizeof(Hit) + nq * 4); if (rc) return rc;
+  std::memcpy(c.h_q.p, queries, nq * (size_t)dim * 4);
+  COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, c.h_q.p, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+  rc = search_enqueue(c, st, (const float*)c.q_in.p, nq, k, select_mode, math_mode, use_subset ? (const uint32_t*)c.subset.p : nullptr,
+                      n_sub, (Hit*)c.out.p, (int*)c.counts.p, true);
+  if (rc) return rc;
+  Hit* h_hits = (Hit*)c.h_out.p;
+  int* h_counts = (int*)((uint8_t*)c.h_out.p + nq * (size_t)k * sizeof(Hit));
+  COLTT_CUDA(cudaMemcpyAsync(h_counts, c.counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  COLTT_CUDA(cudaMemcpyAsync(h_hits, c.out.p, nq * (size_t)k * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  c.used = true;
+  c.last_stream = st;
+  cudaEventRecord(c.done, st);
+  const bool had_rows = (use_subset ? n_sub : n_rows) != 0;
+  if (had_rows) {
+    c.have_times = true;
+    cudaEventElapsedTime(&c.ms[0], c.ev[0], c.ev[1]);
+    cudaEventElapsedTime(&c.ms[1], c.ev[1], c.ev[2]);
+    c.ms[2] = 0.0f;
+    cudaEventElapsedTime(&c.ms[3], c.ev[2], c.ev[3]);
+  }
+  for (size_t q = 0; q < nq; q++) {
+    const int n = h_counts[q];
+    out_counts[q] = n;
+    for (int i = 0; i < n; i++) {
+      out_ids[q * (size_t)k + i] = h_hits[q * (size_t)k + i].id;
+      out_scores[q * (size_t)k + i] = h_hits[q * (size_t)k + i].score;
+    }
+  }
+  return COLTT_OK;
+}
+
+int Store::search_dev(const void* d_queries, size_t nq, int k, int select_mode, int math_mode, void* d_out, void* d_counts,
+                      void* stream_) {
+  if (nq == 0) return COLTT_OK;
+  if (!d_queries || !d_out || !d_counts) return fail(COLTT_ERR_INVALID, "null argument");
+  std::shared_lock<std::shared_mutex> lk(mu);
+  COLTT_CUDA(cudaSetDevice(device));
+  auto ctx = acquire_ctx((cudaStream_t)stream_);
+  if (!ctx) return fail(COLTT_ERR_CUDA, "could not create a search context");
+  struct Rel { Store* s; std::unique_ptr<SearchCtx>* c; ~Rel() { s->release_ctx(std::move(*c)); } } rel{this, &ctx};
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  // timings of the previous use of this scratch become readable once that work has finished
+  if (ctx->used && n_rows && cudaEventQuery(ctx->ev[3]) == cudaSuccess) {
+    cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
+    ctx->ms[2] = 0.0f;
+    cudaEventElapsedTime(&ctx->ms[3], ctx->ev[2], ctx->ev[3]);
+    ctx->have_times = true;
+  }
+  cudaGetLastError();
+  int rc = search_enqueue(*ctx, st, (const float*)d_queries, nq, k, select_mode, math_mode, nullptr, 0, (Hit*)d_out, (int*)d_counts, true);
+  ctx->used = true;
+  ctx->last_stream = st;
+  cudaEventRecord(ctx->done, st);
+  if (rc) return rc;
+  if (!stream_) {  // own stream: synchronous call
+    COLTT_CUDA(cudaStreamSynchronize(st));
+    if (n_rows) {
+      cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
+      cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
+      ctx->ms[2] = 0.0f;
+      cudaEventElapsedTime(&ctx->ms[3], ctx->ev[2], ctx->ev[3]);
+      ctx->have_times = true;
+    }
+  }
+  return COLTT_OK;
+}
+
+int Store::get_row(uint64_t id, void* out, size_t out_bytes) {
+  std::shared_lock<std::shared_mutex> lk(mu);
+  auto it = id2slot.find(id);
+  if (it == id2slot.end()) return fail(COLTT_ERR_NOT_FOUND, "id not found");
+  const size_t need = (size_t)dim * elem_size(elem);
+  if (!out || out_bytes < need) return fail(COLTT_ERR_INVALID, "output buffer too small");
+  COLTT_CUDA(cudaSetDevice(device));
+  COLTT_CUDA(cudaMemcpy(out, d_rows + (size_t)it->second * row_stride, need, cudaMemcpyDeviceToHost));
+  return COLTT_OK;
+}
+
+}  // namespace coltt
+
+// ================================== C-ABI ==================================================
+using coltt::Store;
+using coltt::fail;
+
+extern "C" {
+
+COLTT_API const char* coltt_b200_last_error(void) { return coltt::last_error_cstr(); }
+COLTT_API const char* coltt_b200_version(void) { return "coltt_b200 0.1 (sm_100a)"; }
+COLTT_API int coltt_b200_device_count(void) { return coltt::sm100_device_count(); }
+
+COLTT_API int coltt_b200_store_create(const coltt_store_cfg* cfg, coltt_store** out) {
+  Store* s = nullptr;
+  int rc = Store::create(cfg, &s);
+  if (rc == COLTT_OK) *out = reinterpret_cast<coltt_store*>(s);
+  return rc;
+}
+COLTT_API void coltt_b200_store_destroy(coltt_store* s) { delete reinterpret_cast<Store*>(s); }
+COLTT_API int coltt_b200_store_size(coltt_store* s, uint64_t* n_rows) {
+  if (!s || !n_rows) return fail(COLTT_ERR_INVALID, "null argument");
+  *n_rows = reinterpret_cast<Store*>(s)->size();
+  return COLTT_OK;
+}
+COLTT_API int coltt_b200_store_dim(coltt_store* s, uint32_t* dim) {
+  if (!s || !dim) return fail(COLTT_ERR_INVALID, "null argument");
+  *dim = reinterpret_cast<Store*>(s)->dim;
+  return COLTT_OK;
+}
+COLTT_API int coltt_b200_store_upsert(coltt_store* s, const uint64_t* ids, const float* vecs, size_t n) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->upsert(ids, vecs, n);
+}
+COLTT_API int coltt_b200_store_remove(coltt_store* s, const uint64_t* ids, size_t n) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->remove(ids, n);
+}
+COLTT_API int coltt_b200_store_search(coltt_store* s, const float* queries, size_t nq, int k, int select_mode, int math_mode,
+                                      uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->search_host(queries, nq, nullptr, 0, false, k, select_mode, math_mode, out_ids, out_scores, out_counts);
+}
+COLTT_API int coltt_b200_store_search_subset(coltt_store* s, const float* queries, size_t nq, const uint64_t* cand_ids,
+                                             size_t n_cand, int k, int select_mode, uint64_t* out_ids, float* out_scores,
+                                             int32_t* out_counts) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  if (n_cand && !cand_ids) return fail(COLTT_ERR_INVALID, "null candidate list");
+  return reinterpret_cast<Store*>(s)->search_host(queries, nq, cand_ids, n_cand, true, k, select_mode, COLTT_MATH_EXACT, out_ids, out_scores, out_counts);
+}
+COLTT_API int coltt_b200_store_search_dev(coltt_store* s, const void* d_queries, size_t nq, int k, int select_mode,
+                                          int math_mode, void* d_out, void* d_counts, void* stream) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->search_dev(d_queries, nq, k, select_mode, math_mode, d_out, d_counts, stream);
+}
+COLTT_API int coltt_b200_merge_topk_dev(int device, const void* d_lists, const void* d_list_counts, int n_lists, size_t nq,
+                                        int k_in, int k, int select_mode, void* d_out, void* d_out_counts, void* stream) {
+  if (!d_lists || !d_list_counts || !d_out || !d_out_counts || n_lists <= 0 || k <= 0 || k_in <= 0) return fail(COLTT_ERR_INVALID, "bad merge arguments");
+  int rc = coltt::require_device(device);
+  if (rc) return rc;
+  COLTT_CUDA(cudaSetDevice(device));
+  coltt::MergeParams mp{};
+  mp.lists = (const coltt::Hit*)d_lists; mp.counts = (const int*)d_list_counts; mp.n_lists = n_lists; mp.nq = (uint32_t)nq;
+  mp.k_in = (uint32_t)k_in; mp.k = (uint32_t)k; mp.nearest = select_mode == COLTT_SELECT_NEAREST; mp.in_best_first = 0;
+  mp.out = (coltt::Hit*)d_out; mp.out_counts = (int*)d_out_counts;
+  rc = coltt::launch_merge_topk(mp, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!stream) COLTT_CUDA(cudaStreamSynchronize(0));
+  return COLTT_OK;
+}
+COLTT_API int coltt_b200_store_export(coltt_store* s, void* buf, size_t* len) {
+  if (!s || !len) return fail(COLTT_ERR_INVALID, "null argument");
+  return reinterpret_cast<Store*>(s)->export_blob(buf, len);
+}
+COLTT_API int coltt_b200_store_import(coltt_store* s, const void* buf, size_t len) {
+  if (!s || (!buf && len)) return fail(COLTT_ERR_INVALID, "null argument");
+  return reinterpret_cast<Store*>(s)->import_blob(buf, len);
+}
+COLTT_API int coltt_b200_store_get_row(coltt_store* s, uint64_t id, void* out, size_t out_bytes) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->get_row(id, out, out_bytes);
+}
+COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n) {
+  if (!s || !ms) return fail(COLTT_ERR_INVALID, "null argument");
+  Store* st = reinterpret_cast<Store*>(s);
+  {
+    // an asynchronous search_dev leaves its events in the pooled scratch: harvest finished ones
+    std::lock_guard<std::mutex> g(st->pool_mu);
+    for (auto& c : st->pool) {
+      if (c->used && cudaEventQuery(c->ev[3]) == cudaSuccess && cudaEventQuery(c->ev[0]) == cudaSuccess) {
+        float a, b, d;
+        if (cudaEventElapsedTime(&a, c->ev[0], c->ev[1]) == cudaSuccess && cudaEventElapsedTime(&b, c->ev[1], c->ev[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&d, c->ev[2], c->ev[3]) == cudaSuccess) {
+          st->last_ms[0] = a; st->last_ms[1] = b; st->last_ms[2] = 0.0f; st->last_ms[3] = d;
+        }
+      }
+    }
+    cudaGetLastError();
+  }
+  for (int i = 0; i < n && i < 4; i++) ms[i] = st->last_ms[i];
+  return COLTT_OK;
+}
+COLTT_API uint64_t coltt_b200_kernel_launches(void) { return coltt::launch_count(); }
+
+}  // extern "C"

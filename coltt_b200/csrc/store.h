@@ -1,0 +1,88 @@
+// store.h — host-side objects behind the C-ABI handles (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace coltt {
+
+const char* last_error_cstr();
+int sm100_device_count();
+int require_device(int device);
+void count_launch(int n = 1);
+uint64_t launch_count();
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  ~DeviceBuf();
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  ~PinnedBuf();
+};
+
+// Per-search scratch: own stream + buffers, so that searches on one handle run concurrently
+// (the reference searches under per-shard RLocks, edge/none_vectorstore.go:137-146).
+struct SearchCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done = nullptr;       // recorded after the last enqueue that used this scratch
+  cudaStream_t last_stream = nullptr;
+  bool used = false, have_times = false;
+  float ms[4] = {0, 0, 0, 0};
+  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, flags;
+  PinnedBuf h_q, h_out;
+  ~SearchCtx();
+};
+
+struct Store {
+  coltt_store_cfg cfg{};
+  int device = 0, elem = 0, n_sms = 148;
+  uint32_t dim = 0, row_stride = 0;
+  size_t n_rows = 0, capacity = 0;
+  uint8_t* d_rows = nullptr;
+  float* d_norm2 = nullptr;
+  uint64_t* d_ids = nullptr;
+  std::vector<uint64_t> h_ids;                     // slot -> id
+  std::unordered_map<uint64_t, uint32_t> id2slot;  // id -> slot
+  std::shared_mutex mu;                            // searches shared, mutations exclusive
+  cudaStream_t stream = nullptr;                   // mutation stream
+  DeviceBuf up_in, up_slots, up_ids;
+  PinnedBuf up_pinned;
+  std::mutex pool_mu;
+  std::vector<std::unique_ptr<SearchCtx>> pool;
+  float last_ms[4] = {0, 0, 0, 0};
+
+  static int create(const coltt_store_cfg* cfg, Store** out);
+  ~Store();
+  uint64_t size() {
+    std::shared_lock<std::shared_mutex> lk(mu);
+    return n_rows;
+  }
+  int reserve(size_t rows);
+  int upsert(const uint64_t* ids, const float* vecs, size_t n);
+  int remove(const uint64_t* ids, size_t n);
+  int search_host(const float* queries, size_t nq, const uint64_t* cand_ids, size_t n_cand, bool use_subset, int k,
+                  int select_mode, int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts);
+  int search_dev(const void* d_queries, size_t nq, int k, int select_mode, int math_mode, void* d_out, void* d_counts,
+                 void* stream);
+  int search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int select_mode,
+                     int math_mode, const uint32_t* d_subset, size_t n_subset, Hit* d_out, int* d_counts, bool timed);
+  int get_row(uint64_t id, void* out, size_t out_bytes);
+  int export_blob(void* buf, size_t* len);
+  int import_blob(const void* buf, size_t len);
+  std::unique_ptr<SearchCtx> acquire_ctx(cudaStream_t user_stream);
+  void release_ctx(std::unique_ptr<SearchCtx> c);
+};
+
+}  // namespace coltt

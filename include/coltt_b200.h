@@ -1,0 +1,182 @@
+/* coltt_b200.h — C-ABI of libcoltt_b200.so: the B200-native ANN search path that drops in
+ * behind coltt's edge Vectorstore/Quantization and core/vectorindex HNSW interfaces.
+ *
+ * The reference (sjy-dv/coltt) is pure Go with no FFI boundary; the seams this library
+ * replaces are Go interfaces.  Each entry point below names the reference method(s) a cgo
+ * shim would forward to it (INTEGRATION.md shows the shim).  Plain pointers and sizes only;
+ * no torch/CUDA types in signatures (device pointers travel as void*).
+ *
+ * Conventions: every function returns COLTT_OK (0) or a negative coltt_status and never
+ * aborts or throws across the boundary; coltt_b200_last_error() returns a thread-local
+ * message for the last failure on the calling thread.  *_search calls on one handle may run
+ * concurrently from many threads (the reference searches under per-shard RLock,
+ * edge/none_vectorstore.go:137-146); upsert/remove/import are serialized per handle
+ * (reference: one shard Lock, none_vectorstore.go:99-101).  Caller-owned buffers are
+ * copied in and never retained (cgo pointer rules).  There is NO CPU fallback: if no
+ * sm_100 device is present every call that needs one fails with COLTT_ERR_NO_DEVICE.
+ */
+#ifndef COLTT_B200_H
+#define COLTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define COLTT_API __attribute__((visibility("default")))
+#else
+#define COLTT_API
+#endif
+
+typedef enum coltt_status {
+  COLTT_OK = 0,
+  COLTT_ERR_INVALID = -1,     /* bad argument */
+  COLTT_ERR_CUDA = -2,        /* CUDA runtime/driver error (message has the detail) */
+  COLTT_ERR_NOMEM = -3,
+  COLTT_ERR_NOT_FOUND = -4,
+  COLTT_ERR_DIM = -5,         /* "Dim Length UnmatchdError" (none_vectorstore.go:86-88) */
+  COLTT_ERR_UNSUPPORTED = -6,
+  COLTT_ERR_FORMAT = -7,      /* malformed SaveVertex / Commit blob */
+  COLTT_ERR_NO_DEVICE = -8    /* no sm_100 GPU: there is no CPU fallback */
+} coltt_status;
+
+/* edgepb.Distance (idl/proto/v4/edge.proto:69-72) */
+typedef enum coltt_metric { COLTT_COSINE = 0, COLTT_EUCLIDEAN = 1 } coltt_metric;
+
+/* edgepb.Quantization (edge.proto:75-80).  BF16 is stored and decoded as IEEE binary16
+ * because the reference's "bf16" codec is (pkg/compresshelper/bf16.go:233-317).
+ * F8 is the reference's literal (broken) 8-bit code (float8.go:233-313).
+ * F8_E4M3 is a builder extension (real fp8 rows, per-row scale) with no reference parity. */
+typedef enum coltt_quant {
+  COLTT_QUANT_NONE = 0,
+  COLTT_QUANT_F16 = 1,
+  COLTT_QUANT_F8 = 2,
+  COLTT_QUANT_BF16 = 3,
+  COLTT_QUANT_F8_E4M3 = 16
+} coltt_quant;
+
+/* Which K rows a FLAT search keeps.
+ * COLTT_SELECT_COMPAT: the reference's literal behaviour — edge.PriorityQueue over a MIN heap
+ *   pops the minimum distance when over capacity, i.e. keeps the K LARGEST distances, returned
+ *   ascending (edge/priority_queue.go:39-69).
+ * COLTT_SELECT_NEAREST: keeps the K smallest distances, ascending (what HNSW and users expect).
+ * Equal scores: lower id wins and sorts first (the reference is nondeterministic here, F6). */
+typedef enum coltt_select { COLTT_SELECT_COMPAT = 0, COLTT_SELECT_NEAREST = 1 } coltt_select;
+
+/* COLTT_MATH_EXACT: CUDA-core kernel that reproduces the reference AVX evaluation order
+ *   (pkg/distance/simd/cpp/avx.cpp:3-8,15-32,51-75) — scores bit-identical to the Go path.
+ * COLTT_MATH_FAST: tcgen05 tensor-core filter over the whole shard, then the survivors are
+ *   re-scored by the EXACT arithmetic; a certified margin makes the returned ids/scores equal
+ *   to EXACT, and queries whose margin cannot be certified are re-run EXACT automatically. */
+typedef enum coltt_math { COLTT_MATH_EXACT = 0, COLTT_MATH_FAST = 1 } coltt_math;
+
+typedef struct coltt_store coltt_store; /* one edge collection's vectors on one GPU */
+typedef struct coltt_hnsw coltt_hnsw;   /* one core/vectorindex.Hnsw on one GPU */
+
+typedef struct coltt_store_cfg {
+  uint32_t dim;            /* Collection.dim (edge.proto:34) */
+  int32_t metric;          /* coltt_metric */
+  int32_t quant;           /* coltt_quant */
+  int32_t device;          /* CUDA device ordinal */
+  uint64_t capacity_hint;  /* rows to reserve up front (0 = grow on demand) */
+} coltt_store_cfg;
+
+/* ---- library ------------------------------------------------------------------------- */
+COLTT_API const char* coltt_b200_last_error(void);
+COLTT_API const char* coltt_b200_version(void);
+/* Number of visible sm_100 devices (0 when none; never an error). */
+COLTT_API int coltt_b200_device_count(void);
+
+/* ---- edge FLAT store: replaces the `vectorspace` implementations ------------------------
+ * newNoneVectorstore / newF16Vectorstore / newBF16Vectorstore / newF8Vectorstore
+ * (edge/vectorstore.go:62-85). */
+COLTT_API int coltt_b200_store_create(const coltt_store_cfg* cfg, coltt_store** out);
+COLTT_API void coltt_b200_store_destroy(coltt_store* s);
+/* vectorspace.LoadSize / Dim (edge/vectorstore.go:44-46) */
+COLTT_API int coltt_b200_store_size(coltt_store* s, uint64_t* n_rows);
+COLTT_API int coltt_b200_store_dim(coltt_store* s, uint32_t* dim);
+
+/* vectorspace.ChangedVertex (edge/none_vectorstore.go:66-103, bf16_vectorstore.go:66-106):
+ * n rows of `dim` un-normalized fp32; normalized (cosine) and Lower()ed on the GPU with the
+ * reference's arithmetic; an existing id is overwritten in place.  Metadata / inverted index
+ * stay on the Go side.  `vecs` is a host pointer. */
+COLTT_API int coltt_b200_store_upsert(coltt_store* s, const uint64_t* ids, const float* vecs, size_t n);
+/* vectorspace.RemoveVertex after the Go side resolved dropFilter to ids
+ * (none_vectorstore.go:105-127).  Unknown ids are ignored like the Go `delete`. */
+COLTT_API int coltt_b200_store_remove(coltt_store* s, const uint64_t* ids, size_t n);
+
+/* vectorspace.VertexSearch (edge/none_vectorstore.go:129-180 and the bf16/f16/f8 twins),
+ * batched: nq un-normalized fp32 queries (host), top-k each.  The reference call is nq = 1;
+ * `highCpu` has no meaning on the GPU.  Outputs (host, caller-allocated): out_ids and
+ * out_scores are [nq][k], rows filled to out_counts[q] = min(k, rows), ascending score. */
+COLTT_API int coltt_b200_store_search(coltt_store* s, const float* queries, size_t nq, int k, int select_mode,
+                                      int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts);
+
+/* vectorspace.FilterableVertexSearch (edge/none_vectorstore.go:182-253) given the candidate
+ * ids that inverted.SearchWithExpression produced (pkg/inverted/search.go:113-119): the same
+ * scan behind a gather front-end.  Ids not present are skipped like the Go map lookup. */
+COLTT_API int coltt_b200_store_search_subset(coltt_store* s, const float* queries, size_t nq, const uint64_t* cand_ids,
+                                             size_t n_cand, int k, int select_mode, uint64_t* out_ids,
+                                             float* out_scores, int32_t* out_counts);
+
+/* Device-resident variant for pipelines that keep queries and results on the GPU (multi-GPU
+ * merge, benchmarks).  d_queries: device fp32 [nq][dim]; d_out: device coltt_hit [nq][k];
+ * d_counts: device int32 [nq].  `stream` is a cudaStream_t (NULL = the store's own stream;
+ * then the call returns after the work completed).  With a caller stream the call only
+ * enqueues. */
+typedef struct coltt_hit {
+  uint64_t id;
+  float score;
+  uint32_t slot; /* row slot inside this store (diagnostic; ignore across stores) */
+} coltt_hit;
+COLTT_API int coltt_b200_store_search_dev(coltt_store* s, const void* d_queries, size_t nq, int k, int select_mode,
+                                          int math_mode, void* d_out, void* d_counts, void* stream);
+
+/* The exchange step of a sharded search (reference analogue: merging the 16 shard-local
+ * queues, none_vectorstore.go:173-178): merges n_lists best-first lists of `k_in` hits per
+ * query — d_lists is device coltt_hit [n_lists][nq][k_in] with d_list_counts int32
+ * [n_lists][nq] — into device [nq][k] ascending, d_out_counts int32 [nq]. */
+COLTT_API int coltt_b200_merge_topk_dev(int device, const void* d_lists, const void* d_list_counts, int n_lists,
+                                        size_t nq, int k_in, int k, int select_mode, void* d_out, void* d_out_counts,
+                                        void* stream);
+
+/* vectorspace.SaveVertex / LoadVertex (edge/none_vectorstore.go:308-516; element widths
+ * f16_vectorstore.go:338-343, f8_vectorstore.go:340): the reference's big-endian vertex blob.
+ * Export writes metaCount = 0 for every vertex (metadata lives on the Go side); import skips
+ * metadata records.  export: pass buf = NULL to query the size in *len. */
+COLTT_API int coltt_b200_store_export(coltt_store* s, void* buf, size_t* len);
+COLTT_API int coltt_b200_store_import(coltt_store* s, const void* buf, size_t len);
+
+/* Stored (normalized + lowered) row for an id, as the reference keeps it in ENode.Vector:
+ * dim elements of 4/2/1 bytes.  For tests and for Hnsw-style Get(). */
+COLTT_API int coltt_b200_store_get_row(coltt_store* s, uint64_t id, void* out, size_t out_bytes);
+
+/* ---- core/vectorindex HNSW ------------------------------------------------------------
+ * Hnsw.Load (core/vectorindex/hnsw_commit.go:164-278): parses a Commit(header=true) blob
+ * into a device-resident CSR graph + row matrix. */
+COLTT_API int coltt_b200_hnsw_load(const void* commit_blob, size_t len, int device, coltt_hnsw** out);
+COLTT_API void coltt_b200_hnsw_destroy(coltt_hnsw* h);
+COLTT_API int coltt_b200_hnsw_len(coltt_hnsw* h, uint64_t* n);
+/* Hnsw.Search (hnsw.go:243-278), batched: normalize, greedy descent (hnsw.go:320-343),
+ * searchLevel with ef = max(ef, k) (hnsw.go:345-389), trim to k, ascending.  ef <= 0 uses the
+ * ef stored in the blob (hnsw_config.go:138).  Neighbour order = ascending id. */
+COLTT_API int coltt_b200_hnsw_search(coltt_hnsw* h, const float* queries, size_t nq, int k, int ef, uint64_t* out_ids,
+                                     float* out_scores, int32_t* out_counts);
+/* Counters of the last search call: distance evaluations and expansions (for the roofline). */
+COLTT_API int coltt_b200_hnsw_last_stats(coltt_hnsw* h, uint64_t* dist_evals, uint64_t* expansions);
+
+/* ---- timing (replaces pprof for this path) ---------------------------------
+ * Device time in milliseconds of the kernels of the last search on this handle, measured
+ * with CUDA events on the stream they ran on: [0] query prep, [1] scan/GEMM, [2] rerank,
+ * [3] merge.  n = number of floats the caller provides. */
+COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n);
+/* Kernels this library has launched in this process so far (bench.py's gpu_launches). */
+COLTT_API uint64_t coltt_b200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLTT_B200_H */

@@ -560,8 +560,7 @@ ORC_API int orc_store_search_subset(OrcStore* s, const float* query, const uint6
   return emit(pq.to_slice(), out_ids, out_scores);
 }
 
-// Total-order selector (builder-defined tie rule: equal scores -> lower id wins, output
-// ascending score then ascending id).  Scores are computed exactly as above; only the
+// Total-order selector (builder-defined tie rule: a window of the (score,id)-sorted order).  Scores are computed exactly as above; only the
 // selection is order-independent.  This is what the CUDA path implements; on tie-free
 // inputs it equals orc_store_search (tests assert that).
 ORC_API int orc_store_search_total_order(OrcStore* s, const float* query, const uint64_t* cand, size_t n_cand,
@@ -592,26 +591,20 @@ ORC_API int orc_store_search_total_order(OrcStore* s, const float* query, const 
     for (auto& t : th) t.join();
     for (auto& p : part) all.insert(all.end(), p.begin(), p.end());
   }
+  // Total order T: ascending score, NaN after every number, then ascending id.
+  // NEAREST = the first K of T; COLTT_COMPAT = the last K of T (the K largest distances,
+  // SURVEY F1; among equal scores the higher ids stay, the exact mirror image); output in T order.
   auto isnan_ = [](float f) { return f != f; };
-  // "better" order: NaN is worst in both modes.
-  auto better = [&](const HeapItem& a, const HeapItem& b) {
+  auto t_less = [&](const HeapItem& a, const HeapItem& b) {
     bool an = isnan_(a.priority), bn = isnan_(b.priority);
     if (an != bn) return bn;
-    if (!an) {
-      if (select_mode == 1) { if (a.priority < b.priority) return true; if (b.priority < a.priority) return false; }
-      else { if (a.priority > b.priority) return true; if (b.priority > a.priority) return false; }
-    }
-    return a.id < b.id;
-  };
-  size_t k = std::min((size_t)top_k, all.size());
-  std::partial_sort(all.begin(), all.begin() + k, all.end(), better);
-  all.resize(k);
-  std::sort(all.begin(), all.end(), [&](const HeapItem& a, const HeapItem& b) {
-    bool an = isnan_(a.priority), bn = isnan_(b.priority);
-    if (an != bn) return bn;  // NaN last
     if (!an) { if (a.priority < b.priority) return true; if (b.priority < a.priority) return false; }
     return a.id < b.id;
-  });
+  };
+  std::sort(all.begin(), all.end(), t_less);
+  size_t k = std::min((size_t)top_k, all.size());
+  if (select_mode == 1) all.resize(k);
+  else all.erase(all.begin(), all.end() - k);
   return emit(all, out_ids, out_scores);
 }
 
