@@ -23,6 +23,7 @@
 //
 // Algorithmic bytes per launch:  n_items*dim*elem + n_items*4 (norms)
 //   + nq*dim*4 (queries) + grid*nq*k*16 (lists) — one HBM pass over the shard per QT queries.
+#include "exact_math.cuh"
 #include "kernels.cuh"
 #include "store.h"
 #include "topk.cuh"
@@ -32,28 +33,6 @@ namespace coltt {
 static constexpr int kScanWarps = 8;
 static constexpr int kRowsPerWarp = 16;
 static constexpr uint32_t kRowPad = 16;
-
-template <int ELEM>
-__device__ __forceinline__ void load4(const uint8_t* p, const float* lut, float (&v)[4]) {
-  if (ELEM == ELEM_F32) {
-    float4 f = *reinterpret_cast<const float4*>(p);
-    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-  } else if (ELEM == ELEM_F16) {
-    uint2 raw = *reinterpret_cast<const uint2*>(p);
-    float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-  } else {
-    uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
-    v[0] = lut[raw & 0xff]; v[1] = lut[(raw >> 8) & 0xff]; v[2] = lut[(raw >> 16) & 0xff]; v[3] = lut[raw >> 24];
-  }
-}
-template <int ELEM>
-__device__ __forceinline__ float load1(const uint8_t* row, uint32_t idx, const float* lut) {
-  if (ELEM == ELEM_F32) return reinterpret_cast<const float*>(row)[idx];
-  if (ELEM == ELEM_F16) return __half2float(reinterpret_cast<const __half*>(row)[idx]);
-  return lut[row[idx]];
-}
 
 template <int ELEM, int METRIC, int QT>
 __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParams p) {

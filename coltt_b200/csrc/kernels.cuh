@@ -61,6 +61,48 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
                    ScanPlan* plan);
 int launch_flat_scan(const ScanParams& p, const ScanPlan& plan, int elem, cudaStream_t stream);
 
+// ---- gemm_filter.cu (K2) + rerank.cu ------------------------------------------------------
+struct GemmCand {
+  float key;      // "larger is better" approximate score (see gemm_filter.cu)
+  uint32_t row;   // row slot
+};
+struct GemmParams {
+  uint32_t n_rows, dim, nq;
+  const __half* q_f16;       // [nq][q_stride] lowered queries, zero padded to kblocks*64
+  uint32_t q_stride;
+  const float* row_norm2;    // [n_rows]
+  int metric, nearest;
+  uint32_t* g_thr;           // [nq] order-encoded shared thresholds, zero-initialised
+  GemmCand* cand_out;        // [nq][grid_x][cand_cap]
+  uint32_t* cand_cnt;        // [nq][grid_x]
+  uint32_t kblocks, kprime, cand_cap, n_stages;  // filled from the plan
+  float* dbg_acc;            // nullable (tests): raw accumulators [nq][n_rows]
+};
+struct GemmPlan {
+  uint32_t kblocks, kprime, cand_cap, n_stages, grid_x, grid_y, q_stride;
+  size_t smem_bytes;
+};
+int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
+int launch_gemm_filter(const GemmParams& p, const GemmPlan& plan, const void* d_rows, uint32_t row_stride, cudaStream_t stream);
+
+struct RerankParams {
+  uint32_t nq, k, dim, q_stride, row_stride, grid_x, cand_cap;
+  int metric, nearest, elem;
+  const float* queries;      // [nq][q_stride] dequantized fp32 (exact path operand)
+  const float* q_norm2;      // [nq]
+  const uint8_t* rows;
+  const float* row_norm2;
+  const uint64_t* ids;
+  const GemmCand* cand_in;   // [nq][grid_x][cand_cap]
+  const uint32_t* cand_cnt;  // [nq][grid_x]
+  const uint32_t* g_thr;     // [nq]
+  Hit* out;                  // [nq][k_out_stride] in T order
+  uint32_t out_stride;
+  int* out_counts;           // [nq]
+  uint32_t* flags;           // [nq] 1 = margin not certified: the caller re-runs that query EXACT
+};
+int launch_rerank(const RerankParams& p, cudaStream_t stream);
+
 // ---- topk_merge.cu (K5) -----------------------------------------------------------------
 struct MergeParams {
   const Hit* lists;          // [n_lists][nq][k_in]

@@ -1,0 +1,168 @@
+// rerank.cu — exact re-scoring of the tcgen05 filter's survivors + margin certificate.
+//
+// Second half of COLTT_MATH_FAST.  For one query per CTA: gather the candidates every filter CTA
+// kept (gemm_filter.cu), drop those below the final shared threshold, re-score the rest with
+// the EXACT arithmetic of flat_scan.cu (the reference's AVX evaluation order,
+// pkg/distance/simd/cpp/avx.cpp:51-75 -> simd/avx/AVX_amd64.go:44-52 -> space.go:93-95), select
+// the top K in T order and certify that no row the filter dropped can beat the K-th:
+//   every dropped row has approximate key <= B (the final threshold), the approximate and exact
+//   scores differ by at most eps (fp32 accumulation-order error over exact fp16 x fp16 products),
+//   so the answer is provably the EXACT answer when the exact K-th score clears B by eps.
+// Queries that cannot be certified (heavy ties at the threshold) are flagged and re-run on the
+// exact path by the caller.  Traffic: ~2K rows of dim*2 bytes per query — negligible next to the scan.
+#include "exact_math.cuh"
+#include "store.h"
+#include "topk.cuh"
+
+namespace coltt {
+
+static constexpr int kRerankThreads = 128;
+static constexpr uint32_t kRerankMaxCand = 1024;
+
+__host__ __device__ __forceinline__ float ord2f_(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ uint32_t n_s;
+  float* q_s = reinterpret_cast<float*>(smem);                     // [q_stride]
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(q_s + p.q_stride); // [kRerankMaxCand]
+  float* score_s = reinterpret_cast<float*>(row_s + kRerankMaxCand);
+  uint64_t* id_s = reinterpret_cast<uint64_t*>(score_s + kRerankMaxCand);
+  const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
+
+  if (tid == 0) n_s = 0;
+  for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
+  __syncthreads();
+
+  // ---- 1. gather the survivors of every filter CTA that clear the final threshold
+  const uint32_t thr_bits = p.g_thr[q];
+  const bool have_bound = thr_bits != 0;
+  const float B = have_bound ? ord2f_(thr_bits) : 0.0f;
+  for (uint32_t i = tid; i < p.grid_x * p.cand_cap; i += blockDim.x) {
+    const uint32_t cta = i / p.cand_cap, s = i - cta * p.cand_cap;
+    if (s < p.cand_cnt[(size_t)q * p.grid_x + cta]) {
+      const GemmCand c = p.cand_in[((size_t)q * p.grid_x + cta) * p.cand_cap + s];
+      if (!have_bound || c.key >= B || c.key != c.key) {
+        const uint32_t pos = atomicAdd(&n_s, 1u);
+        if (pos < kRerankMaxCand) row_s[pos] = c.row;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n_all = n_s;
+  const uint32_t n = n_all < kRerankMaxCand ? n_all : kRerankMaxCand;
+
+  // ---- 2. exact re-score: 16 candidates per warp pass, two lanes per row, 4 chains per lane
+  const uint32_t r = lane_row16(lane), g = lane_half(lane);
+  const uint32_t full8 = (p.dim / 8) * 8;
+  const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
+  for (uint32_t base = warp * 16; base < n; base += (blockDim.x >> 5) * 16) {
+    const uint32_t j = base + r;
+    const bool valid = j < n;
+    const uint32_t row = valid ? row_s[j] : row_s[0];
+    const uint8_t* rowp = p.rows + (size_t)row * p.row_stride;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t e = 0; e < full8; e += 8) {
+      float rv[4];
+      load4<ELEM>(rowp + (size_t)(e + 4 * g) * ES, nullptr, rv);
+      const float4 qv = *reinterpret_cast<const float4*>(q_s + e + 4 * g);
+      if (METRIC == COLTT_COSINE) {
+        acc[0] = add_rn(acc[0], mul_rn(qv.x, rv[0])); acc[1] = add_rn(acc[1], mul_rn(qv.y, rv[1]));
+        acc[2] = add_rn(acc[2], mul_rn(qv.z, rv[2])); acc[3] = add_rn(acc[3], mul_rn(qv.w, rv[3]));
+      } else {
+        float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
+        acc[0] = add_rn(acc[0], mul_rn(d0, d0)); acc[1] = add_rn(acc[1], mul_rn(d1, d1));
+        acc[2] = add_rn(acc[2], mul_rn(d2, d2)); acc[3] = add_rn(acc[3], mul_rn(d3, d3));
+      }
+    }
+    float h = add_rn(add_rn(acc[0], acc[1]), add_rn(acc[2], acc[3]));
+    float o = __shfl_xor_sync(0xffffffffu, h, 8);
+    float tot = g == 0 ? add_rn(h, o) : add_rn(o, h);
+    for (uint32_t d = full8; d < p.dim; d++) {
+      float rv = load1<ELEM>(rowp, d, nullptr);
+      float qv = q_s[d];
+      if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
+      else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
+    }
+    if (valid && g == 0) {
+      score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[row]) : sqrt_via_f64(tot);
+      id_s[j] = p.ids[row];
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. top-K of the exact scores, straight into T order
+  const uint32_t n_out = n < p.k ? n : p.k;
+  Hit* out = p.out + (size_t)q * p.out_stride;
+  __shared__ float kth_s;
+  if (tid == 0) kth_s = 0.0f;
+  __syncthreads();
+  for (uint32_t e = tid; e < n; e += blockDim.x) {
+    const float sc = score_s[e];
+    const uint64_t id = id_s[e];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) rank += better(score_s[j], id_s[j], sc, id, p.nearest) ? 1u : 0u;
+    if (rank < n_out) {
+      Hit hh; hh.id = id; hh.score = sc; hh.slot = row_s[e];
+      out[p.nearest ? rank : n_out - 1 - rank] = hh;
+      if (rank == n_out - 1) kth_s = sc;
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. certificate
+  if (tid == 0) {
+    p.out_counts[q] = (int)n_out;
+    bool ok = n_all <= kRerankMaxCand;
+    if (ok && have_bound) {
+      const float dK = kth_s;  // exact score (a distance) of the worst row we return
+      if (!(dK == dK)) {
+        ok = !p.nearest;       // NaN is the best COMPAT score and the worst NEAREST one
+      } else if (METRIC == COLTT_COSINE) {
+        const float invq = rsqrtf(qn);
+        const float eps = 1.5e-4f;
+        // key = +-dot/||row||; exact sim within eps of key*invq; distance = |1 - sim|
+        if (p.nearest) ok = dK < 1.0f - B * invq - eps;         // dropped rows: distance >= 1 - B*invq - eps
+        else ok = dK > 1.0f + B * invq + eps;                   // dropped rows: distance <= 1 + B*invq + eps
+      } else {
+        const float nq2 = p.q_norm2[q];
+        const float d2 = dK * dK;
+        const float scale = nq2 + (sqrtf(nq2) + dK) * (sqrtf(nq2) + dK);
+        const float eps = 2.0e-4f * scale;
+        if (p.nearest) ok = d2 < nq2 - B - eps;                 // key = 2dot - ||row||^2  =>  d^2 = ||q||^2 - key
+        else ok = d2 > nq2 + B + eps;                           // key = ||row||^2 - 2dot  =>  d^2 = ||q||^2 + key
+      }
+      if (n_out < p.k) ok = false;  // the filter keeps K' >= K rows once it has a bound: fewer means trouble
+    }
+    p.flags[q] = ok ? 0u : 1u;
+  }
+}
+
+int launch_rerank(const RerankParams& p, cudaStream_t stream) {
+  if (p.nq == 0) return COLTT_OK;
+  const size_t smem = (size_t)p.q_stride * 4 + (size_t)kRerankMaxCand * (4 + 4 + 8);
+  const bool cosine = p.metric == COLTT_COSINE;
+#define COLTT_RR(E, M)                                                                                    \
+  {                                                                                                       \
+    COLTT_CUDA(cudaFuncSetAttribute(rerank_kernel<E, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rerank_kernel<E, M><<<p.nq, kRerankThreads, smem, stream>>>(p);                                        \
+  }
+  if (p.elem == ELEM_F16) { if (cosine) COLTT_RR(ELEM_F16, COLTT_COSINE) else COLTT_RR(ELEM_F16, COLTT_EUCLIDEAN) }
+  else if (p.elem == ELEM_F32) { if (cosine) COLTT_RR(ELEM_F32, COLTT_COSINE) else COLTT_RR(ELEM_F32, COLTT_EUCLIDEAN) }
+  else return fail(COLTT_ERR_UNSUPPORTED, "rerank: element type");
+#undef COLTT_RR
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  return COLTT_OK;
+}
+
+}  // namespace coltt

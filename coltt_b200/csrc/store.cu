@@ -100,6 +100,7 @@ PinnedBuf::~PinnedBuf() {
   if (p) cudaFreeHost(p);
 }
 
+thread_local bool Store::in_fallback = false;
 static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -324,6 +325,12 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
     if (timed) for (auto& e : c.ev) cudaEventRecord(e, st);
     return COLTT_OK;
   }
+  if (math_mode == COLTT_MATH_FAST && !d_subset && !in_fallback) {
+    bool used = false;
+    rc = fast_enqueue(c, st, d_queries, nq, k, nearest, d_out, d_counts, timed, nullptr, &used);
+    if (rc) return rc;
+    if (used) return COLTT_OK;   // otherwise the shape is not served by the tensor-core filter: exact path below
+  }
   const uint32_t k_eff = (uint32_t)std::min<size_t>((size_t)k, n_items);  // lists never hold more than n_items
   // query batches bounded by list scratch
   ScanPlan plan;
@@ -382,7 +389,78 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
     }
   }
   if (timed) cudaEventRecord(c.ev[3], st);
-  (void)math_mode;  // COLTT_MATH_FAST is routed to the tcgen05 filter in gemm_filter.cu once built
+  return COLTT_OK;
+}
+
+// COLTT_MATH_FAST: tcgen05 filter (gemm_filter.cu) -> exact re-rank + certificate (rerank.cu) ->
+// exact re-run of the (rare) queries whose margin could not be certified.
+int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int nearest, Hit* d_out,
+                        int* d_counts, bool timed, float* dbg_acc, bool* used_fast) {
+  *used_fast = false;
+  if (elem != ELEM_F16 || n_rows < 4096 || (size_t)k > n_rows) return COLTT_OK;
+  GemmPlan gp;
+  if (plan_gemm_filter(dim, (uint32_t)nq, (uint32_t)k, n_sms, &gp) != COLTT_OK) return COLTT_OK;  // unsupported shape -> exact
+  const uint32_t q_stride = (dim + 7) / 8 * 8;
+  int rc;
+  rc = c.q_deq.ensure(nq * q_stride * 4); if (rc) return rc;
+  rc = c.q_n2.ensure(nq * 4); if (rc) return rc;
+  rc = c.q_f16.ensure(nq * (size_t)gp.q_stride * 2); if (rc) return rc;
+  rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
+  rc = c.cand.ensure(nq * (size_t)gp.grid_x * gp.cand_cap * sizeof(GemmCand)); if (rc) return rc;
+  rc = c.cand_cnt.ensure(nq * (size_t)gp.grid_x * 4); if (rc) return rc;
+  rc = c.flags.ensure(nq * 4); if (rc) return rc;
+  rc = c.h_flags.ensure(nq * 4); if (rc) return rc;
+  if (timed) cudaEventRecord(c.ev[0], st);
+  PrepParams pp{};
+  pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
+  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
+  pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
+  pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride;
+  rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
+  COLTT_CUDA(cudaMemsetAsync(c.g_thr.p, 0, nq * 4, st));
+  COLTT_CUDA(cudaMemsetAsync(c.cand_cnt.p, 0, nq * (size_t)gp.grid_x * 4, st));
+  if (timed) cudaEventRecord(c.ev[1], st);
+  GemmParams g{};
+  g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
+  g.row_norm2 = d_norm2; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
+  g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc;
+  rc = launch_gemm_filter(g, gp, d_rows, row_stride, st); if (rc) return rc;
+  if (timed) cudaEventRecord(c.ev[2], st);
+  RerankParams r{};
+  r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
+  const uint32_t n_tiles = ((uint32_t)n_rows + 63) / 64;
+  r.grid_x = gp.grid_x < n_tiles ? gp.grid_x : n_tiles; r.cand_cap = gp.cand_cap;
+  r.metric = cfg.metric; r.nearest = nearest; r.elem = elem;
+  r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.rows = d_rows; r.row_norm2 = d_norm2; r.ids = d_ids;
+  r.cand_in = (const GemmCand*)c.cand.p; r.cand_cnt = (const uint32_t*)c.cand_cnt.p; r.g_thr = (const uint32_t*)c.g_thr.p;
+  r.out = d_out; r.out_stride = (uint32_t)k; r.out_counts = d_counts; r.flags = (uint32_t*)c.flags.p;
+  rc = launch_rerank(r, st); if (rc) return rc;
+  if (timed) cudaEventRecord(c.ev[3], st);
+  *used_fast = true;
+  fast_queries += nq;
+  // certificate check: queries that could not be certified are re-run on the exact path
+  COLTT_CUDA(cudaMemcpyAsync(c.h_flags.p, c.flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  const uint32_t* hf = (const uint32_t*)c.h_flags.p;
+  std::vector<uint32_t> bad;
+  for (size_t q = 0; q < nq; q++) if (hf[q]) bad.push_back((uint32_t)q);
+  if (bad.empty()) return COLTT_OK;
+  fast_fallbacks += bad.size();
+  rc = c.fb_q.ensure(bad.size() * dim * 4); if (rc) return rc;
+  rc = c.fb_out.ensure(bad.size() * (size_t)k * sizeof(Hit)); if (rc) return rc;
+  rc = c.fb_cnt.ensure(bad.size() * 4); if (rc) return rc;
+  for (size_t i = 0; i < bad.size(); i++)
+    COLTT_CUDA(cudaMemcpyAsync((float*)c.fb_q.p + i * dim, d_queries + (size_t)bad[i] * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, st));
+  in_fallback = true;
+  rc = search_enqueue(c, st, (const float*)c.fb_q.p, bad.size(), k, nearest ? COLTT_SELECT_NEAREST : COLTT_SELECT_COMPAT, COLTT_MATH_EXACT,
+                      nullptr, 0, (Hit*)c.fb_out.p, (int*)c.fb_cnt.p, false);
+  in_fallback = false;
+  if (rc) return rc;
+  for (size_t i = 0; i < bad.size(); i++) {
+    COLTT_CUDA(cudaMemcpyAsync(d_out + (size_t)bad[i] * k, (Hit*)c.fb_out.p + i * (size_t)k, (size_t)k * sizeof(Hit), cudaMemcpyDeviceToDevice, st));
+    COLTT_CUDA(cudaMemcpyAsync(d_counts + bad[i], (int*)c.fb_cnt.p + i, 4, cudaMemcpyDeviceToDevice, st));
+  }
   return COLTT_OK;
 }
 
@@ -603,5 +681,44 @@ COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n) {
   return COLTT_OK;
 }
 COLTT_API uint64_t coltt_b200_kernel_launches(void) { return coltt::launch_count(); }
+
+// ---- test/diagnostic hooks (not part of include/coltt_b200.h) --------------------------------
+// Raw tcgen05 accumulators of the FAST filter for host queries: out_acc is a host [nq][n_rows] fp32.
+COLTT_API int coltt_b200_debug_fast_scores(coltt_store* s_, const float* queries, size_t nq, int k, int select_mode, float* out_acc,
+                                           uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  Store* s = reinterpret_cast<Store*>(s_);
+  if (!s || !queries || !out_acc) return fail(COLTT_ERR_INVALID, "null argument");
+  std::shared_lock<std::shared_mutex> lk(s->mu);
+  COLTT_CUDA(cudaSetDevice(s->device));
+  auto ctx = s->acquire_ctx(nullptr);
+  if (!ctx) return fail(COLTT_ERR_CUDA, "ctx");
+  struct Rel { Store* s; std::unique_ptr<coltt::SearchCtx>* c; ~Rel() { s->release_ctx(std::move(*c)); } } rel{s, &ctx};
+  coltt::DeviceBuf dq, dacc, dout, dcnt;
+  int rc;
+  if ((rc = dq.ensure(nq * s->dim * 4)) || (rc = dacc.ensure(nq * s->n_rows * 4)) || (rc = dout.ensure(nq * (size_t)k * 16)) || (rc = dcnt.ensure(nq * 4))) return rc;
+  COLTT_CUDA(cudaMemcpy(dq.p, queries, nq * s->dim * 4, cudaMemcpyHostToDevice));
+  COLTT_CUDA(cudaMemset(dacc.p, 0xff, nq * s->n_rows * 4));
+  bool used = false;
+  rc = s->fast_enqueue(*ctx, ctx->stream, (const float*)dq.p, nq, k, select_mode == COLTT_SELECT_NEAREST, (coltt::Hit*)dout.p, (int*)dcnt.p, false,
+                       (float*)dacc.p, &used);
+  if (rc) return rc;
+  if (!used) return fail(COLTT_ERR_UNSUPPORTED, "shape not served by the FAST path");
+  COLTT_CUDA(cudaStreamSynchronize(ctx->stream));
+  COLTT_CUDA(cudaMemcpy(out_acc, dacc.p, nq * s->n_rows * 4, cudaMemcpyDeviceToHost));
+  if (out_ids && out_scores && out_counts) {
+    std::vector<coltt::Hit> h(nq * (size_t)k);
+    COLTT_CUDA(cudaMemcpy(h.data(), dout.p, h.size() * 16, cudaMemcpyDeviceToHost));
+    COLTT_CUDA(cudaMemcpy(out_counts, dcnt.p, nq * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); i++) { out_ids[i] = h[i].id; out_scores[i] = h[i].score; }
+  }
+  return COLTT_OK;
+}
+// [0] queries served by the FAST path, [1] of those re-run exactly because the margin was not certified
+COLTT_API int coltt_b200_store_fast_stats(coltt_store* s, uint64_t* out2) {
+  if (!s || !out2) return fail(COLTT_ERR_INVALID, "null argument");
+  out2[0] = reinterpret_cast<Store*>(s)->fast_queries;
+  out2[1] = reinterpret_cast<Store*>(s)->fast_fallbacks;
+  return COLTT_OK;
+}
 
 }  // extern "C"

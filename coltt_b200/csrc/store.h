@@ -40,7 +40,8 @@ struct SearchCtx {
   cudaStream_t last_stream = nullptr;
   bool used = false, have_times = false;
   float ms[4] = {0, 0, 0, 0};
-  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, flags;
+  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt;
+  PinnedBuf h_flags;
   PinnedBuf h_q, h_out;
   ~SearchCtx();
 };
@@ -79,6 +80,10 @@ struct Store {
   int search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int select_mode,
                      int math_mode, const uint32_t* d_subset, size_t n_subset, Hit* d_out, int* d_counts, bool timed);
   int get_row(uint64_t id, void* out, size_t out_bytes);
+  int fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int nearest, Hit* d_out,
+                   int* d_counts, bool timed, float* dbg_acc, bool* used_fast);
+  uint64_t fast_fallbacks = 0, fast_queries = 0;
+  static thread_local bool in_fallback;
   int export_blob(void* buf, size_t* len);
   int import_blob(const void* buf, size_t len);
   std::unique_ptr<SearchCtx> acquire_ctx(cudaStream_t user_stream);

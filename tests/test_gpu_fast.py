@@ -1,0 +1,123 @@
+"""COLTT_MATH_FAST (tcgen05 filter + exact re-rank + certificate) must return exactly what
+COLTT_MATH_EXACT returns — ids and fp32 score bits — and its raw tensor-core accumulators must
+match an fp64 reference of the same fp16 x fp16 products (tolerance stated below)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import QUERY_SEED, assert_same_hits, normal, rng, sparse_ids, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import coltt_b200
+    from coltt_b200 import _lib
+    assert _lib.lib().coltt_b200_device_count() >= 1, "needs a B200"
+    return coltt_b200
+
+
+def _fast_scores(cb, sp, qs, k, mode):
+    from coltt_b200 import _lib
+    L = _lib.lib()
+    f = L.coltt_b200_debug_fast_scores
+    f.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64),
+                  C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    nq, n = qs.shape[0], sp.LoadSize()
+    acc = np.zeros((nq, n), np.float32)
+    ids = np.zeros((nq, k), np.uint64)
+    sc = np.zeros((nq, k), np.float32)
+    cnt = np.zeros(nq, np.int32)
+    q = np.ascontiguousarray(qs, np.float32)
+    _lib.check(f(sp._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, mode, acc.ctypes.data_as(C.POINTER(C.c_float)),
+                 ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+    return acc, ids, sc, cnt
+
+
+def _fast_stats(sp):
+    from coltt_b200 import _lib
+    out = (C.c_uint64 * 2)()
+    f = _lib.lib().coltt_b200_store_fast_stats
+    f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    _lib.check(f(sp._h, out))
+    return int(out[0]), int(out[1])
+
+
+@pytest.mark.parametrize("d,n,nq", [(768, 8192, 5), (768, 8200, 130), (128, 4096, 128), (100, 5000, 200), (64, 4100, 256)])
+def test_tensor_core_accumulators_match_fp64_reference(cb, oracle, d, n, nq):
+    """The GEMM itself: acc[q][row] = sum_k fp16(q)[k] * fp16(row)[k] with fp32 accumulation.
+    Tolerance: 2e-4 absolute on unit-norm operands (768 exact products, fp32 accumulate)."""
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    vecs = normal(n, d)
+    qs = normal(nq, d, QUERY_SEED)
+    sp = cb.VectorSpace("g", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_BF16))
+    sp.ChangedVertices(ids, vecs)
+    acc, gi, gs, gc = _fast_scores(cb, sp, qs, 10, cb.SELECT_NEAREST)
+    rows16 = np.stack([oracle.f16_to_f32(oracle.f32_to_f16(oracle.normalize(v))) for v in vecs]).astype(np.float64)
+    q16 = np.stack([oracle.f16_to_f32(oracle.f32_to_f16(oracle.normalize(q))) for q in qs]).astype(np.float64)
+    want = q16 @ rows16.T
+    # slots == insertion order for a fresh store, so acc column j is row j
+    err = np.abs(acc.astype(np.float64) - want)
+    assert np.isfinite(acc).all(), "some accumulators were never written"
+    assert err.max() < 2e-4, f"max abs err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+    # and the FAST answer equals the EXACT answer
+    ei, es, ec = sp.BatchVertexSearch(qs, 10, select_mode=cb.SELECT_NEAREST, math_mode=cb.MATH_EXACT)
+    for j in range(nq):
+        assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], ei[j, :ec[j]], es[j, :ec[j]], f"fast vs exact q{j}")
+    sp.close()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("data", ["normal", "uniform"])
+def test_fast_equals_exact_at_batch(cb, metric, data):
+    n, d, k = 100_000, 768, 10
+    ids = sparse_ids(n)
+    vecs = normal(n, d) if data == "normal" else uniform(n, d)
+    sp = cb.VectorSpace("f", cb.Metadata(d, metric, cb.Quantization_BF16))
+    sp.ChangedVertices(ids, vecs)
+    for nq in (1, 256):
+        qs = (normal if data == "normal" else uniform)(nq, d, QUERY_SEED + nq)
+        for mode in (cb.SELECT_NEAREST, cb.SELECT_COMPAT):
+            fi, fs, fc = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=cb.MATH_FAST)
+            ei, es, ec = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=cb.MATH_EXACT)
+            assert np.array_equal(fc, ec)
+            for j in range(nq):
+                assert_same_hits(fi[j, :fc[j]], fs[j, :fc[j]], ei[j, :ec[j]], es[j, :ec[j]], f"{data} m={metric} mode={mode} q{j}")
+    served, fell_back = _fast_stats(sp)
+    assert served > 0, "FAST path was never taken"
+    assert fell_back <= served * 0.05, f"too many uncertified queries: {fell_back}/{served}"
+    sp.close()
+
+
+def test_fast_with_heavy_ties_falls_back_and_stays_exact(cb):
+    """Every vector repeated ~200 times: the threshold is full of ties, the certificate must refuse
+    and the exact re-run must make the answer identical to EXACT."""
+    n, d, k = 20_000, 256, 10
+    base = normal(100, d)
+    vecs = base[rng(3).integers(0, 100, size=n)]
+    ids = sparse_ids(n)
+    sp = cb.VectorSpace("t", cb.Metadata(d, 0, cb.Quantization_F16))
+    sp.ChangedVertices(ids, vecs)
+    qs = normal(32, d, QUERY_SEED)
+    for mode in (cb.SELECT_NEAREST, cb.SELECT_COMPAT):
+        fi, fs, fc = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=cb.MATH_FAST)
+        ei, es, ec = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=cb.MATH_EXACT)
+        for j in range(len(qs)):
+            assert_same_hits(fi[j, :fc[j]], fs[j, :fc[j]], ei[j, :ec[j]], es[j, :ec[j]], f"ties mode={mode} q{j}")
+    sp.close()
+
+
+def test_fast_unsupported_shapes_silently_use_exact(cb, oracle):
+    """dim > 768 (query tile exceeds tensor memory), k > 32, fp32 stores and tiny stores are served by the
+    exact kernel under COLTT_MATH_FAST — same answer, no error."""
+    for d, n, k, quant in [(1536, 5000, 10, 3), (128, 5000, 64, 3), (128, 5000, 10, 0), (128, 300, 10, 3)]:
+        ids, vecs = sparse_ids(n), normal(n, d)
+        sp = cb.VectorSpace("u", cb.Metadata(d, 0, quant))
+        sp.ChangedVertices(ids, vecs)
+        qs = normal(3, d, QUERY_SEED)
+        fi, fs, fc = sp.BatchVertexSearch(qs, k, select_mode=1, math_mode=cb.MATH_FAST)
+        ei, es, ec = sp.BatchVertexSearch(qs, k, select_mode=1, math_mode=cb.MATH_EXACT)
+        assert np.array_equal(fi, ei) and fs.tobytes() == es.tobytes()
+        sp.close()

@@ -7,7 +7,7 @@ none/f16/"bf16"/f8 stores, cosine and euclidean, both select modes.
 import numpy as np
 import pytest
 
-from tests.util import BASE_SEED, QUERY_SEED, assert_same_hits, normal, rng, sparse_ids, uniform
+from tests.util import BASE_SEED, QUERY_SEED, assert_same_hits, normal, rng, score_bits, sparse_ids, uniform
 
 pytestmark = pytest.mark.gpu
 
@@ -142,7 +142,7 @@ def test_ties_follow_the_documented_total_order(cb, oracle):
             wi, ws = st.search_total_order(q, k, select_mode=mode)
             assert_same_hits([h.Id for h in hits], [h.Score for h in hits], wi, ws, f"ties quant={quant}")
             _, ls = st.search(q, k, select_mode=mode)       # literal Go heap: same scores, tie ids may differ
-            assert np.array([h.Score for h in hits], np.float32).tobytes() == ls.tobytes()
+            assert score_bits([h.Score for h in hits]) == score_bits(ls)
         sp.close()
 
 

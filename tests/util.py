@@ -25,9 +25,17 @@ def sparse_ids(n, seed=BASE_SEED):
     return ids[:n].copy()
 
 
+def score_bits(sc):
+    """fp32 bit patterns with every NaN canonicalised (NaN payload/sign is not part of the contract:
+    the reference's own 0/0 comes out of an x86 divss, ours out of the GPU's divider)."""
+    a = np.asarray(sc, np.float32).copy()
+    a[np.isnan(a)] = np.float32(np.nan)
+    return a.tobytes()
+
+
 def assert_same_hits(got_ids, got_sc, want_ids, want_sc, what=""):
     assert len(got_ids) == len(want_ids), f"{what}: count {len(got_ids)} != {len(want_ids)}"
-    assert np.asarray(got_sc, np.float32).tobytes() == np.asarray(want_sc, np.float32).tobytes(), \
+    assert score_bits(got_sc) == score_bits(want_sc), \
         f"{what}: scores differ\n got {got_sc}\nwant {want_sc}"
     assert np.array_equal(np.asarray(got_ids, np.uint64), np.asarray(want_ids, np.uint64)), \
         f"{what}: ids differ\n got {got_ids}\nwant {want_ids}"
