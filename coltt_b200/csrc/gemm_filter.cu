@@ -119,12 +119,14 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int KP>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t NS = p.n_stages, C = p.cand_cap, KB = p.kblocks;
+  static_assert(KP == 16 || KP == 32, "K' is a register array");
   constexpr uint32_t STAGE_BYTES = kBN * kBK * 2;  // 8 KB
 
   uint8_t* b_stages = smem;
@@ -219,35 +221,90 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     const uint32_t q = q_tile0 + ql;
     const uint32_t et = threadIdx.x - 64;               // 0..127 among the epilogue threads
     const bool q_valid = q < p.nq;
-    const uint32_t Kp = p.kprime;
     const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+    // top[]: this CTA's KP best keys for this query, sorted descending, in registers.
+    // thr = max(top[KP-1], G): G is the KP-th largest of the per-CTA best keys every CTA publishes
+    // (KP different CTAs each hold a row at least that good), refreshed every few tiles — so the
+    // bound tracks the shard-wide KP-th best key, not just this CTA's.
+    float top[KP];
+#pragma unroll
+    for (int i = 0; i < KP; i++) top[i] = NEG_INF;
+    float G = NEG_INF, my_best = NEG_INF;
     float thr = q_valid ? NEG_INF : POS_INF;
+    bool overflowed = false;
     uint32_t cnt = 0;
     float* my_key = cand_key + ql;                       // [slot*kCandStride]
     uint32_t* my_row = cand_row + ql;
+    float* my_pub = p.pub + (size_t)q * gridDim.x;       // [cta] best key of each CTA for this query
     uint32_t ti = 0;
+
+    auto take = [&](float key, uint32_t row) {
+      my_key[cnt * kCandStride] = key;
+      my_row[cnt * kCandStride] = row;
+      cnt++;
+      if (key > top[KP - 1]) {
+        top[KP - 1] = key;
+#pragma unroll
+        for (int i = KP - 1; i > 0; --i) {
+          const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
+          top[i - 1] = hi;
+          top[i] = lo;
+        }
+        thr = fmaxf(thr, top[KP - 1]);
+      }
+      if (key > my_best) {
+        my_best = key;
+        __stcg(my_pub + blockIdx.x, key);
+      }
+    };
+
+    // per-row key coefficients: key = acc * a + b, larger is better for the select mode.  The
+    // ||row||^2 of tile i+1 is fetched while tile i is being processed (its latency is off the path).
+    auto coef_store = [&](uint32_t b_, uint32_t row, float n2) {
+      float a = 0.0f, b = NEG_INF;
+      if (row < p.n_rows) {
+        if (p.metric == COLTT_COSINE) {
+          if (n2 > 0.0f) { a = p.nearest ? rsqrtf(n2) : -rsqrtf(n2); b = 0.0f; }
+          else b = p.nearest ? NEG_INF : POS_INF;       // zero row: NaN distance, last in T order
+        } else {
+          a = p.nearest ? 2.0f : -2.0f;
+          b = p.nearest ? -n2 : n2;
+        }
+      }
+      coef_a[b_ * kBN + et] = a;
+      coef_b[b_ * kBN + et] = b;
+    };
+    if (et < (uint32_t)kBN && blockIdx.x < n_tiles) {
+      const uint32_t row = blockIdx.x * kBN + et;
+      coef_store(0, row, row < p.n_rows ? p.row_norm2[row] : 0.0f);
+    }
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ti++) {
       const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
       const uint32_t row0 = t * kBN;
-      if (et < (uint32_t)kBN) {
-        // per-row key coefficients: key = acc * a + b, larger is better for the select mode
-        const uint32_t row = row0 + et;
-        float a = 0.0f, b = NEG_INF;
-        if (row < p.n_rows) {
-          const float n2 = p.row_norm2[row];
-          if (p.metric == COLTT_COSINE) {
-            if (n2 > 0.0f) { a = p.nearest ? rsqrtf(n2) : -rsqrtf(n2); b = 0.0f; }
-            else b = p.nearest ? NEG_INF : POS_INF;       // zero row: NaN distance, last in T order
-          } else {
-            a = p.nearest ? 2.0f : -2.0f;
-            b = p.nearest ? -n2 : n2;
+      if (q_valid && !overflowed && (ti & 3) == 1 && gridDim.x >= (uint32_t)KP) {
+        // refresh G = KP-th largest of the published per-CTA maxima (a fresh snapshot each time)
+        float g[KP];
+#pragma unroll
+        for (int i = 0; i < KP; i++) g[i] = NEG_INF;
+        for (uint32_t c = 0; c < gridDim.x; c++) {
+          const float v = __ldcg(my_pub + c);
+          if (v > g[KP - 1]) {
+            g[KP - 1] = v;
+#pragma unroll
+            for (int i = KP - 1; i > 0; --i) {
+              const float hi = fmaxf(g[i - 1], g[i]), lo = fminf(g[i - 1], g[i]);
+              g[i - 1] = hi;
+              g[i] = lo;
+            }
           }
         }
-        coef_a[buf * kBN + et] = a;
-        coef_b[buf * kBN + et] = b;
+        G = fmaxf(G, g[KP - 1]);
+        thr = fmaxf(thr, G);
       }
-      if (q_valid) thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile const uint32_t*>(p.g_thr + q)));
       named_bar_sync(1, 128);
+      const uint32_t next_row = (t + gridDim.x) * kBN + et;
+      float n2_next = 0.0f;
+      if (et < (uint32_t)kBN && next_row < p.n_rows) n2_next = p.row_norm2[next_row];
       mbar_wait(smem_u32(tfull_bar + buf), bph);
       tc_fence_after();
 #pragma unroll
@@ -277,71 +334,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
           const float k2 = fmaf(__uint_as_float(v[4 * c4 + 2]), a4.z, b4.z);
           const float k3 = fmaf(__uint_as_float(v[4 * c4 + 3]), a4.w, b4.w);
           const uint32_t rb = row0 + half * 32 + 4 * c4;
-          if (k0 > thr) { my_key[cnt * kCandStride] = k0; my_row[cnt * kCandStride] = rb + 0; cnt++; }
-          if (k1 > thr) { my_key[cnt * kCandStride] = k1; my_row[cnt * kCandStride] = rb + 1; cnt++; }
-          if (k2 > thr) { my_key[cnt * kCandStride] = k2; my_row[cnt * kCandStride] = rb + 2; cnt++; }
-          if (k3 > thr) { my_key[cnt * kCandStride] = k3; my_row[cnt * kCandStride] = rb + 3; cnt++; }
+          if (k0 > thr) take(k0, rb + 0);
+          if (k1 > thr) take(k1, rb + 1);
+          if (k2 > thr) take(k2, rb + 2);
+          if (k3 > thr) take(k3, rb + 3);
         }
-        // ---- compaction: a buffer that could overflow in the next 32 columns keeps its best K'
-        uint32_t need = __ballot_sync(0xffffffffu, cnt + 32 > C);
-        while (need) {
-          const int L = __ffs(need) - 1;
-          need &= need - 1;
-          const uint32_t n = __shfl_sync(0xffffffffu, cnt, L);
-          const float* kq = cand_key + quarter * 32 + L;
-          uint32_t* rq = cand_row + quarter * 32 + L;
-          // rank counting: entry e keeps rank = #entries strictly better (ties: lower slot first)
-          float mk[4]; uint32_t mr[4]; uint32_t rank[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t e = lane + 32 * u;
-            mk[u] = e < n ? kq[e * kCandStride] : NEG_INF;
-            mr[u] = e < n ? rq[e * kCandStride] : 0u;
-            rank[u] = 0;
+        // ---- the buffer must have room for the next 32 columns: drop what fell below the bound
+        if (cnt + 32 > C) {
+          uint32_t w = 0;
+          for (uint32_t s = 0; s < cnt; s++) {
+            const float kk = my_key[s * kCandStride];
+            const uint32_t rr = my_row[s * kCandStride];
+            if (kk >= thr) { my_key[w * kCandStride] = kk; my_row[w * kCandStride] = rr; w++; }
           }
-          for (uint32_t j = 0; j < n; j++) {
-            const float kj = kq[j * kCandStride];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const uint32_t e = lane + 32 * u;
-              rank[u] += (kj > mk[u] || (kj == mk[u] && j < e)) ? 1u : 0u;
-            }
-          }
-          __syncwarp();
-          float kth = NEG_INF;
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t e = lane + 32 * u;
-            if (e < n && rank[u] < Kp) {
-              const_cast<float*>(kq)[rank[u] * kCandStride] = mk[u];
-              rq[rank[u] * kCandStride] = mr[u];
-              if (rank[u] == Kp - 1) kth = mk[u];
-            }
-          }
-          // the lane holding rank K'-1 knows the new threshold
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-          __syncwarp();
-          if ((int)lane == L) {
-            if (n >= Kp) {
-              cnt = Kp;
-              thr = fmaxf(thr, kth);
-              atomicMax(p.g_thr + q, f2ord(thr));      // share the bound with every other CTA
-            }
+          cnt = w;
+          if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
+            overflowed = true;
+            cnt = 0;
+            thr = POS_INF;
           }
         }
       }
+      if (et < (uint32_t)kBN) coef_store(buf ^ 1, next_row, n2_next);
     }
-    // ---- hand the survivors to rerank.cu: [query][cta][slot]
+    // ---- hand the survivors to rerank.cu: [query][cta][slot]; publish the bound they were cut at
     if (q_valid) {
-      const float gth = ord2f(*reinterpret_cast<volatile const uint32_t*>(p.g_thr + q));
       GemmCand* out = p.cand_out + ((size_t)q * gridDim.x + blockIdx.x) * C;
       uint32_t w = 0;
       for (uint32_t s = 0; s < cnt; s++) {
         const float kk = my_key[s * kCandStride];
-        if (kk >= gth || !(gth == gth)) { out[w].key = kk; out[w].row = my_row[s * kCandStride]; w++; }
+        if (kk >= thr) { out[w].key = kk; out[w].row = my_row[s * kCandStride]; w++; }
       }
-      p.cand_cnt[(size_t)q * gridDim.x + blockIdx.x] = w;
+      p.cand_cnt[(size_t)q * gridDim.x + blockIdx.x] = overflowed ? 0xffffffffu : w;
+      if (!overflowed && thr > NEG_INF) atomicMax(p.g_thr + q, f2ord(thr));
     }
   }
 
@@ -369,9 +394,9 @@ static EncodeTiledFn encode_tiled_fn() {
 int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan) {
   const uint32_t kblocks = (dim + kBK - 1) / kBK;
   if (kblocks * 32 + 2 * kBN > 512) return fail(COLTT_ERR_UNSUPPORTED, "FAST: query tile does not fit tensor memory (dim > 768 fp16)");
-  if (k > 32) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 32 is served by the exact path");
-  const uint32_t kprime = k <= 8 ? 16 : ((2 * k + 15) / 16 * 16);
-  const uint32_t cap = kprime + 32 > 128 ? 128 : kprime + 32;
+  if (k > 24) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 24 is served by the exact path");
+  const uint32_t kprime = k <= 8 ? 16 : 32;          // K' (register-resident per query); margin for the certificate
+  const uint32_t cap = kprime + 48;                  // K' + 32 columns of headroom + 16 slack
   const size_t cand_bytes = (size_t)cap * kCandStride * 8;
   const size_t misc = 2 * 2 * kBN * 4 + 1024;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - cand_bytes - misc;
@@ -405,8 +430,13 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan, const void*
   p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.n_stages = plan.n_stages;
   uint32_t n_tiles = (p.n_rows + kBN - 1) / kBN;
   dim3 grid(plan.grid_x < n_tiles ? plan.grid_x : n_tiles, plan.grid_y);
-  COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
-  gemm_filter_kernel<<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, p);
+  if (plan.kprime == 16) {
+    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    gemm_filter_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, p);
+  } else {
+    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    gemm_filter_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, p);
+  }
   count_launch();
   COLTT_CUDA(cudaGetLastError());
   return COLTT_OK;

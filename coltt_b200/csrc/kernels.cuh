@@ -72,7 +72,8 @@ struct GemmParams {
   uint32_t q_stride;
   const float* row_norm2;    // [n_rows]
   int metric, nearest;
-  uint32_t* g_thr;           // [nq] order-encoded shared thresholds, zero-initialised
+  uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over CTAs), zero-initialised
+  float* pub;                // [nq][grid_x] best key each CTA has seen per query, initialised to -inf
   GemmCand* cand_out;        // [nq][grid_x][cand_cap]
   uint32_t* cand_cnt;        // [nq][grid_x]
   uint32_t kblocks, kprime, cand_cap, n_stages;  // filled from the plan

@@ -47,9 +47,14 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   const uint32_t thr_bits = p.g_thr[q];
   const bool have_bound = thr_bits != 0;
   const float B = have_bound ? ord2f_(thr_bits) : 0.0f;
+  __shared__ uint32_t ovf_s;
+  if (tid == 0) ovf_s = 0;
+  __syncthreads();
   for (uint32_t i = tid; i < p.grid_x * p.cand_cap; i += blockDim.x) {
     const uint32_t cta = i / p.cand_cap, s = i - cta * p.cand_cap;
-    if (s < p.cand_cnt[(size_t)q * p.grid_x + cta]) {
+    const uint32_t ccnt = p.cand_cnt[(size_t)q * p.grid_x + cta];
+    if (ccnt == 0xffffffffu) { ovf_s = 1; continue; }   // that CTA overflowed on ties: exact path
+    if (s < ccnt) {
       const GemmCand c = p.cand_in[((size_t)q * p.grid_x + cta) * p.cand_cap + s];
       if (!have_bound || c.key >= B || c.key != c.key) {
         const uint32_t pos = atomicAdd(&n_s, 1u);
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   // ---- 4. certificate
   if (tid == 0) {
     p.out_counts[q] = (int)n_out;
-    bool ok = n_all <= kRerankMaxCand;
+    bool ok = n_all <= kRerankMaxCand && ovf_s == 0;
     if (ok && have_bound) {
       const float dK = kth_s;  // exact score (a distance) of the worst row we return
       if (!(dK == dK)) {

@@ -410,6 +410,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = c.cand_cnt.ensure(nq * (size_t)gp.grid_x * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
   rc = c.h_flags.ensure(nq * 4); if (rc) return rc;
+  rc = c.pub.ensure(nq * (size_t)gp.grid_x * 4); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[0], st);
   PrepParams pp{};
   pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
@@ -420,11 +421,12 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
   COLTT_CUDA(cudaMemsetAsync(c.g_thr.p, 0, nq * 4, st));
   COLTT_CUDA(cudaMemsetAsync(c.cand_cnt.p, 0, nq * (size_t)gp.grid_x * 4, st));
+  COLTT_CUDA(cudaMemsetAsync(c.pub.p, 0xff, nq * (size_t)gp.grid_x * 4, st));  // 0xffffffff = -NaN: never > anything, i.e. "nothing yet"
   if (timed) cudaEventRecord(c.ev[1], st);
   GemmParams g{};
   g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
   g.row_norm2 = d_norm2; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
-  g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc;
+  g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p;
   rc = launch_gemm_filter(g, gp, d_rows, row_stride, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};

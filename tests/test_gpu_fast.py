@@ -60,6 +60,13 @@ def test_tensor_core_accumulators_match_fp64_reference(cb, oracle, d, n, nq):
     want = q16 @ rows16.T
     # slots == insertion order for a fresh store, so acc column j is row j
     err = np.abs(acc.astype(np.float64) - want)
+    if not np.isfinite(acc).all() or err.max() >= 2e-4:   # leave evidence for the next debugging step
+        import os
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez(f"gpurun_out/fast_dbg_d{d}_n{n}_q{nq}.npz", got=acc[:, :512], want=want[:, :512].astype(np.float32))
+        bad = ~np.isfinite(acc) | (err >= 2e-4)
+        print("bad fraction", bad.mean(), "bad rows(q) sample", np.where(bad.any(1))[0][:10], "bad cols sample", np.where(bad.any(0))[0][:20])
+        print("got[0,:8]", acc[0, :8], "want[0,:8]", want[0, :8])
     assert np.isfinite(acc).all(), "some accumulators were never written"
     assert err.max() < 2e-4, f"max abs err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
     # and the FAST answer equals the EXACT answer
