@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
   uint8_t* b_stages = smem;
   float* cand_key = reinterpret_cast<float*>(smem + (size_t)NS * STAGE_BYTES);
   uint32_t* cand_row = reinterpret_cast<uint32_t*>(cand_key + (size_t)C * kCandStride);
-  float* coef_a = reinterpret_cast<float*>(cand_row + (size_t)C * kCandStride);  // [2][kBN]
+  float* top_s = reinterpret_cast<float*>(cand_row + (size_t)C * kCandStride);   // [KP][kCandStride]
+  float* sweep_s = top_s + (size_t)KP * kCandStride;                             // [KP][kCandStride]
+  float* coef_a = sweep_s + (size_t)KP * kCandStride;                            // [2][kBN]
   float* coef_b = coef_a + 2 * kBN;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(coef_b + 2 * kBN);
   uint64_t* empty_bar = full_bar + NS;
@@ -181,13 +183,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
+      long long w_empty = 0, t_start = clock64();
       for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (uint32_t kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(smem_u32(empty_bar + s), ph ^ 1);
+          const long long c0 = clock64();
+          while (!mbar_try_wait(smem_u32(empty_bar + s), ph ^ 1)) __nanosleep(64);   // do not steal issue slots from the epilogue
+          w_empty += clock64() - c0;
           mbar_arrive_expect_tx(smem_u32(full_bar + s), STAGE_BYTES);
           tma_load_2d(smem_u32(b_stages + (size_t)s * STAGE_BYTES), &tmap, (int)(kb * kBK), (int)(t * kBN), smem_u32(full_bar + s));
         }
+      }
+      if (p.dbg_prof) {
+        p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 0] = (unsigned long long)w_empty;
+        p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 1] = (unsigned long long)(clock64() - t_start);
       }
     }
   } else if (warp == 1) {
@@ -196,14 +205,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
       // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t it = 0, ti = 0;
+      long long w_tempty = 0, w_full = 0, t_start = clock64();
       for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ti++) {
         const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
-        mbar_wait(smem_u32(tempty_bar + buf), bph ^ 1);   // epilogue drained this accumulator
+        const long long c0 = clock64();
+        while (!mbar_try_wait(smem_u32(tempty_bar + buf), bph ^ 1)) __nanosleep(20);   // epilogue drained this accumulator
+        w_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kBN;
         for (uint32_t kb = 0; kb < KB; kb++, it++) {
           const uint32_t s = it % NS, ph = (it / NS) & 1;
-          mbar_wait(smem_u32(full_bar + s), ph);
+          const long long c1 = clock64();
+          while (!mbar_try_wait(smem_u32(full_bar + s), ph)) __nanosleep(20);
+          w_full += clock64() - c1;
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_stages + (size_t)s * STAGE_BYTES);
 #pragma unroll
@@ -212,6 +226,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
           umma_commit(smem_u32(empty_bar + s));           // frees the smem stage when these MMAs retire
         }
         umma_commit(smem_u32(tfull_bar + buf));            // accumulator complete
+      }
+      if (p.dbg_prof) {
+        p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 2] = (unsigned long long)w_tempty;
+        p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 3] = (unsigned long long)w_full;
+        p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 4] = (unsigned long long)(clock64() - t_start);
       }
     }
   } else {
@@ -222,40 +241,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     const uint32_t et = threadIdx.x - 64;               // 0..127 among the epilogue threads
     const bool q_valid = q < p.nq;
     const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-    // top[]: this CTA's KP best keys for this query, sorted descending, in registers.
-    // thr = max(top[KP-1], G): G is the KP-th largest of the per-CTA best keys every CTA publishes
-    // (KP different CTAs each hold a row at least that good), refreshed every few tiles — so the
-    // bound tracks the shard-wide KP-th best key, not just this CTA's.
-    float top[KP];
-#pragma unroll
-    for (int i = 0; i < KP; i++) top[i] = NEG_INF;
+    // Per-query state.  top_s[]: this CTA's KP best keys (sorted, descending); sweep_s[]: the KP
+    // largest per-CTA maxima seen in the current sweep.  Both are shared-memory columns so the rare
+    // insertions are small dynamic loops, and the per-tile hot path stays branch-free and I-cache small.
+    // thr = max(top_s[KP-1], G): G = KP-th largest of the best keys the CTAs publish (KP different
+    // CTAs each hold a row at least that good) — the bound tracks the shard-wide KP-th best key.
+    float* top_c = top_s + ql;
+    float* sweep_c_ = sweep_s + ql;
+    for (int i = 0; i < KP; i++) { top_c[i * kCandStride] = NEG_INF; sweep_c_[i * kCandStride] = NEG_INF; }
     float G = NEG_INF, my_best = NEG_INF;
+    uint32_t sweep_pos = 0;
+    const bool sweeping = q_valid && gridDim.x >= (uint32_t)KP;
     float thr = q_valid ? NEG_INF : POS_INF;
     bool overflowed = false;
     uint32_t cnt = 0;
     float* my_key = cand_key + ql;                       // [slot*kCandStride]
     uint32_t* my_row = cand_row + ql;
-    float* my_pub = p.pub + (size_t)q * gridDim.x;       // [cta] best key of each CTA for this query
+    float* my_pub = p.pub + (size_t)blockIdx.x * p.nq + q; // pub[cta][query]: best key this CTA has seen for the query
     uint32_t ti = 0;
+    long long w_tfull = 0, t_start_e = clock64();
 
-    auto take = [&](float key, uint32_t row) {
-      my_key[cnt * kCandStride] = key;
-      my_row[cnt * kCandStride] = row;
-      cnt++;
-      if (key > top[KP - 1]) {
-        top[KP - 1] = key;
-#pragma unroll
-        for (int i = KP - 1; i > 0; --i) {
-          const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
-          top[i - 1] = hi;
-          top[i] = lo;
-        }
-        thr = fmaxf(thr, top[KP - 1]);
+    // insert v into a descending sorted column of KP entries (v > last entry)
+    auto sorted_insert = [&](float* col, float v) {
+      int i = KP - 1;
+      while (i > 0) {
+        const float up = col[(i - 1) * kCandStride];
+        if (up >= v) break;
+        col[i * kCandStride] = up;
+        --i;
       }
-      if (key > my_best) {
-        my_best = key;
-        __stcg(my_pub + blockIdx.x, key);
-      }
+      col[i * kCandStride] = v;
     };
 
     // per-row key coefficients: key = acc * a + b, larger is better for the select mode.  The
@@ -281,33 +296,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ti++) {
       const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
       const uint32_t row0 = t * kBN;
-      if (q_valid && !overflowed && (ti & 3) == 1 && gridDim.x >= (uint32_t)KP) {
-        // refresh G = KP-th largest of the published per-CTA maxima (a fresh snapshot each time)
-        float g[KP];
+      // rolling sweep over the per-CTA maxima: 16 loads issued here, consumed after this tile's
+      // scores (their L2 latency hides behind the tile); a sweep of all CTAs ends every gx/16 tiles
+      float pend[16];
+      if (sweeping) {
 #pragma unroll
-        for (int i = 0; i < KP; i++) g[i] = NEG_INF;
-        for (uint32_t c = 0; c < gridDim.x; c++) {
-          const float v = __ldcg(my_pub + c);
-          if (v > g[KP - 1]) {
-            g[KP - 1] = v;
-#pragma unroll
-            for (int i = KP - 1; i > 0; --i) {
-              const float hi = fmaxf(g[i - 1], g[i]), lo = fminf(g[i - 1], g[i]);
-              g[i - 1] = hi;
-              g[i] = lo;
-            }
-          }
+        for (int i = 0; i < 16; i++) {
+          const uint32_t c = sweep_pos + i;
+          pend[i] = c < gridDim.x ? __ldcg(p.pub + (size_t)c * p.nq + q) : NEG_INF;
         }
-        G = fmaxf(G, g[KP - 1]);
-        thr = fmaxf(thr, G);
       }
       named_bar_sync(1, 128);
       const uint32_t next_row = (t + gridDim.x) * kBN + et;
       float n2_next = 0.0f;
       if (et < (uint32_t)kBN && next_row < p.n_rows) n2_next = p.row_norm2[next_row];
+      const long long ce0 = clock64();
       mbar_wait(smem_u32(tfull_bar + buf), bph);
+      w_tfull += clock64() - ce0;
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (uint32_t half = 0; half < kBN / 32; half++) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((quarter * 32) << 16) + buf * kBN + half * 32, v);
@@ -324,46 +331,92 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
             if (row < p.n_rows) p.dbg_acc[(size_t)q * p.n_rows + row] = __uint_as_float(v[c]);
           }
         }
+        if (p.dbg_flags & 1u) continue;
+        // hot path: 32 FFMA + a max tree + one vote; no per-element branches
         const float4* ca = reinterpret_cast<const float4*>(coef_a + buf * kBN + half * 32);
         const float4* cb = reinterpret_cast<const float4*>(coef_b + buf * kBN + half * 32);
+        float key[32];
+        float kmax = NEG_INF;
 #pragma unroll
         for (int c4 = 0; c4 < 8; c4++) {
           const float4 a4 = ca[c4], b4 = cb[c4];
-          const float k0 = fmaf(__uint_as_float(v[4 * c4 + 0]), a4.x, b4.x);
-          const float k1 = fmaf(__uint_as_float(v[4 * c4 + 1]), a4.y, b4.y);
-          const float k2 = fmaf(__uint_as_float(v[4 * c4 + 2]), a4.z, b4.z);
-          const float k3 = fmaf(__uint_as_float(v[4 * c4 + 3]), a4.w, b4.w);
-          const uint32_t rb = row0 + half * 32 + 4 * c4;
-          if (k0 > thr) take(k0, rb + 0);
-          if (k1 > thr) take(k1, rb + 1);
-          if (k2 > thr) take(k2, rb + 2);
-          if (k3 > thr) take(k3, rb + 3);
+          key[4 * c4 + 0] = fmaf(__uint_as_float(v[4 * c4 + 0]), a4.x, b4.x);
+          key[4 * c4 + 1] = fmaf(__uint_as_float(v[4 * c4 + 1]), a4.y, b4.y);
+          key[4 * c4 + 2] = fmaf(__uint_as_float(v[4 * c4 + 2]), a4.z, b4.z);
+          key[4 * c4 + 3] = fmaf(__uint_as_float(v[4 * c4 + 3]), a4.w, b4.w);
+          kmax = fmaxf(kmax, fmaxf(fmaxf(key[4 * c4 + 0], key[4 * c4 + 1]), fmaxf(key[4 * c4 + 2], key[4 * c4 + 3])));
         }
-        // ---- the buffer must have room for the next 32 columns: drop what fell below the bound
-        if (cnt + 32 > C) {
-          uint32_t w = 0;
-          for (uint32_t s = 0; s < cnt; s++) {
-            const float kk = my_key[s * kCandStride];
-            const uint32_t rr = my_row[s * kCandStride];
-            if (kk >= thr) { my_key[w * kCandStride] = kk; my_row[w * kCandStride] = rr; w++; }
-          }
-          cnt = w;
-          if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
-            overflowed = true;
-            cnt = 0;
-            thr = POS_INF;
+        const bool mine = kmax > thr;
+        if (__any_sync(0xffffffffu, mine)) {
+          // rare path: park the 32 keys in the free tail of the candidate buffer (room for 32 is an
+          // invariant), then walk them with a dynamic loop
+          if (mine) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) my_key[(cnt + c) * kCandStride] = key[c];
+            const uint32_t base = cnt, rb = row0 + half * 32;
+            uint32_t w = cnt;
+            for (uint32_t c = 0; c < 32; c++) {
+              const float kk = my_key[(base + c) * kCandStride];
+              if (kk > thr) {
+                my_key[w * kCandStride] = kk;
+                my_row[w * kCandStride] = rb + c;
+                w++;
+                if (kk > top_c[(KP - 1) * kCandStride]) {
+                  sorted_insert(top_c, kk);
+                  thr = fmaxf(thr, top_c[(KP - 1) * kCandStride]);
+                }
+                if (kk > my_best) { my_best = kk; __stcg(my_pub, kk); }
+              }
+            }
+            cnt = w;
+            // the buffer must keep room for the next 32 columns: drop what fell below the bound
+            if (cnt + 32 > C) {
+              uint32_t w2 = 0;
+              for (uint32_t s2 = 0; s2 < cnt; s2++) {
+                const float k2 = my_key[s2 * kCandStride];
+                const uint32_t r2 = my_row[s2 * kCandStride];
+                if (k2 >= thr) { my_key[w2 * kCandStride] = k2; my_row[w2 * kCandStride] = r2; w2++; }
+              }
+              cnt = w2;
+              if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
+                overflowed = true;
+                cnt = 0;
+                thr = POS_INF;
+              }
+            }
           }
         }
       }
       if (et < (uint32_t)kBN) coef_store(buf ^ 1, next_row, n2_next);
+      if (sweeping && !overflowed) {
+        float pmax = pend[0];
+#pragma unroll
+        for (int i = 1; i < 16; i++) pmax = fmaxf(pmax, pend[i]);
+        if (pmax > sweep_c_[(KP - 1) * kCandStride]) {
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            if (pend[i] > sweep_c_[(KP - 1) * kCandStride]) sorted_insert(sweep_c_, pend[i]);
+        }
+        sweep_pos += 16;
+        if (sweep_pos >= gridDim.x) {   // KP different CTAs each hold a row with key >= sweep[KP-1]
+          G = fmaxf(G, sweep_c_[(KP - 1) * kCandStride]);
+          thr = fmaxf(thr, G);
+          sweep_pos = 0;
+          for (int i = 0; i < KP; i++) sweep_c_[i * kCandStride] = NEG_INF;
+        }
+      }
+    }
+    if (p.dbg_prof && et == 0) {
+      p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 5] = (unsigned long long)w_tfull;
+      p.dbg_prof[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 6] = (unsigned long long)(clock64() - t_start_e);
     }
     // ---- hand the survivors to rerank.cu: [query][cta][slot]; publish the bound they were cut at
     if (q_valid) {
       GemmCand* out = p.cand_out + ((size_t)q * gridDim.x + blockIdx.x) * C;
       uint32_t w = 0;
-      for (uint32_t s = 0; s < cnt; s++) {
-        const float kk = my_key[s * kCandStride];
-        if (kk >= thr) { out[w].key = kk; out[w].row = my_row[s * kCandStride]; w++; }
+      for (uint32_t s2 = 0; s2 < cnt; s2++) {
+        const float kk = my_key[s2 * kCandStride];
+        if (kk >= thr) { out[w].key = kk; out[w].row = my_row[s2 * kCandStride]; w++; }
       }
       p.cand_cnt[(size_t)q * gridDim.x + blockIdx.x] = overflowed ? 0xffffffffu : w;
       if (!overflowed && thr > NEG_INF) atomicMax(p.g_thr + q, f2ord(thr));
@@ -395,9 +448,9 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
   const uint32_t kblocks = (dim + kBK - 1) / kBK;
   if (kblocks * 32 + 2 * kBN > 512) return fail(COLTT_ERR_UNSUPPORTED, "FAST: query tile does not fit tensor memory (dim > 768 fp16)");
   if (k > 24) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 24 is served by the exact path");
-  const uint32_t kprime = k <= 8 ? 16 : 32;          // K' (register-resident per query); margin for the certificate
+  const uint32_t kprime = k <= 10 ? 16 : 32;         // K' (register-resident per query); margin for the certificate
   const uint32_t cap = kprime + 48;                  // K' + 32 columns of headroom + 16 slack
-  const size_t cand_bytes = (size_t)cap * kCandStride * 8;
+  const size_t cand_bytes = (size_t)cap * kCandStride * 8 + 2 * (size_t)kprime * kCandStride * 4;
   const size_t misc = 2 * 2 * kBN * 4 + 1024;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - cand_bytes - misc;
   uint32_t ns = (uint32_t)(budget / (kBN * kBK * 2));

@@ -73,11 +73,13 @@ struct GemmParams {
   const float* row_norm2;    // [n_rows]
   int metric, nearest;
   uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over CTAs), zero-initialised
-  float* pub;                // [nq][grid_x] best key each CTA has seen per query, initialised to -inf
+  float* pub;                // [grid_x][nq] best key each CTA has seen per query, initialised to NaN
   GemmCand* cand_out;        // [nq][grid_x][cand_cap]
   uint32_t* cand_cnt;        // [nq][grid_x]
   uint32_t kblocks, kprime, cand_cap, n_stages;  // filled from the plan
   float* dbg_acc;            // nullable (tests): raw accumulators [nq][n_rows]
+  unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
+  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe)
 };
 struct GemmPlan {
   uint32_t kblocks, kprime, cand_cap, n_stages, grid_x, grid_y, q_stride;

@@ -15,6 +15,8 @@
 // host (the Go side owns metadata and filters; it hands ids across the boundary).
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -427,6 +429,16 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
   g.row_norm2 = d_norm2; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
   g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p;
+  {
+    static const char* prof_env = getenv("COLTT_DEBUG_PROF");
+    static const char* flags_env = getenv("COLTT_DEBUG_FLAGS");
+    g.dbg_flags = flags_env ? (uint32_t)atoi(flags_env) : 0u;
+    if (prof_env) {
+      rc = c.prof.ensure((size_t)gp.grid_x * gp.grid_y * 8 * 8); if (rc) return rc;
+      COLTT_CUDA(cudaMemsetAsync(c.prof.p, 0, (size_t)gp.grid_x * gp.grid_y * 8 * 8, st));
+      g.dbg_prof = (unsigned long long*)c.prof.p;
+    }
+  }
   rc = launch_gemm_filter(g, gp, d_rows, row_stride, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
@@ -439,6 +451,20 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   r.out = d_out; r.out_stride = (uint32_t)k; r.out_counts = d_counts; r.flags = (uint32_t*)c.flags.p;
   rc = launch_rerank(r, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[3], st);
+  if (g.dbg_prof) {
+    static int printed = 0;
+    COLTT_CUDA(cudaStreamSynchronize(st));
+    if (printed++ == 3) {   // a warmed-up step
+      std::vector<unsigned long long> h((size_t)gp.grid_x * gp.grid_y * 8);
+      COLTT_CUDA(cudaMemcpy(h.data(), c.prof.p, h.size() * 8, cudaMemcpyDeviceToHost));
+      const char* names[8] = {"prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total", "epi_wait_tfull", "epi_total", "-"};
+      for (int k2 = 0; k2 < 7; k2++) {
+        double sum = 0, mx = 0;
+        for (size_t i = 0; i < h.size() / 8; i++) { sum += (double)h[i * 8 + k2]; if ((double)h[i * 8 + k2] > mx) mx = (double)h[i * 8 + k2]; }
+        fprintf(stderr, "[coltt prof] %-16s avg %.0f max %.0f cycles\n", names[k2], sum / (h.size() / 8), mx);
+      }
+    }
+  }
   *used_fast = true;
   fast_queries += nq;
   // certificate check: queries that could not be certified are re-run on the exact path
