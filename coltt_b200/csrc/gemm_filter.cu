@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     float* sweep_c_ = sweep_s + ql;
     for (int i = 0; i < KP; i++) { top_c[i * kCandStride] = NEG_INF; sweep_c_[i * kCandStride] = NEG_INF; }
     float G = NEG_INF, my_best = NEG_INF;
-    uint32_t sweep_pos = 0;
+    uint32_t next_sweep = 1;
     const bool sweeping = q_valid && gridDim.x >= (uint32_t)KP;
     float thr = q_valid ? NEG_INF : POS_INF;
     bool overflowed = false;
@@ -296,16 +296,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ti++) {
       const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
       const uint32_t row0 = t * kBN;
-      // rolling sweep over the per-CTA maxima: 16 loads issued here, consumed after this tile's
-      // scores (their L2 latency hides behind the tile); a sweep of all CTAs ends every gx/16 tiles
-      float pend[16];
-      if (sweeping) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const uint32_t c = sweep_pos + i;
-          pend[i] = c < gridDim.x ? __ldcg(p.pub + (size_t)c * p.nq + q) : NEG_INF;
-        }
-      }
       named_bar_sync(1, 128);
       const uint32_t next_row = (t + gridDim.x) * kBN + et;
       float n2_next = 0.0f;
@@ -354,10 +344,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
 #pragma unroll
             for (int c = 0; c < 32; c++) my_key[(cnt + c) * kCandStride] = key[c];
             const uint32_t base = cnt, rb = row0 + half * 32;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 32; c++) mask |= (key[c] > thr ? 1u : 0u) << c;
             uint32_t w = cnt;
-            for (uint32_t c = 0; c < 32; c++) {
+            while (mask) {
+              const uint32_t c = __ffs(mask) - 1;
+              mask &= mask - 1;
               const float kk = my_key[(base + c) * kCandStride];
-              if (kk > thr) {
+              if (kk > thr) {   // thr may have risen since the mask was taken
                 my_key[w * kCandStride] = kk;
                 my_row[w * kCandStride] = rb + c;
                 w++;
@@ -388,22 +383,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_filter_kernel(const __gr
         }
       }
       if (et < (uint32_t)kBN) coef_store(buf ^ 1, next_row, n2_next);
-      if (sweeping && !overflowed) {
-        float pmax = pend[0];
+      // Full sweep of the per-CTA maxima on an exponential schedule (tiles 1,2,3,4,6,8,12,16,...):
+      // the bound moves like 1/rows-seen, so late sweeps are rare.  Loads go out in batches of 8.
+      if (sweeping && !overflowed && ti == next_sweep) {
+        next_sweep = ti < 4 ? ti + 1 : ti + (ti >> 1);
+        for (int i = 0; i < KP; i++) sweep_c_[i * kCandStride] = NEG_INF;
+        for (uint32_t c0 = 0; c0 < gridDim.x; c0 += 8) {
+          float pv[8];
 #pragma unroll
-        for (int i = 1; i < 16; i++) pmax = fmaxf(pmax, pend[i]);
-        if (pmax > sweep_c_[(KP - 1) * kCandStride]) {
+          for (int i = 0; i < 8; i++) pv[i] = c0 + i < gridDim.x ? __ldcg(p.pub + (size_t)(c0 + i) * p.nq + q) : NEG_INF;
 #pragma unroll
-          for (int i = 0; i < 16; i++)
-            if (pend[i] > sweep_c_[(KP - 1) * kCandStride]) sorted_insert(sweep_c_, pend[i]);
+          for (int i = 0; i < 8; i++)
+            if (pv[i] > sweep_c_[(KP - 1) * kCandStride]) sorted_insert(sweep_c_, pv[i]);
         }
-        sweep_pos += 16;
-        if (sweep_pos >= gridDim.x) {   // KP different CTAs each hold a row with key >= sweep[KP-1]
-          G = fmaxf(G, sweep_c_[(KP - 1) * kCandStride]);
-          thr = fmaxf(thr, G);
-          sweep_pos = 0;
-          for (int i = 0; i < KP; i++) sweep_c_[i * kCandStride] = NEG_INF;
-        }
+        G = fmaxf(G, sweep_c_[(KP - 1) * kCandStride]);   // KP different CTAs each hold a row at least this good
+        thr = fmaxf(thr, G);
       }
     }
     if (p.dbg_prof && et == 0) {
