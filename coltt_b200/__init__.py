@@ -13,3 +13,4 @@ from .edge import (  # noqa: F401
     Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16,
     SELECT_COMPAT, SELECT_NEAREST, MATH_EXACT, MATH_FAST, score_helper,
 )
+from .vectorindex import Hnsw  # noqa: F401,E402

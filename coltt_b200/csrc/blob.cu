@@ -50,6 +50,15 @@ __global__ void __launch_bounds__(256) norm2_stored_kernel(const uint8_t* rows, 
   }
 }
 
+int launch_norm2_stored_f32(const uint8_t* rows, uint32_t row_stride, uint32_t dim, size_t n, float* norm2, cudaStream_t stream) {
+  if (n == 0) return COLTT_OK;
+  const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+  norm2_stored_kernel<ELEM_F32><<<blocks, 256, 0, stream>>>(rows, row_stride, dim, n, norm2);
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  return COLTT_OK;
+}
+
 static inline void put_be(uint8_t*& p, uint64_t v, int nb) {
   for (int i = nb - 1; i >= 0; i--) *p++ = (uint8_t)(v >> (8 * i));
 }

@@ -1,0 +1,99 @@
+"""GPU parity of core/vectorindex HNSW search: the oracle (restatement of hnsw.go, ascending-id
+neighbour order) builds and Commit()s a graph; the GPU loads the reference's Commit blob and must
+return the same ids, bit-identical scores and the same number of distance evaluations."""
+import numpy as np
+import pytest
+
+from tests.util import QUERY_SEED, assert_same_hits, normal, sparse_ids, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import coltt_b200
+    from coltt_b200 import _lib
+    assert _lib.lib().coltt_b200_device_count() >= 1, "needs a B200"
+    return coltt_b200
+
+
+def _build(oracle, n, d, metric, m=16, seed=1, data=normal):
+    ids, vecs = sparse_ids(n, seed), data(n, d, seed)
+    h = oracle.Hnsw(d, metric, m=m)
+    h.build(ids, vecs, seed=seed)
+    return h, ids, vecs
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d", [(1, 16), (2, 8), (300, 24), (3000, 128), (2000, 770)])
+def test_hnsw_search_matches_oracle(cb, oracle, metric, n, d):
+    h, ids, vecs = _build(oracle, n, d, metric, seed=n + d)
+    g = cb.Hnsw.Load(h.commit())
+    assert g.Len() == len(h) == n
+    qs = normal(12, d, QUERY_SEED + d)
+    for ef, k in [(0, 10), (64, 10), (128, 1), (40, 40)]:
+        if ef:
+            h.set_ef(ef)
+        else:
+            h.set_ef(20)   # hnsw_config.go:138 default, also what the blob stores
+        h.stats(reset=True)
+        want = [h.search(q, k) for q in qs]
+        evals, exps = h.stats(reset=True)
+        gi, gs, gc = g.BatchSearch(qs, k, ef)
+        for j in range(len(qs)):
+            assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], want[j][0], want[j][1], f"n={n} d={d} m={metric} ef={ef} k={k} q{j}")
+        st = g.last_stats()
+        assert st["dist_evals"] == evals and st["expansions"] == exps, (st, evals, exps)
+    g.close()
+
+
+def test_hnsw_uniform_data_and_ties(cb, oracle):
+    """e2e/hnsw/e2e_hnsw.go shape (uniform data, ascending distances) + duplicated vectors (distance ties:
+    the Go-heap restatement decides, and the GPU replays the same heap algorithm)."""
+    n, d = 1500, 128
+    base = uniform(300, d, 5)
+    vecs = np.concatenate([base, base, base, base, base])   # every vector 5 times
+    ids = sparse_ids(n, 9)
+    h = oracle.Hnsw(d, 0)
+    h.build(ids, vecs, seed=4)
+    g = cb.Hnsw.Load(h.commit())
+    h.set_ef(50)
+    for q in uniform(10, d, QUERY_SEED):
+        wi, ws = h.search(q, 10)
+        hits = g.Search(q, 10, ef=50)
+        assert_same_hits([x.Id for x in hits], [x.Score for x in hits], wi, ws, "ties")
+        assert np.all(np.diff(ws) >= 0)
+    g.close()
+
+
+def test_hnsw_empty_and_malformed_blobs(cb, oracle):
+    h = oracle.Hnsw(32, 0)
+    g = cb.Hnsw.Load(h.commit())          # header only: `if xx.Len() == 0 { return nil }` hnsw_commit.go:82-84
+    assert g.Len() == 0 and g.Search(np.zeros(32, np.float32), 5) == []
+    g.close()
+    h2, _, _ = _build(oracle, 50, 16, 0, seed=2)
+    blob = h2.commit()
+    for bad in (blob[: len(blob) // 2], blob[:10], b""):
+        with pytest.raises(cb.ColttError):
+            cb.Hnsw.Load(bad)
+
+
+def test_hnsw_config3_shape_recall(cb, oracle):
+    """BASELINE config 3 shape (fp32, dim 768, efSearch 128, top-10) at an oracle-buildable N:
+    identical to the oracle walk, and recall@10 vs exact FLAT (edge/resultset.go:55-65) is high."""
+    n, d, k, ef = 6000, 768, 10, 128
+    h, ids, vecs = _build(oracle, n, d, 0, seed=77)
+    g = cb.Hnsw.Load(h.commit())
+    h.set_ef(ef)
+    flat = oracle.FlatStore(d, 0, 0)
+    flat.upsert(ids, vecs)
+    qs = normal(16, d, QUERY_SEED)
+    gi, gs, gc = g.BatchSearch(qs, k, ef)
+    rec = []
+    for j, q in enumerate(qs):
+        wi, ws = h.search(q, k)
+        assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], wi, ws, f"c3 q{j}")
+        fi, _ = flat.search_total_order(q, k, select_mode=1)
+        rec.append(oracle.compute_recall(fi, gi[j], k))
+    assert np.mean(rec) > 0.9
+    g.close()
