@@ -1,0 +1,109 @@
+"""Sharded search across the GPUs of one node: one process per GPU, rows partitioned one shard per
+GPU, ONE exchange step per batch — an all-gather of the per-shard top-k — then the K5 merge.
+
+Reference analogue: the 16 in-process shards of a vectorspace, each scanned into a shard-local queue
+and re-merged (edge/none_vectorstore.go:152-178); rows -> shard by pkg/sharding.ShardVertex
+(pkg/sharding/shard.go:34-41).  There is no other collective in the path.
+
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is plumbing only: the local
+search and the merge are injected callables — on a GPU box they are the C-ABI calls
+coltt_b200_store_search_dev / coltt_b200_merge_topk_dev.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+FNV_OFFSET = np.uint64(14695981039346656037)
+FNV_PRIME = np.uint64(1099511628211)
+
+# one hit on the wire == coltt_hit (include/coltt_b200.h): u64 id, f32 score, u32 slot
+HIT_DTYPE = np.dtype([("id", "<u8"), ("score", "<f4"), ("slot", "<u4")])
+
+
+def shard_vertex(ids, c: int = 16) -> np.ndarray:
+    """pkg/sharding.ShardVertex vectorised: FNV-1a 64 over the little-endian bytes of the id, mod c."""
+    x = np.ascontiguousarray(ids, dtype=np.uint64)
+    h = np.full(x.shape, FNV_OFFSET, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(8):
+            h ^= (x >> np.uint64(8 * i)) & np.uint64(0xFF)
+            h *= FNV_PRIME
+    return (h % np.uint64(c)).astype(np.int64)
+
+
+def gpu_of(ids, world: int) -> np.ndarray:
+    """Row -> GPU: the reference's shard identity folded onto the GPUs (ShardVertex(id,16) mod G)."""
+    return shard_vertex(ids, 16) % world
+
+
+class ShardedSearch:
+    """Per-rank driver of the sharded FLAT search.
+
+    local_search(queries[nq,dim] f32, k, select_mode) -> (hits[nq,k] HIT_DTYPE-shaped tensor, counts[nq] int32 tensor)
+    merge(gathered_hits[world,nq,k], gathered_counts[world,nq], k, select_mode) -> (hits[nq,k], counts[nq])
+    Both work on torch tensors living where the process group communicates (CUDA for NCCL, CPU for gloo);
+    hits travel as int32 [..., 4] views of coltt_hit.
+    """
+
+    def __init__(self, local_search: Callable, merge: Callable, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.local_search = local_search
+        self.merge = merge
+
+    def search(self, queries, k: int, select_mode: int):
+        import torch
+        hits, counts = self.local_search(queries, k, select_mode)
+        if self.world == 1:
+            return self.merge(hits.unsqueeze(0), counts.unsqueeze(0), k, select_mode)
+        nq = hits.shape[0]
+        # concatenated-along-dim-0 output: the layout both NCCL and gloo accept; viewed as [world, nq, ...]
+        gathered = torch.empty((self.world * nq,) + tuple(hits.shape[1:]), dtype=hits.dtype, device=hits.device)
+        gcounts = torch.empty((self.world * nq,), dtype=counts.dtype, device=counts.device)
+        # the one exchange step: per-shard top-k of every rank to every rank
+        self.dist.all_gather_into_tensor(gathered, hits.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(gcounts, counts.contiguous(), group=self.group)
+        return self.merge(gathered.view((self.world, nq) + tuple(hits.shape[1:])), gcounts.view(self.world, nq), k, select_mode)
+
+
+def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, stream=None):
+    """(local_search, merge) bound to a coltt_b200 VectorSpace on one GPU through the C-ABI."""
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", device_index)
+    mm = space.math_mode if math_mode is None else math_mode
+
+    def _stream_ptr():
+        return (stream or torch.cuda.current_stream(dev)).cuda_stream
+
+    def local_search(queries, k, select_mode):
+        q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries, np.float32))
+        q = q.to(dev, dtype=torch.float32).contiguous()
+        nq = q.shape[0]
+        hits = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
+        counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        _lib.check(L.coltt_b200_store_search_dev(space._h, q.data_ptr(), nq, k, select_mode, mm, hits.data_ptr(), counts.data_ptr(),
+                                                  _stream_ptr()))
+        return hits, counts
+
+    def merge(gathered, gcounts, k, select_mode):
+        world, nq = gathered.shape[0], gathered.shape[1]
+        out = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        _lib.check(L.coltt_b200_merge_topk_dev(device_index, gathered.data_ptr(), gcounts.data_ptr(), world, nq, gathered.shape[2], k,
+                                                select_mode, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
+        return out, cnt
+
+    return local_search, merge
+
+
+def unpack_hits(hits, counts):
+    """int32 [nq,k,4] coltt_hit tensor -> (ids u64 [nq,k], scores f32 [nq,k], counts)."""
+    h = hits.detach().cpu().contiguous().numpy().view(HIT_DTYPE).reshape(hits.shape[0], hits.shape[1])
+    return h["id"].copy(), h["score"].copy(), counts.detach().cpu().numpy()
