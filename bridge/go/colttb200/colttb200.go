@@ -1,0 +1,204 @@
+// Package colttb200 is the cgo shim that lets coltt's Go host code drive libcoltt_b200.so.
+//
+// It is WRITTEN BUT NOT COMPILED in this repository's build image (no Go toolchain, no network;
+// DESIGN.md §1).  It implements the search/ingest half of edge.vectorspace
+// (edge/vectorstore.go:30-49) and wraps vectorindex.Hnsw's Load/Search
+// (core/vectorindex/hnsw.go:243-278, hnsw_commit.go:164-278) over include/coltt_b200.h.
+// Metadata maps, the inverted index and filter expressions stay on the Go side: the shim hands
+// ids and vectors across the boundary and maps returned ids back to metadata.
+//
+//	build: CGO_CFLAGS="-I${COLTT_B200}/include" CGO_LDFLAGS="-L${COLTT_B200}/coltt_b200/lib -lcoltt_b200" go build ./...
+package colttb200
+
+/*
+#cgo LDFLAGS: -lcoltt_b200
+#include <stdlib.h>
+#include "coltt_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"runtime"
+	"unsafe"
+)
+
+// Select / math modes (coltt_select, coltt_math).
+const (
+	SelectCompat  = 0 // the reference's literal behaviour: K largest distances (SURVEY F1)
+	SelectNearest = 1
+	MathExact     = 0
+	MathFast      = 1
+)
+
+func lastErr(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return errors.New(C.GoString(C.coltt_b200_last_error()))
+}
+
+// Store is one edge collection's vectors on one GPU.
+type Store struct{ h *C.coltt_store }
+
+// NewStore replaces newNoneVectorstore / newF16Vectorstore / newBF16Vectorstore / newF8Vectorstore
+// (edge/vectorstore.go:62-85).  distance and quantization are the edgepb enum values.
+func NewStore(dim uint32, distance, quantization int32, device int32, capacityHint uint64) (*Store, error) {
+	cfg := C.coltt_store_cfg{dim: C.uint32_t(dim), metric: C.int32_t(distance), quant: C.int32_t(quantization),
+		device: C.int32_t(device), capacity_hint: C.uint64_t(capacityHint)}
+	var h *C.coltt_store
+	if err := lastErr(C.coltt_b200_store_create(&cfg, &h)); err != nil {
+		return nil, err
+	}
+	s := &Store{h: h}
+	runtime.SetFinalizer(s, func(s *Store) { s.Close() })
+	return s, nil
+}
+
+func (s *Store) Close() {
+	if s.h != nil {
+		C.coltt_b200_store_destroy(s.h)
+		s.h = nil
+	}
+}
+
+// ChangedVertex: edge/none_vectorstore.go:66-103 (normalize + Lower happen on the GPU).
+func (s *Store) ChangedVertex(id uint64, vector []float32) error {
+	return lastErr(C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&id)),
+		(*C.float)(unsafe.Pointer(&vector[0])), 1))
+}
+
+// ChangedVertices is the batched form (bulk load).
+func (s *Store) ChangedVertices(ids []uint64, vectors []float32) error {
+	if len(ids) == 0 {
+		return nil
+	}
+	return lastErr(C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])),
+		(*C.float)(unsafe.Pointer(&vectors[0])), C.size_t(len(ids))))
+}
+
+// RemoveVertex after dropFilter was resolved to ids (none_vectorstore.go:105-127).
+func (s *Store) RemoveVertex(ids []uint64) error {
+	if len(ids) == 0 {
+		return nil
+	}
+	return lastErr(C.coltt_b200_store_remove(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])), C.size_t(len(ids))))
+}
+
+// Hit is edge.SearchResultItem without the metadata map (the caller re-attaches it by Id).
+type Hit struct {
+	Id    uint64
+	Score float32
+}
+
+// VertexSearch: edge/none_vectorstore.go:129-180.  highCpu has no meaning on the GPU.
+func (s *Store) VertexSearch(target []float32, topK int, selectMode, mathMode int) ([]Hit, error) {
+	ids := make([]uint64, topK)
+	scores := make([]float32, topK)
+	var count C.int32_t
+	rc := C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1, C.int(topK), C.int(selectMode), C.int(mathMode),
+		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	if err := lastErr(rc); err != nil {
+		return nil, err
+	}
+	out := make([]Hit, int(count))
+	for i := range out {
+		out[i] = Hit{ids[i], scores[i]}
+	}
+	return out, nil
+}
+
+// FilterableVertexSearch: edge/none_vectorstore.go:182-253, given inverted.SearchWithExpression's ids.
+func (s *Store) FilterableVertexSearch(candidates []uint64, target []float32, topK int, selectMode int) ([]Hit, error) {
+	if len(candidates) == 0 {
+		return nil, nil
+	}
+	ids := make([]uint64, topK)
+	scores := make([]float32, topK)
+	var count C.int32_t
+	rc := C.coltt_b200_store_search_subset(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1,
+		(*C.uint64_t)(unsafe.Pointer(&candidates[0])), C.size_t(len(candidates)), C.int(topK), C.int(selectMode),
+		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	if err := lastErr(rc); err != nil {
+		return nil, err
+	}
+	out := make([]Hit, int(count))
+	for i := range out {
+		out[i] = Hit{ids[i], scores[i]}
+	}
+	return out, nil
+}
+
+// BatchVertexSearch is the new surface a micro-batcher in Edge.Search (edge/edge.go:610-690) would call.
+func (s *Store) BatchVertexSearch(targets []float32, nq, topK int, selectMode, mathMode int) ([]uint64, []float32, []int32, error) {
+	ids := make([]uint64, nq*topK)
+	scores := make([]float32, nq*topK)
+	counts := make([]int32, nq)
+	rc := C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&targets[0])), C.size_t(nq), C.int(topK), C.int(selectMode), C.int(mathMode),
+		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&counts[0])))
+	return ids, scores, counts, lastErr(rc)
+}
+
+// SaveVertex / LoadVertex: edge/none_vectorstore.go:308-516 (metaCount = 0; metadata is saved by the Go side).
+func (s *Store) SaveVertex() ([]byte, error) {
+	var n C.size_t
+	if err := lastErr(C.coltt_b200_store_export(s.h, nil, &n)); err != nil {
+		return nil, err
+	}
+	buf := make([]byte, int(n)+1)
+	if err := lastErr(C.coltt_b200_store_export(s.h, unsafe.Pointer(&buf[0]), &n)); err != nil {
+		return nil, err
+	}
+	return buf[:int(n)], nil
+}
+
+func (s *Store) LoadVertex(data []byte) error {
+	if len(data) == 0 {
+		return lastErr(C.coltt_b200_store_import(s.h, nil, 0))
+	}
+	return lastErr(C.coltt_b200_store_import(s.h, unsafe.Pointer(&data[0]), C.size_t(len(data))))
+}
+
+func (s *Store) LoadSize() (int64, error) {
+	var n C.uint64_t
+	err := lastErr(C.coltt_b200_store_size(s.h, &n))
+	return int64(n), err
+}
+
+// Hnsw wraps a device-resident vectorindex.Hnsw built from Hnsw.Commit(w, true).
+type Hnsw struct{ h *C.coltt_hnsw }
+
+// LoadHnsw: core/vectorindex/hnsw_commit.go:164-278.
+func LoadHnsw(commitBlob []byte, device int32) (*Hnsw, error) {
+	var h *C.coltt_hnsw
+	if err := lastErr(C.coltt_b200_hnsw_load(unsafe.Pointer(&commitBlob[0]), C.size_t(len(commitBlob)), C.int(device), &h)); err != nil {
+		return nil, err
+	}
+	g := &Hnsw{h: h}
+	runtime.SetFinalizer(g, func(g *Hnsw) { g.Close() })
+	return g, nil
+}
+
+func (g *Hnsw) Close() {
+	if g.h != nil {
+		C.coltt_b200_hnsw_destroy(g.h)
+		g.h = nil
+	}
+}
+
+// Search: core/vectorindex/hnsw.go:243-278 (ef <= 0 uses the ef stored in the blob).
+func (g *Hnsw) Search(query []float32, k int, ef int) ([]Hit, error) {
+	ids := make([]uint64, k)
+	scores := make([]float32, k)
+	var count C.int32_t
+	rc := C.coltt_b200_hnsw_search(g.h, (*C.float)(unsafe.Pointer(&query[0])), 1, C.int(k), C.int(ef),
+		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	if err := lastErr(rc); err != nil {
+		return nil, err
+	}
+	out := make([]Hit, int(count))
+	for i := range out {
+		out[i] = Hit{ids[i], scores[i]}
+	}
+	return out, nil
+}
