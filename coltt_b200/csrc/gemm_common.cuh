@@ -1,0 +1,333 @@
+// gemm_common.cuh — tcgen05 / TMA / mbarrier PTX wrappers and the fused threshold top-K' epilogue
+// shared by the one-CTA (gemm_filter.cu) and CTA-pair (gemm_filter2.cu) filter kernels.
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace coltt {
+
+static constexpr int kGemmThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+static constexpr int kBN = 256;            // shard rows per tile (MMA N): one 128-cycle tcgen05.mma per K step
+static constexpr int kBK = 64;             // fp16 elements per K block of the resident query tile (128-byte swizzle rows)
+static constexpr int kBKB = 32;            // fp16 elements per shard-tile stage (64-byte swizzle rows)
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA-pair commit: arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// SS-mode: D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate); SASS: UTCHMMA
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// CTA-pair load: data lands in THIS CTA's shared memory, completion is signalled on the barrier at `bar`
+// in the pair's leader (even) CTA — the peer bit of the barrier address is cleared as CUTLASS does.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+// order-preserving float <-> uint32 (for atomicMax on thresholds that may be negative)
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// K-major, 128B-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version(1)<<46 | SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// K-major, 64B-swizzled operand (8-row atoms of 512 B): SBO = 512>>4, SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+
+// key[c] for a per-lane dynamic c out of 32 registers: a 5-level select tree (31 SEL), no memory
+__device__ __forceinline__ float pick32(const float (&k)[32], uint32_t c) {
+  float a[16], b[8], d[4], e[2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = (c & 16u) ? k[i + 16] : k[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) b[i] = (c & 8u) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) d[i] = (c & 4u) ? b[i + 4] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; i++) e[i] = (c & 2u) ? d[i + 2] : d[i];
+  return (c & 1u) ? e[1] : e[0];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Epilogue of the filter GEMM (warps 2-5, thread = query).  For every 256-row tile: tcgen05.ld the
+// 128x256 fp32 accumulator 32 columns at a time, one FFMA turns each score into a "larger is better" key
+// (cosine: +-dot/||row||; L2: +-(2 dot - ||row||^2)), a max tree and ONE warp vote per 32 scores decide
+// whether anything beats the running K'-th bound held in a register; the rare survivors are appended to an
+// L2-resident per-(column,query) buffer.  top[] = this column's KP best keys (registers, sorted).
+// thr = max(top[KP-1], G), G = min over KP groups of columns of the best key any column of the group has
+// published: KP different columns each hold a row at least that good, so G bounds the shard-wide K'-th key.
+//   col / n_cols: this CTA's index among the CTAs that see this query, and how many there are
+//   tile0 / tile_stride: the tiles this CTA processes
+//   arrive_tempty(buf): releases accumulator `buf` to the MMA issuer (local or leader-CTA barrier)
+template <int KP, class ArriveFn>
+__device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tmem_base, float* coef_a, float* coef_b, uint64_t* tfull_bar,
+                                                ArriveFn arrive_tempty, uint32_t tile0, uint32_t tile_stride, uint32_t n_tiles,
+                                                uint32_t q_tile0, uint32_t col, uint32_t n_cols, uint32_t buf_slot, uint32_t prof_slot) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t C = p.cand_cap;
+  const uint32_t quarter = warp & 3;                   // TMEM lane quarter this warp may touch
+  const uint32_t ql = quarter * 32 + lane;             // query within the tile == TMEM lane
+  const uint32_t q = q_tile0 + ql;
+  const uint32_t et = threadIdx.x - 64;                // 0..127 among the epilogue threads
+  const bool q_valid = q < p.nq;
+  const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
+  float top[KP];
+#pragma unroll
+  for (int i = 0; i < KP; i++) top[i] = NEG_INF;
+  float my_best = NEG_INF;
+  uint32_t next_sweep = 1;
+  const bool sweeping = q_valid && n_cols >= (uint32_t)KP;
+  float thr = q_valid ? NEG_INF : POS_INF;
+  bool overflowed = false;
+  uint32_t cnt = 0;
+  GemmCand* my_buf = p.cand_buf + ((size_t)buf_slot * C) * 128 + ql;   // [cta][slot][128 queries], written rarely
+  float* my_pub = p.pub + (size_t)col * p.nq + q;                        // pub[column][query]
+  uint32_t ti = 0;
+  long long w_tfull = 0, t_start_e = clock64(), c_bar = 0, c_hot = 0, c_slow = 0, c_sweep = 0, n_slow = 0;
+
+  auto coef_store = [&](uint32_t idx, uint32_t row, float n2) {
+    float a = 0.0f, b = NEG_INF;
+    if (row < p.n_rows) {
+      if (p.metric == COLTT_COSINE) {
+        if (n2 > 0.0f) { a = p.nearest ? rsqrtf(n2) : -rsqrtf(n2); b = 0.0f; }
+        else b = p.nearest ? NEG_INF : POS_INF;       // zero row: NaN distance, last in T order
+      } else {
+        a = p.nearest ? 2.0f : -2.0f;
+        b = p.nearest ? -n2 : n2;
+      }
+    }
+    coef_a[idx] = a;
+    coef_b[idx] = b;
+  };
+  // ||row||^2 of the next tile is fetched while the current one is processed (two rows per thread)
+  float n2_a = 0.0f, n2_b = 0.0f;
+  {
+    const uint32_t ra = tile0 * kBN + et, rb2 = ra + 128;
+    if (tile0 < n_tiles) { if (ra < p.n_rows) n2_a = p.row_norm2[ra]; if (rb2 < p.n_rows) n2_b = p.row_norm2[rb2]; }
+  }
+  for (uint32_t t = tile0; t < n_tiles; t += tile_stride, ti++) {
+    const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
+    const uint32_t row0 = t * kBN;
+    const long long cb0 = clock64();
+    coef_store(et, row0 + et, n2_a);
+    coef_store(et + 128, row0 + et + 128, n2_b);
+    named_bar_sync(1, 128);                              // coefficients of this tile visible
+    c_bar += clock64() - cb0;
+    {
+      const uint32_t ra = (t + tile_stride) * kBN + et, rb2 = ra + 128;
+      n2_a = ra < p.n_rows ? p.row_norm2[ra] : 0.0f;
+      n2_b = rb2 < p.n_rows ? p.row_norm2[rb2] : 0.0f;
+    }
+    const long long ce0 = clock64();
+    mbar_wait(smem_u32(tfull_bar + buf), bph);
+    w_tfull += clock64() - ce0;
+    tc_fence_after();
+#pragma unroll 1
+    for (uint32_t half = 0; half < kBN / 32; half++) {
+      uint32_t v[32];
+      const long long cl0 = clock64();
+      tmem_ld32(tmem_base + ((quarter * 32) << 16) + buf * kBN + half * 32, v);
+      tmem_wait_ld();
+      if (half == kBN / 32 - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty(buf);               // accumulator free for tile ti+2
+      }
+      if (p.dbg_acc && q_valid) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+          const uint32_t row = row0 + half * 32 + c;
+          if (row < p.n_rows) p.dbg_acc[(size_t)q * p.n_rows + row] = __uint_as_float(v[c]);
+        }
+      }
+      if (p.dbg_flags & 1u) continue;                    // pipeline-speed probe: drain only
+      // hot path: 32 FFMA + a max tree + one vote; no per-element branches
+      const float4* ca = reinterpret_cast<const float4*>(coef_a + half * 32);
+      const float4* cb = reinterpret_cast<const float4*>(coef_b + half * 32);
+      float key[32];
+      float kmax = NEG_INF;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; c4++) {
+        const float4 a4 = ca[c4], b4 = cb[c4];
+        key[4 * c4 + 0] = fmaf(__uint_as_float(v[4 * c4 + 0]), a4.x, b4.x);
+        key[4 * c4 + 1] = fmaf(__uint_as_float(v[4 * c4 + 1]), a4.y, b4.y);
+        key[4 * c4 + 2] = fmaf(__uint_as_float(v[4 * c4 + 2]), a4.z, b4.z);
+        key[4 * c4 + 3] = fmaf(__uint_as_float(v[4 * c4 + 3]), a4.w, b4.w);
+        kmax = fmaxf(kmax, fmaxf(fmaxf(key[4 * c4 + 0], key[4 * c4 + 1]), fmaxf(key[4 * c4 + 2], key[4 * c4 + 3])));
+      }
+      const bool mine = kmax > thr;
+      const long long ch1 = clock64();
+      c_hot += ch1 - cl0;
+      if (__any_sync(0xffffffffu, mine)) {
+        // rare path, kept small: pass mask, then each lane walks its own set bits; the key of column c
+        // comes out of the 32 key registers through a select tree (no memory, no re-read)
+        n_slow++;
+        if (mine) {
+          uint32_t mask = 0;
+#pragma unroll
+          for (int c = 0; c < 32; c++) mask |= (key[c] > thr ? 1u : 0u) << c;
+          const uint32_t rb = row0 + half * 32;
+          while (mask) {
+            const uint32_t c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float kk = pick32(key, c);
+            if (kk > thr) {   // thr may have risen since the mask was taken
+              GemmCand e; e.key = kk; e.row = rb + c;
+              my_buf[(size_t)cnt * 128] = e;
+              cnt++;
+              if (kk > top[KP - 1]) {
+                top[KP - 1] = kk;
+#pragma unroll
+                for (int i = KP - 1; i > 0; --i) {
+                  const float hi = fmaxf(top[i - 1], top[i]), lo = fminf(top[i - 1], top[i]);
+                  top[i - 1] = hi;
+                  top[i] = lo;
+                }
+                thr = fmaxf(thr, top[KP - 1]);
+              }
+              if (kk > my_best) { my_best = kk; __stcg(my_pub, kk); }
+            }
+          }
+          // the buffer must keep room for the next 32 columns: drop what fell below the bound
+          if (cnt + 32 > C) {
+            uint32_t w2 = 0;
+            for (uint32_t s2 = 0; s2 < cnt; s2++) {
+              const GemmCand e = my_buf[(size_t)s2 * 128];   // written by this thread only
+              if (e.key >= thr) { my_buf[(size_t)w2 * 128] = e; w2++; }
+            }
+            cnt = w2;
+            if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
+              overflowed = true;
+              cnt = 0;
+              thr = POS_INF;
+            }
+          }
+        }
+        c_slow += clock64() - ch1;
+      }
+    }
+    const long long cs0 = clock64();
+    named_bar_sync(2, 128);                              // everyone is done reading this tile's coefficients
+    c_bar += clock64() - cs0;
+    // Cross-column bound on a doubling schedule (tiles 1,2,4,8,...): the bound moves like 1/rows-seen.
+    if (sweeping && !overflowed && ti == next_sweep) {
+      const long long cw0 = clock64();
+      next_sweep = ti * 2;
+      float gmax[KP];
+#pragma unroll
+      for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
+      for (uint32_t c0 = 0; c0 < n_cols; c0 += KP) {
+#pragma unroll
+        for (int i = 0; i < KP; i++) {
+          const float pv = c0 + i < n_cols ? __ldcg(p.pub + (size_t)(c0 + i) * p.nq + q) : NEG_INF;
+          gmax[i] = fmaxf(gmax[i], pv);   // fmaxf ignores the NaN "nothing published yet" marker
+        }
+      }
+      float G = gmax[0];
+#pragma unroll
+      for (int i = 1; i < KP; i++) G = fminf(G, gmax[i]);
+      thr = fmaxf(thr, G);
+      c_sweep += clock64() - cw0;
+    }
+  }
+  if (p.dbg_prof && et == 0) {
+    p.dbg_prof[(size_t)prof_slot * 8 + 5] = (unsigned long long)w_tfull;
+    p.dbg_prof[(size_t)prof_slot * 8 + 6] = (unsigned long long)(clock64() - t_start_e);
+    p.dbg_prof[(size_t)prof_slot * 8 + 7] = (unsigned long long)c_bar;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 0] = (unsigned long long)0;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 1] = (unsigned long long)c_hot;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 2] = (unsigned long long)c_sweep;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 3] = (unsigned long long)n_slow;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 4] = (unsigned long long)cnt;
+    p.dbg_prof2[(size_t)prof_slot * 8 + 5] = (unsigned long long)c_slow;
+  }
+  // ---- hand the survivors to rerank.cu: [query][column][slot]; publish the bound they were cut at
+  if (q_valid) {
+    GemmCand* out = p.cand_out + ((size_t)q * n_cols + col) * C;
+    uint32_t w = 0;
+    for (uint32_t s2 = 0; s2 < cnt; s2++) {
+      const GemmCand e = my_buf[(size_t)s2 * 128];
+      if (e.key >= thr) { out[w] = e; w++; }
+    }
+    p.cand_cnt[(size_t)q * n_cols + col] = overflowed ? 0xffffffffu : w;
+    if (!overflowed && thr > NEG_INF) atomicMax(p.g_thr + q, f2ord(thr));
+  }
+}
+
+}  // namespace coltt

@@ -1,0 +1,166 @@
+// gemm_filter2.cu — K2, CTA-pair variant (tcgen05 cta_group::2) for batches of more than 128 queries.
+//
+// Same role as gemm_filter.cu (the batched query x shard filter behind COLTT_MATH_FAST), but two CTAs of
+// one thread-block cluster work as a pair on every shard tile:
+//   * M = 256 queries: CTA rank r keeps queries [256*y + 128*r, +128) resident in its shared memory and
+//     gets the matching 128 x 256 accumulator in its own tensor memory;
+//   * every 256-row shard tile is loaded ONCE for both query halves: each CTA TMA-loads 128 of the 256 rows
+//     (8 KB per 32-element K stage) and tcgen05.mma.cta_group::2 reads both halves — per SM the L2->SM
+//     traffic and the shared-memory operand reads of B are halved (ncu on the one-CTA kernel showed an
+//     M128xN256 SS MMA costs ~280 cycles against the 128-cycle math floor, shared-memory-read bound);
+//   * the leader (rank 0) issues the MMAs; tcgen05.commit multicasts "stage free" / "accumulator ready"
+//     to both CTAs' mbarriers; both CTAs' epilogue warps release accumulators on the leader's barrier.
+// Warp roles per CTA as in gemm_filter.cu; the epilogue is the shared filter_epilogue().
+#include "gemm_common.cuh"
+#include "store.h"
+
+namespace coltt {
+
+template <int KP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_q,
+                        const __grid_constant__ CUtensorMap tmap_pf, GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t NS = p.n_stages, KB = p.kblocks;
+  constexpr uint32_t HALF_ROWS = kBN / 2;                   // shard rows each CTA of the pair loads
+  constexpr uint32_t STAGE_BYTES = HALF_ROWS * kBKB * 2;    // 128 rows x 64 B = 8 KB per CTA per stage
+  constexpr uint32_t ABLK_BYTES = 128 * kBK * 2;
+  const uint32_t NSTEP = KB * (kBK / kBKB);
+
+  uint8_t* a_smem = smem;
+  uint8_t* b_stages = a_smem + (size_t)KB * ABLK_BYTES;     // [NS][128 rows][64 B], 64B-swizzled
+  float* coef_a = reinterpret_cast<float*>(b_stages + (size_t)NS * STAGE_BYTES);
+  float* coef_b = coef_a + kBN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(coef_b + kBN);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tfull_bar = empty_bar + NS;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;   // [2]   (used in the leader only)
+  uint64_t* a_bar = tempty_bar + 2;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  const uint32_t rank = cluster_ctarank();                  // 0 = leader
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t n_tiles = (p.n_rows + kBN - 1) / kBN;
+  const uint32_t q_tile0 = blockIdx.y * 256 + rank * 128;
+  const uint32_t cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (uint32_t s = 0; s < NS; s++) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(smem_u32(tfull_bar + b), 1); mbar_init(smem_u32(tempty_bar + b), 8); }  // 4 warps x 2 CTAs
+    mbar_init(smem_u32(a_bar), 1);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_pf) : "memory");
+  }
+  if (warp == 1) {   // the same warp of both CTAs allocates all 512 columns in both tensor memories
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // each CTA's own query half: resident A operand
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(smem_u32(a_bar), KB * ABLK_BYTES);
+    for (uint32_t kb = 0; kb < KB; kb++)
+      tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)(kb * kBK), (int)q_tile0, smem_u32(a_bar));
+    mbar_wait(smem_u32(a_bar), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // barriers initialised and both query halves resident before anything crosses CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own half of every shard tile) =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      long long w_empty = 0, t_start = clock64();
+      const int row_off = (int)(rank * HALF_ROWS);
+      if (pair < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(pair * kBN) + row_off);
+      for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+        const uint32_t tp = t + n_pairs;
+        for (uint32_t st = 0; st < NSTEP; st++, it++) {
+          if (tp < n_tiles && (st & 1) == 0) tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), (int)(tp * kBN) + row_off);
+          const uint32_t s = it % NS, ph = (it / NS) & 1;
+          const long long c0 = clock64();
+          while (!mbar_try_wait(smem_u32(empty_bar + s), ph ^ 1)) __nanosleep(32);
+          w_empty += clock64() - c0;
+          // the leader's barrier collects both halves: it expects 2 x STAGE_BYTES, each CTA's load signals it
+          if (rank == 0) mbar_arrive_expect_tx(smem_u32(full_bar + s), 2 * STAGE_BYTES);
+          tma_load_2d_pair(smem_u32(b_stages + (size_t)s * STAGE_BYTES), &tmap, (int)(st * kBKB), (int)(t * kBN) + row_off, smem_u32(full_bar + s));
+        }
+      }
+      if (p.dbg_prof) {
+        p.dbg_prof[(size_t)cta_lin * 8 + 0] = (unsigned long long)w_empty;
+        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(clock64() - t_start);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      // M = 256 (M>>4 = 16 at bit 24), N = 256
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((256u >> 4) << 24);
+      uint32_t it = 0, ti = 0;
+      long long w_tempty = 0, w_full = 0, t_start = clock64();
+      const uint32_t a_addr = smem_u32(a_smem);
+      for (uint32_t t = pair; t < n_tiles; t += n_pairs, ti++) {
+        const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
+        const long long c0 = clock64();
+        while (!mbar_try_wait(smem_u32(tempty_bar + buf), bph ^ 1)) __nanosleep(20);   // both CTAs' epilogues drained it
+        w_tempty += clock64() - c0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        for (uint32_t st = 0; st < NSTEP; st++, it++) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1;
+          const long long c1 = clock64();
+          while (!mbar_try_wait(smem_u32(full_bar + s), ph)) __nanosleep(20);
+          w_full += clock64() - c1;
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(b_stages + (size_t)s * STAGE_BYTES);
+          const uint32_t a_blk = a_addr + (st >> 1) * ABLK_BYTES + (st & 1) * 64;
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t j = 0; j < kBKB / 16; j++)
+              umma_f16_ss_pair(d_tmem, make_desc_sw128(a_blk + j * 32), make_desc_sw64(b_addr + j * 32), idesc, (st | j) != 0 ? 1u : 0u);
+            umma_commit_pair(smem_u32(empty_bar + s), 3);          // stage free in both CTAs
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(smem_u32(tfull_bar + buf), 3);   // accumulator ready in both CTAs
+        __syncwarp();
+      }
+      if (p.dbg_prof && lane == 0) {
+        p.dbg_prof[(size_t)cta_lin * 8 + 2] = (unsigned long long)w_tempty;
+        p.dbg_prof[(size_t)cta_lin * 8 + 3] = (unsigned long long)w_full;
+        p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(clock64() - t_start);
+      }
+    }
+  } else {
+    auto arrive = [&](uint32_t buf) { mbar_arrive_cluster(smem_u32(tempty_bar + buf), 0); };   // on the leader's barrier
+    filter_epilogue<KP>(p, tmem_base, coef_a, coef_b, tfull_bar, arrive, pair, n_pairs, n_tiles, q_tile0, pair, n_pairs, cta_lin, cta_lin);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // nobody leaves while the peer may still read its shared memory or signal its barriers
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+int launch_gemm_filter_pair(const CUtensorMap& tm, const CUtensorMap& tmq, const CUtensorMap& tmpf, const GemmParams& p, const GemmPlan& plan,
+                            cudaStream_t stream) {
+  dim3 grid(plan.grid_x, plan.grid_y);
+  if (plan.kprime == 16) {
+    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    gemm_filter_pair_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
+  } else {
+    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    gemm_filter_pair_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
+  }
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  return COLTT_OK;
+}
+
+}  // namespace coltt

@@ -74,19 +74,23 @@ struct GemmParams {
   int metric, nearest;
   uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over CTAs), zero-initialised
   float* pub;                // [grid_x][nq] best key each CTA has seen per query, initialised to NaN
+  GemmCand* cand_buf;        // scratch [grid_y*grid_x][cand_cap][128]: per-(CTA,query) candidate buffers
   GemmCand* cand_out;        // [nq][grid_x][cand_cap]
   uint32_t* cand_cnt;        // [nq][grid_x]
   uint32_t kblocks, kprime, cand_cap, n_stages;  // filled from the plan
   float* dbg_acc;            // nullable (tests): raw accumulators [nq][n_rows]
   unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
+  unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
+  uint32_t mma_split;        // independent accumulation chains per tile (1, 2 or 4)
   uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe)
 };
 struct GemmPlan {
-  uint32_t kblocks, kprime, cand_cap, n_stages, grid_x, grid_y, q_stride;
+  uint32_t kblocks, kprime, cand_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
   size_t smem_bytes;
 };
 int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
 int launch_gemm_filter(const GemmParams& p, const GemmPlan& plan, const void* d_rows, uint32_t row_stride, cudaStream_t stream);
+uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows);
 
 struct RerankParams {
   uint32_t nq, k, dim, q_stride, row_stride, grid_x, cand_cap;

@@ -408,11 +408,13 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = c.q_n2.ensure(nq * 4); if (rc) return rc;
   rc = c.q_f16.ensure(nq * (size_t)gp.q_stride * 2); if (rc) return rc;
   rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
-  rc = c.cand.ensure(nq * (size_t)gp.grid_x * gp.cand_cap * sizeof(GemmCand)); if (rc) return rc;
-  rc = c.cand_cnt.ensure(nq * (size_t)gp.grid_x * 4); if (rc) return rc;
+  const uint32_t n_cols = gemm_filter_cols(gp, (uint32_t)n_rows);   // CTAs that see one query
+  rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_cap * sizeof(GemmCand)); if (rc) return rc;
+  rc = c.cand_cnt.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
   rc = c.h_flags.ensure(nq * 4); if (rc) return rc;
-  rc = c.pub.ensure(nq * (size_t)gp.grid_x * 4); if (rc) return rc;
+  rc = c.pub.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
+  rc = c.cand_buf.ensure((size_t)gp.grid_x * gp.grid_y * gp.cand_cap * 128 * sizeof(GemmCand)); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[0], st);
   PrepParams pp{};
   pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
@@ -422,29 +424,32 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride;
   rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
   COLTT_CUDA(cudaMemsetAsync(c.g_thr.p, 0, nq * 4, st));
-  COLTT_CUDA(cudaMemsetAsync(c.cand_cnt.p, 0, nq * (size_t)gp.grid_x * 4, st));
-  COLTT_CUDA(cudaMemsetAsync(c.pub.p, 0xff, nq * (size_t)gp.grid_x * 4, st));  // 0xffffffff = -NaN: never > anything, i.e. "nothing yet"
+  COLTT_CUDA(cudaMemsetAsync(c.cand_cnt.p, 0, nq * (size_t)n_cols * 4, st));
+  COLTT_CUDA(cudaMemsetAsync(c.pub.p, 0xff, nq * (size_t)n_cols * 4, st));  // 0xffffffff = -NaN: never > anything, i.e. "nothing yet"
   if (timed) cudaEventRecord(c.ev[1], st);
   GemmParams g{};
   g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
   g.row_norm2 = d_norm2; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
-  g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p;
+  g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p; g.cand_buf = (GemmCand*)c.cand_buf.p;
   {
     static const char* prof_env = getenv("COLTT_DEBUG_PROF");
     static const char* flags_env = getenv("COLTT_DEBUG_FLAGS");
     g.dbg_flags = flags_env ? (uint32_t)atoi(flags_env) : 0u;
+    static const char* split_env = getenv("COLTT_MMA_SPLIT");
+    g.mma_split = split_env ? (uint32_t)atoi(split_env) : 4u;
+    if (g.mma_split != 1 && g.mma_split != 2 && g.mma_split != 4) g.mma_split = 4;
     if (prof_env) {
-      rc = c.prof.ensure((size_t)gp.grid_x * gp.grid_y * 8 * 8); if (rc) return rc;
-      COLTT_CUDA(cudaMemsetAsync(c.prof.p, 0, (size_t)gp.grid_x * gp.grid_y * 8 * 8, st));
+      rc = c.prof.ensure((size_t)gp.grid_x * gp.grid_y * 16 * 8); if (rc) return rc;
+      COLTT_CUDA(cudaMemsetAsync(c.prof.p, 0, (size_t)gp.grid_x * gp.grid_y * 16 * 8, st));
       g.dbg_prof = (unsigned long long*)c.prof.p;
+      g.dbg_prof2 = g.dbg_prof + (size_t)gp.grid_x * gp.grid_y * 8;
     }
   }
   rc = launch_gemm_filter(g, gp, d_rows, row_stride, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
   r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
-  const uint32_t n_tiles = ((uint32_t)n_rows + 63) / 64;
-  r.grid_x = gp.grid_x < n_tiles ? gp.grid_x : n_tiles; r.cand_cap = gp.cand_cap;
+  r.grid_x = n_cols; r.cand_cap = gp.cand_cap;
   r.metric = cfg.metric; r.nearest = nearest; r.elem = elem;
   r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.rows = d_rows; r.row_norm2 = d_norm2; r.ids = d_ids;
   r.cand_in = (const GemmCand*)c.cand.p; r.cand_cnt = (const uint32_t*)c.cand_cnt.p; r.g_thr = (const uint32_t*)c.g_thr.p;
@@ -455,13 +460,18 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
     static int printed = 0;
     COLTT_CUDA(cudaStreamSynchronize(st));
     if (printed++ == 3) {   // a warmed-up step
-      std::vector<unsigned long long> h((size_t)gp.grid_x * gp.grid_y * 8);
+      const size_t nc = (size_t)gp.grid_x * gp.grid_y;
+      std::vector<unsigned long long> h(nc * 16);
       COLTT_CUDA(cudaMemcpy(h.data(), c.prof.p, h.size() * 8, cudaMemcpyDeviceToHost));
-      const char* names[8] = {"prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total", "epi_wait_tfull", "epi_total", "-"};
-      for (int k2 = 0; k2 < 7; k2++) {
+      const char* names[16] = {"prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "mma_total", "epi_wait_tfull", "epi_total", "epi_bars",
+                               "epi_tmem_ld", "epi_hot_math", "epi_bar2+sweep", "n_slow_entries", "final_cnt", "epi_slow_path", "-", "-"};
+      for (int k2 = 0; k2 < 14; k2++) {
         double sum = 0, mx = 0;
-        for (size_t i = 0; i < h.size() / 8; i++) { sum += (double)h[i * 8 + k2]; if ((double)h[i * 8 + k2] > mx) mx = (double)h[i * 8 + k2]; }
-        fprintf(stderr, "[coltt prof] %-16s avg %.0f max %.0f cycles\n", names[k2], sum / (h.size() / 8), mx);
+        for (size_t i = 0; i < nc; i++) {
+          const double v = (double)(k2 < 8 ? h[i * 8 + k2] : h[nc * 8 + i * 8 + (k2 - 8)]);
+          sum += v; if (v > mx) mx = v;
+        }
+        fprintf(stderr, "[coltt prof] split=%u %-16s avg %.0f max %.0f\n", g.mma_split, names[k2], sum / nc, mx);
       }
     }
   }

@@ -40,7 +40,7 @@ struct SearchCtx {
   cudaStream_t last_stream = nullptr;
   bool used = false, have_times = false;
   float ms[4] = {0, 0, 0, 0};
-  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof;
+  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf;
   PinnedBuf h_flags;
   PinnedBuf h_q, h_out;
   ~SearchCtx();
