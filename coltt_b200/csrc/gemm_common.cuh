@@ -7,7 +7,9 @@
 
 namespace coltt {
 
-static constexpr int kGemmThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+static constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two sets of four)
+static constexpr int kEpiThreads = 256;
+static constexpr int kEpiSets = 2;         // each set owns half of every tile's columns and its own per-query state
 static constexpr int kBN = 256;            // shard rows per tile (MMA N): one 128-cycle tcgen05.mma per K step
 static constexpr int kBK = 64;             // fp16 elements per K block of the resident query tile (128-byte swizzle rows)
 static constexpr int kBKB = 32;            // fp16 elements per shard-tile stage (64-byte swizzle rows)
@@ -139,12 +141,18 @@ template <int KP, class ArriveFn>
 __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tmem_base, float* coef_a, float* coef_b, uint64_t* tfull_bar,
                                                 ArriveFn arrive_tempty, uint32_t tile0, uint32_t tile_stride, uint32_t n_tiles,
                                                 uint32_t q_tile0, uint32_t col, uint32_t n_cols, uint32_t buf_slot, uint32_t prof_slot) {
+  // col / n_cols / buf_slot arrive per CTA and are refined per epilogue set below
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t C = p.cand_cap;
   const uint32_t quarter = warp & 3;                   // TMEM lane quarter this warp may touch
+  const uint32_t set = (warp - 2) >> 2;                // warps 2-5: columns 0-127 of every tile; warps 6-9: 128-255
   const uint32_t ql = quarter * 32 + lane;             // query within the tile == TMEM lane
   const uint32_t q = q_tile0 + ql;
-  const uint32_t et = threadIdx.x - 64;                // 0..127 among the epilogue threads
+  const uint32_t et = threadIdx.x - 64;                // 0..255 among the epilogue threads
+  constexpr uint32_t CHUNKS = kBN / 32 / kEpiSets;     // 32-column chunks per set per tile
+  col = col * kEpiSets + set;                          // every set is its own "column" of candidates / published maxima
+  n_cols *= kEpiSets;
+  buf_slot = buf_slot * kEpiSets + set;
   const bool q_valid = q < p.nq;
   const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
   float top[KP];
@@ -175,39 +183,37 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     coef_a[idx] = a;
     coef_b[idx] = b;
   };
-  // ||row||^2 of the next tile is fetched while the current one is processed (two rows per thread)
-  float n2_a = 0.0f, n2_b = 0.0f;
+  // ||row||^2 of the next tile is fetched while the current one is processed (one row per epilogue thread)
+  float n2_a = 0.0f;
   {
-    const uint32_t ra = tile0 * kBN + et, rb2 = ra + 128;
-    if (tile0 < n_tiles) { if (ra < p.n_rows) n2_a = p.row_norm2[ra]; if (rb2 < p.n_rows) n2_b = p.row_norm2[rb2]; }
+    const uint32_t ra = tile0 * kBN + et;
+    if (tile0 < n_tiles && ra < p.n_rows) n2_a = p.row_norm2[ra];
   }
   for (uint32_t t = tile0; t < n_tiles; t += tile_stride, ti++) {
     const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
     const uint32_t row0 = t * kBN;
     const long long cb0 = clock64();
     coef_store(et, row0 + et, n2_a);
-    coef_store(et + 128, row0 + et + 128, n2_b);
-    named_bar_sync(1, 128);                              // coefficients of this tile visible
+    named_bar_sync(1, kEpiThreads);                      // coefficients of this tile visible
     c_bar += clock64() - cb0;
     {
-      const uint32_t ra = (t + tile_stride) * kBN + et, rb2 = ra + 128;
+      const uint32_t ra = (t + tile_stride) * kBN + et;
       n2_a = ra < p.n_rows ? p.row_norm2[ra] : 0.0f;
-      n2_b = rb2 < p.n_rows ? p.row_norm2[rb2] : 0.0f;
     }
     const long long ce0 = clock64();
     mbar_wait(smem_u32(tfull_bar + buf), bph);
     w_tfull += clock64() - ce0;
     tc_fence_after();
 #pragma unroll 1
-    for (uint32_t half = 0; half < kBN / 32; half++) {
+    for (uint32_t half = set * CHUNKS; half < (set + 1) * CHUNKS; half++) {
       uint32_t v[32];
       const long long cl0 = clock64();
       tmem_ld32(tmem_base + ((quarter * 32) << 16) + buf * kBN + half * 32, v);
       tmem_wait_ld();
-      if (half == kBN / 32 - 1) {
+      if (half == (set + 1) * CHUNKS - 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_tempty(buf);               // accumulator free for tile ti+2
+        if (lane == 0) arrive_tempty(buf);               // this warp is done with the accumulator of tile ti
       }
       if (p.dbg_acc && q_valid) {
 #pragma unroll
@@ -265,11 +271,16 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
             }
           }
           // the buffer must keep room for the next 32 columns: drop what fell below the bound
+          // (rare: the buffer is sized so that a typical scan never fills it); loads go out 8 at a time
           if (cnt + 32 > C) {
             uint32_t w2 = 0;
-            for (uint32_t s2 = 0; s2 < cnt; s2++) {
-              const GemmCand e = my_buf[(size_t)s2 * 128];   // written by this thread only
-              if (e.key >= thr) { my_buf[(size_t)w2 * 128] = e; w2++; }
+            for (uint32_t s0 = 0; s0 < cnt; s0 += 8) {
+              GemmCand e8[8];
+#pragma unroll
+              for (int u = 0; u < 8; u++) if (s0 + u < cnt) e8[u] = my_buf[(size_t)(s0 + u) * 128];   // written by this thread only
+#pragma unroll
+              for (int u = 0; u < 8; u++)
+                if (s0 + u < cnt && e8[u].key >= thr) { my_buf[(size_t)w2 * 128] = e8[u]; w2++; }
             }
             cnt = w2;
             if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
@@ -283,7 +294,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
       }
     }
     const long long cs0 = clock64();
-    named_bar_sync(2, 128);                              // everyone is done reading this tile's coefficients
+    named_bar_sync(2, kEpiThreads);                      // everyone is done reading this tile's coefficients
     c_bar += clock64() - cs0;
     // Cross-column bound on a doubling schedule (tiles 1,2,4,8,...): the bound moves like 1/rows-seen.
     if (sweeping && !overflowed && ti == next_sweep) {
@@ -306,7 +317,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
       c_sweep += clock64() - cw0;
     }
   }
-  if (p.dbg_prof && et == 0) {
+  if (p.dbg_prof && et == 0) {   // set 0, quarter 2's first lane
     p.dbg_prof[(size_t)prof_slot * 8 + 5] = (unsigned long long)w_tfull;
     p.dbg_prof[(size_t)prof_slot * 8 + 6] = (unsigned long long)(clock64() - t_start_e);
     p.dbg_prof[(size_t)prof_slot * 8 + 7] = (unsigned long long)c_bar;
@@ -319,12 +330,18 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
   }
   // ---- hand the survivors to rerank.cu: [query][column][slot]; publish the bound they were cut at
   if (q_valid) {
-    GemmCand* out = p.cand_out + ((size_t)q * n_cols + col) * C;
+    const uint32_t CO = p.cand_out_cap;
+    GemmCand* out = p.cand_out + ((size_t)q * n_cols + col) * CO;
     uint32_t w = 0;
-    for (uint32_t s2 = 0; s2 < cnt; s2++) {
-      const GemmCand e = my_buf[(size_t)s2 * 128];
-      if (e.key >= thr) { out[w] = e; w++; }
+    for (uint32_t s0 = 0; s0 < cnt; s0 += 8) {
+      GemmCand e8[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (s0 + u < cnt) e8[u] = my_buf[(size_t)(s0 + u) * 128];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (s0 + u < cnt && e8[u].key >= thr) { if (w < CO) out[w] = e8[u]; w++; }
     }
+    if (w > CO) overflowed = true;   // more survivors than the hand-off slot holds: exact path for this query
     p.cand_cnt[(size_t)q * n_cols + col] = overflowed ? 0xffffffffu : w;
     if (!overflowed && thr > NEG_INF) atomicMax(p.g_thr + q, f2ord(thr));
   }

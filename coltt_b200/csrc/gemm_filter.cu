@@ -64,7 +64,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (uint32_t s = 0; s < NS; s++) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-    for (uint32_t b = 0; b < 2; b++) { mbar_init(smem_u32(tfull_bar + b), 1); mbar_init(smem_u32(tempty_bar + b), 4); }
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(smem_u32(tfull_bar + b), 1); mbar_init(smem_u32(tempty_bar + b), 8); }
     mbar_init(smem_u32(a_bar), 1);
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -189,7 +189,8 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
   const uint32_t kblocks = (dim + kBK - 1) / kBK;
   if (k > 24) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 24 is served by the exact path");
   const uint32_t kprime = k <= 10 ? 16 : 32;         // K' (register-resident per query); margin for the certificate
-  const uint32_t cap = 3 * kprime + 32;              // candidate slots per (CTA, query) in global memory
+  const uint32_t cap = 256;                          // working slots per (CTA set, query) in L2-resident global memory
+  const uint32_t out_cap = 2 * kprime + 16;          // survivors handed to rerank.cu per (CTA set, query)
   static const char* pair_env = getenv("COLTT_FAST_PAIR");
   const bool pair = nq > 128 && !(pair_env && atoi(pair_env) == 0);   // CTA pairs (cta_group::2) once there are two query tiles
   const size_t a_bytes = (size_t)kblocks * 128 * kBK * 2;
@@ -203,6 +204,7 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
   plan->kblocks = kblocks;
   plan->kprime = kprime;
   plan->cand_cap = cap;
+  plan->cand_out_cap = out_cap;
   plan->n_stages = ns;
   plan->pair = pair ? 1 : 0;
   if (pair) {
@@ -210,7 +212,7 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
     uint32_t pairs = (uint32_t)(n_sms / 2) / plan->grid_y;
     if (pairs < 1) pairs = 1;
     plan->grid_x = 2 * pairs;              // CTAs along x: (pair, rank)
-    plan->n_cols = pairs;                  // CTAs that see one query
+    plan->n_cols = pairs;                  // CTAs that see one query (x2 epilogue sets, see gemm_filter_cols)
   } else {
     plan->grid_y = (nq + 127) / 128;
     plan->grid_x = n_sms / plan->grid_y;
@@ -241,14 +243,14 @@ static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 // cand_out / cand_cnt / pub)
 uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows) {
   const uint32_t n_tiles = (n_rows + kBN - 1) / kBN;
-  return plan.n_cols < n_tiles ? plan.n_cols : n_tiles;
+  return (plan.n_cols < n_tiles ? plan.n_cols : n_tiles) * kEpiSets;
 }
 
 int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const void* d_rows, uint32_t row_stride, cudaStream_t stream) {
   CUtensorMap tm, tmq, tmpf;
   GemmPlan plan = plan_in;
   const uint32_t n_tiles = (p_in.n_rows + kBN - 1) / kBN;
-  const uint32_t cols = gemm_filter_cols(plan, p_in.n_rows);
+  const uint32_t cols = gemm_filter_cols(plan, p_in.n_rows) / kEpiSets;   // CTAs (or pairs) along x
   // shard tile stages: 256 (or 128 per CTA of a pair) rows x 32 fp16 (64 B), 64B swizzle
   int rc = encode_map(&tm, d_rows, p_in.dim, p_in.n_rows, row_stride, kBKB, plan.pair ? kBN / 2 : kBN, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
@@ -259,7 +261,7 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, kBK, 128, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   GemmParams p = p_in;
-  p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.n_stages = plan.n_stages;
+  p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.cand_out_cap = plan.cand_out_cap; p.n_stages = plan.n_stages;
   if (plan.pair) {
     plan.grid_x = 2 * cols;
     return launch_gemm_filter_pair(tm, tmq, tmpf, p, plan, stream);

@@ -48,7 +48,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 
   if (warp == 0 && lane == 0) {
     for (uint32_t s = 0; s < NS; s++) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
-    for (uint32_t b = 0; b < 2; b++) { mbar_init(smem_u32(tfull_bar + b), 1); mbar_init(smem_u32(tempty_bar + b), 8); }  // 4 warps x 2 CTAs
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(smem_u32(tfull_bar + b), 1); mbar_init(smem_u32(tempty_bar + b), 16); }  // 8 warps x 2 CTAs
     mbar_init(smem_u32(a_bar), 1);
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");

@@ -77,7 +77,7 @@ struct GemmParams {
   GemmCand* cand_buf;        // scratch [grid_y*grid_x][cand_cap][128]: per-(CTA,query) candidate buffers
   GemmCand* cand_out;        // [nq][grid_x][cand_cap]
   uint32_t* cand_cnt;        // [nq][grid_x]
-  uint32_t kblocks, kprime, cand_cap, n_stages;  // filled from the plan
+  uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages;  // filled from the plan
   float* dbg_acc;            // nullable (tests): raw accumulators [nq][n_rows]
   unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
   unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
@@ -85,7 +85,7 @@ struct GemmParams {
   uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe)
 };
 struct GemmPlan {
-  uint32_t kblocks, kprime, cand_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
+  uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
   size_t smem_bytes;
 };
 int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);

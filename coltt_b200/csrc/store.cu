@@ -409,12 +409,12 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = c.q_f16.ensure(nq * (size_t)gp.q_stride * 2); if (rc) return rc;
   rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
   const uint32_t n_cols = gemm_filter_cols(gp, (uint32_t)n_rows);   // CTAs that see one query
-  rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_cap * sizeof(GemmCand)); if (rc) return rc;
+  rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_out_cap * sizeof(GemmCand)); if (rc) return rc;
   rc = c.cand_cnt.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
   rc = c.h_flags.ensure(nq * 4); if (rc) return rc;
   rc = c.pub.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
-  rc = c.cand_buf.ensure((size_t)gp.grid_x * gp.grid_y * gp.cand_cap * 128 * sizeof(GemmCand)); if (rc) return rc;
+  rc = c.cand_buf.ensure((size_t)gp.grid_x * gp.grid_y * 2 * gp.cand_cap * 128 * sizeof(GemmCand)); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[0], st);
   PrepParams pp{};
   pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
@@ -449,7 +449,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
   r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
-  r.grid_x = n_cols; r.cand_cap = gp.cand_cap;
+  r.grid_x = n_cols; r.cand_cap = gp.cand_out_cap;
   r.metric = cfg.metric; r.nearest = nearest; r.elem = elem;
   r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.rows = d_rows; r.row_norm2 = d_norm2; r.ids = d_ids;
   r.cand_in = (const GemmCand*)c.cand.p; r.cand_cnt = (const uint32_t*)c.cand_cnt.p; r.g_thr = (const uint32_t*)c.g_thr.p;
