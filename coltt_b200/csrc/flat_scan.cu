@@ -52,15 +52,24 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   uintptr_t st = reinterpret_cast<uintptr_t>(bars + W * S);
   uint8_t* stages = reinterpret_cast<uint8_t*>((st + 127) & ~uintptr_t(127));  // [W][S][16][RS]
 
-  const uint32_t q0 = blockIdx.y * QT;
-  const uint32_t nqt = p.nq - q0 < (uint32_t)QT ? p.nq - q0 : (uint32_t)QT;
-  for (uint32_t i = threadIdx.x; i < QT * p.q_stride; i += blockDim.x) {
-    uint32_t qi = i / p.q_stride, d = i - qi * p.q_stride;
-    q_s[i] = qi < nqt ? p.queries[(size_t)(q0 + qi) * p.q_stride + d] : 0.0f;
-  }
-  if (threadIdx.x < 8) qn_s[threadIdx.x] = (threadIdx.x < nqt && METRIC == COLTT_COSINE) ? p.q_norm2[q0 + threadIdx.x] : 0.0f;
   if (ELEM == ELEM_F8C)
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __uint_as_float(f8_compat_decode_bits((uint8_t)i));
+  // Query groups of QT: grid.y groups run side by side, each CTA loops over the rest.  With `n_active`
+  // the number of queries lives on the device (the FAST path's exact re-run of uncertified queries is
+  // enqueued unconditionally and costs one empty wave when there is nothing to do); `q_map` then says
+  // which prepared query each compact index stands for.
+  const uint32_t nq_eff = p.n_active ? *p.n_active : p.nq;
+  for (uint32_t q0 = blockIdx.y * QT; q0 < nq_eff; q0 += gridDim.y * QT) {
+  const uint32_t nqt = nq_eff - q0 < (uint32_t)QT ? nq_eff - q0 : (uint32_t)QT;
+  for (uint32_t i = threadIdx.x; i < QT * p.q_stride; i += blockDim.x) {
+    uint32_t qi = i / p.q_stride, d = i - qi * p.q_stride;
+    const uint32_t qsrc = qi < nqt ? (p.q_map ? p.q_map[q0 + qi] : q0 + qi) : 0u;
+    q_s[i] = qi < nqt ? p.queries[(size_t)qsrc * p.q_stride + d] : 0.0f;
+  }
+  if (threadIdx.x < 8) {
+    const uint32_t qsrc = threadIdx.x < nqt ? (p.q_map ? p.q_map[q0 + threadIdx.x] : q0 + threadIdx.x) : 0u;
+    qn_s[threadIdx.x] = (threadIdx.x < nqt && METRIC == COLTT_COSINE) ? p.q_norm2[qsrc] : 0.0f;
+  }
   if (lane == 0)
     for (uint32_t s = 0; s < S; s++) mbar_init(smem_u32(bars + warp * S + s), 1);
   fence_mbar_init();
@@ -189,6 +198,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
 #pragma unroll
     for (int qi = 0; qi < QT; qi++) warp_cnt_s[warp][qi] = (int)cnt[qi];
   __syncthreads();  // all warps done: every issued stage was consumed, stage memory is free
+  // retire this group's mbarriers: the merge staging below overlays them and the next query group re-initialises the ring
+  if (lane == 0)
+    for (uint32_t s = 0; s < S; s++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bars + warp * S + s)) : "memory");
+  __syncthreads();
   Hit* Ls = reinterpret_cast<Hit*>(smem);              // [W][k]
   Hit* sel = Ls + (size_t)W * p.k;                     // [k]
   int* cnt_s = reinterpret_cast<int*>(sel + p.k);      // [W]
@@ -209,6 +222,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
     if (threadIdx.x == 0) p.cta_counts[(size_t)blockIdx.x * p.nq + (q0 + qi)] = (int)n_out;
     __syncthreads();
   }
+  }  // query groups
 }
 
 int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items, uint32_t nq, uint32_t k, int n_sms,

@@ -47,6 +47,8 @@ struct ScanParams {
   Hit* warp_lists;          // scratch [gridDim.x*W][nq][k] best-first
   Hit* cta_lists;           // out     [gridDim.x][nq][k]  best-first
   int* cta_counts;          // out     [gridDim.x][nq]
+  const uint32_t* q_map;    // nullable: compact query index -> prepared query row
+  const uint32_t* n_active; // nullable: number of queries, on the device (overrides nq)
   uint32_t chunk_bytes;     // bytes of one row copied per pipeline stage (multiple of 128)
   uint32_t n_stages;        // stages per warp
 };
@@ -120,7 +122,10 @@ struct MergeParams {
   uint32_t k;
   int nearest;
   int in_best_first;         // 1: lists are best-first (internal); 0: lists are in T order (public)
-  Hit* out;                  // [nq][k] in T order (ascending score, NaN last, then id)
+  const uint32_t* q_map;     // nullable: compact query index -> output row
+  const uint32_t* n_active;  // nullable: number of queries, on the device
+  uint32_t out_stride;       // hits per output row (0 = k)
+  Hit* out;                  // [nq][out_stride] in T order (ascending score, NaN last, then id)
   int* out_counts;           // [nq]
 };
 int launch_merge_topk(const MergeParams& p, cudaStream_t stream);

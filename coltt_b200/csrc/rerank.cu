@@ -17,7 +17,8 @@
 namespace coltt {
 
 static constexpr int kRerankThreads = 128;
-static constexpr uint32_t kRerankMaxCand = 1024;
+static constexpr uint32_t kRerankMaxCand = 1024;   // survivors gathered per query (keys only)
+static constexpr uint32_t kRerankRows = 64;        // rows re-scored exactly per query (>= 2 K')
 
 __host__ __device__ __forceinline__ float ord2f_(uint32_t u) {
   uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
@@ -30,35 +31,38 @@ __host__ __device__ __forceinline__ float ord2f_(uint32_t u) {
 
 template <int ELEM, int METRIC>
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t n_s;
-  float* q_s = reinterpret_cast<float*>(smem);                     // [q_stride]
-  uint32_t* row_s = reinterpret_cast<uint32_t*>(q_s + p.q_stride); // [kRerankMaxCand]
-  float* score_s = reinterpret_cast<float*>(row_s + kRerankMaxCand);
-  uint64_t* id_s = reinterpret_cast<uint64_t*>(score_s + kRerankMaxCand);
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t n_s, ovf_s;
+  __shared__ float kth_s, bound_s;
+  __shared__ __align__(8) uint64_t bar_s;
+  float* q_s = reinterpret_cast<float*>(smem);                       // [q_stride]
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(q_s + p.q_stride);   // [kRerankMaxCand]
+  float* key_s = reinterpret_cast<float*>(row_s + kRerankMaxCand);   // [kRerankMaxCand]
+  uint32_t* sel_row = reinterpret_cast<uint32_t*>(key_s + kRerankMaxCand);  // [kRerankRows]
+  float* score_s = reinterpret_cast<float*>(sel_row + kRerankRows);  // [kRerankRows]
+  uint64_t* id_s = reinterpret_cast<uint64_t*>(score_s + kRerankRows);      // [kRerankRows]
+  uint8_t* rows_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(id_s + kRerankRows) + 127) & ~uintptr_t(127));
   const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
+  const uint32_t RS = p.row_stride + 16;   // padded shared-memory row stride (bank-conflict free, as in flat_scan.cu)
 
-  if (tid == 0) n_s = 0;
+  if (tid == 0) { n_s = 0; ovf_s = 0; kth_s = 0.0f; mbar_init(smem_u32(&bar_s), 1); fence_mbar_init(); }
   for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
   __syncthreads();
 
-  // ---- 1. gather the survivors of every filter CTA that clear the final threshold
+  // ---- 1. gather the survivors of every filter column that clear the final threshold
   const uint32_t thr_bits = p.g_thr[q];
   const bool have_bound = thr_bits != 0;
   const float B = have_bound ? ord2f_(thr_bits) : 0.0f;
-  __shared__ uint32_t ovf_s;
-  if (tid == 0) ovf_s = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < p.grid_x * p.cand_cap; i += blockDim.x) {
-    const uint32_t cta = i / p.cand_cap, s = i - cta * p.cand_cap;
+  for (uint32_t cta = tid; cta < p.grid_x; cta += blockDim.x) {   // one column per thread: count, then its few entries
     const uint32_t ccnt = p.cand_cnt[(size_t)q * p.grid_x + cta];
-    if (ccnt == 0xffffffffu) { ovf_s = 1; continue; }   // that CTA overflowed on ties: exact path
-    if (s < ccnt) {
-      const GemmCand c = p.cand_in[((size_t)q * p.grid_x + cta) * p.cand_cap + s];
+    if (ccnt == 0xffffffffu) { ovf_s = 1; continue; }              // that column overflowed on ties: exact path
+    const GemmCand* src = p.cand_in + ((size_t)q * p.grid_x + cta) * p.cand_cap;
+    for (uint32_t s = 0; s < ccnt && s < p.cand_cap; s++) {
+      const GemmCand c = src[s];
       if (!have_bound || c.key >= B || c.key != c.key) {
         const uint32_t pos = atomicAdd(&n_s, 1u);
-        if (pos < kRerankMaxCand) row_s[pos] = c.row;
+        if (pos < kRerankMaxCand) { row_s[pos] = c.row; key_s[pos] = c.key; }
       }
     }
   }
@@ -66,16 +70,40 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   const uint32_t n_all = n_s;
   const uint32_t n = n_all < kRerankMaxCand ? n_all : kRerankMaxCand;
 
-  // ---- 2. exact re-score: 16 candidates per warp pass, two lanes per row, 4 chains per lane
+  // ---- 2. keep the M best by approximate key (rank counting; ties by row) — everything else, gathered or
+  //         not, has key <= bound': the (M+1)-th best key, or B when fewer than M were gathered
+  const uint32_t M = n < kRerankRows ? n : kRerankRows;
+  if (tid == 0) bound_s = have_bound ? B : __int_as_float(0xff800000);
+  __syncthreads();
+  for (uint32_t e = tid; e < n; e += blockDim.x) {
+    const float ke = key_s[e];
+    const uint32_t re = row_s[e];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) {
+      const float kj = key_s[j];
+      rank += (kj > ke || (kj == ke && row_s[j] < re)) ? 1u : 0u;
+    }
+    if (rank < M) sel_row[rank] = re;
+    if (rank == M && n > M) bound_s = fmaxf(bound_s, ke);   // single writer: ranks are unique
+  }
+  __syncthreads();
+
+  // ---- 3. fetch the M rows with one bulk async copy each (all in flight at once), then re-score them
+  //         from shared memory with the exact AVX-order arithmetic of flat_scan.cu
+  if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bar_s), M * p.row_stride);
+  __syncthreads();
+  for (uint32_t j = tid; j < M; j += blockDim.x)
+    bulk_g2s(smem_u32(rows_s + (size_t)j * RS), p.rows + (size_t)sel_row[j] * p.row_stride, p.row_stride, smem_u32(&bar_s));
+  if (M) mbar_wait(smem_u32(&bar_s), 0);
   const uint32_t r = lane_row16(lane), g = lane_half(lane);
   const uint32_t full8 = (p.dim / 8) * 8;
   const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
-  for (uint32_t base = warp * 16; base < n; base += (blockDim.x >> 5) * 16) {
+  for (uint32_t base = warp * 16; base < M; base += (blockDim.x >> 5) * 16) {
     const uint32_t j = base + r;
-    const bool valid = j < n;
-    const uint32_t row = valid ? row_s[j] : row_s[0];
-    const uint8_t* rowp = p.rows + (size_t)row * p.row_stride;
+    const bool valid = j < M;
+    const uint8_t* rowp = rows_s + (size_t)(valid ? j : 0) * RS;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
     for (uint32_t e = 0; e < full8; e += 8) {
       float rv[4];
       load4<ELEM>(rowp + (size_t)(e + 4 * g) * ES, nullptr, rv);
@@ -99,36 +127,35 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
       else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
     }
     if (valid && g == 0) {
+      const uint32_t row = sel_row[j];
       score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[row]) : sqrt_via_f64(tot);
       id_s[j] = p.ids[row];
     }
   }
   __syncthreads();
 
-  // ---- 3. top-K of the exact scores, straight into T order
-  const uint32_t n_out = n < p.k ? n : p.k;
+  // ---- 4. top-K of the exact scores, straight into T order
+  const uint32_t n_out = M < p.k ? M : p.k;
   Hit* out = p.out + (size_t)q * p.out_stride;
-  __shared__ float kth_s;
-  if (tid == 0) kth_s = 0.0f;
-  __syncthreads();
-  for (uint32_t e = tid; e < n; e += blockDim.x) {
+  for (uint32_t e = tid; e < M; e += blockDim.x) {
     const float sc = score_s[e];
     const uint64_t id = id_s[e];
     uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; j++) rank += better(score_s[j], id_s[j], sc, id, p.nearest) ? 1u : 0u;
+    for (uint32_t j = 0; j < M; j++) rank += better(score_s[j], id_s[j], sc, id, p.nearest) ? 1u : 0u;
     if (rank < n_out) {
-      Hit hh; hh.id = id; hh.score = sc; hh.slot = row_s[e];
+      Hit hh; hh.id = id; hh.score = sc; hh.slot = sel_row[e];
       out[p.nearest ? rank : n_out - 1 - rank] = hh;
       if (rank == n_out - 1) kth_s = sc;
     }
   }
   __syncthreads();
 
-  // ---- 4. certificate
+  // ---- 5. certificate: every row that was not re-scored has approximate key <= bound'
   if (tid == 0) {
     p.out_counts[q] = (int)n_out;
     bool ok = n_all <= kRerankMaxCand && ovf_s == 0;
-    if (ok && have_bound) {
+    const float Bp = bound_s;
+    if (ok && Bp > __int_as_float(0xff800000)) {
       const float dK = kth_s;  // exact score (a distance) of the worst row we return
       if (!(dK == dK)) {
         ok = !p.nearest;       // NaN is the best COMPAT score and the worst NEAREST one
@@ -136,15 +163,15 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
         const float invq = rsqrtf(qn);
         const float eps = 1.5e-4f;
         // key = +-dot/||row||; exact sim within eps of key*invq; distance = |1 - sim|
-        if (p.nearest) ok = dK < 1.0f - B * invq - eps;         // dropped rows: distance >= 1 - B*invq - eps
-        else ok = dK > 1.0f + B * invq + eps;                   // dropped rows: distance <= 1 + B*invq + eps
+        if (p.nearest) ok = dK < 1.0f - Bp * invq - eps;        // dropped rows: distance >= 1 - B'*invq - eps
+        else ok = dK > 1.0f + Bp * invq + eps;                  // dropped rows: distance <= 1 + B'*invq + eps
       } else {
         const float nq2 = p.q_norm2[q];
         const float d2 = dK * dK;
         const float scale = nq2 + (sqrtf(nq2) + dK) * (sqrtf(nq2) + dK);
         const float eps = 2.0e-4f * scale;
-        if (p.nearest) ok = d2 < nq2 - B - eps;                 // key = 2dot - ||row||^2  =>  d^2 = ||q||^2 - key
-        else ok = d2 > nq2 + B + eps;                           // key = ||row||^2 - 2dot  =>  d^2 = ||q||^2 + key
+        if (p.nearest) ok = d2 < nq2 - Bp - eps;                // key = 2dot - ||row||^2  =>  d^2 = ||q||^2 - key
+        else ok = d2 > nq2 + Bp + eps;                          // key = ||row||^2 - 2dot  =>  d^2 = ||q||^2 + key
       }
       if (n_out < p.k) ok = false;  // the filter keeps K' >= K rows once it has a bound: fewer means trouble
     }
@@ -154,7 +181,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
 
 int launch_rerank(const RerankParams& p, cudaStream_t stream) {
   if (p.nq == 0) return COLTT_OK;
-  const size_t smem = (size_t)p.q_stride * 4 + (size_t)kRerankMaxCand * (4 + 4 + 8);
+  const size_t smem = (size_t)p.q_stride * 4 + (size_t)kRerankMaxCand * 8 + (size_t)kRerankRows * 16 + 128 + (size_t)kRerankRows * (p.row_stride + 16);
+  if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "rerank: rows too wide for shared memory");
   const bool cosine = p.metric == COLTT_COSINE;
 #define COLTT_RR(E, M)                                                                                    \
   {                                                                                                       \

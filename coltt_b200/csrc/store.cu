@@ -114,6 +114,11 @@ SearchCtx::~SearchCtx() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+__global__ void compact_flags_kernel(const uint32_t* flags, uint32_t nq, uint32_t* q_map, uint32_t* n_bad) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && flags[q]) q_map[atomicAdd(n_bad, 1u)] = q;
+}
+
 __global__ void scatter_ids_kernel(const uint64_t* src, const uint32_t* slots, uint64_t* dst, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[slots[i]] = src[i];
@@ -289,7 +294,9 @@ std::unique_ptr<SearchCtx> Store::acquire_ctx(cudaStream_t user_stream) {
     for (size_t i = 0; i < pool.size(); i++) {
       SearchCtx& c = *pool[i];
       const bool same = user_stream && c.used && c.last_stream == user_stream;
-      if (same || !c.used || cudaEventQuery(c.done) == cudaSuccess) {
+      const bool finished = !c.used || cudaEventQuery(c.done) == cudaSuccess;
+      if (finished && c.fb_pending) { fast_fallbacks += *(const uint32_t*)c.h_flags.p; c.fb_pending = false; }
+      if (same || finished) {
         auto out = std::move(pool[i]);
         pool.erase(pool.begin() + i);
         return out;
@@ -477,28 +484,42 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   }
   *used_fast = true;
   fast_queries += nq;
-  // certificate check: queries that could not be certified are re-run on the exact path
-  COLTT_CUDA(cudaMemcpyAsync(c.h_flags.p, c.flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
-  COLTT_CUDA(cudaStreamSynchronize(st));
-  const uint32_t* hf = (const uint32_t*)c.h_flags.p;
-  std::vector<uint32_t> bad;
-  for (size_t q = 0; q < nq; q++) if (hf[q]) bad.push_back((uint32_t)q);
-  if (bad.empty()) return COLTT_OK;
-  fast_fallbacks += bad.size();
-  rc = c.fb_q.ensure(bad.size() * dim * 4); if (rc) return rc;
-  rc = c.fb_out.ensure(bad.size() * (size_t)k * sizeof(Hit)); if (rc) return rc;
-  rc = c.fb_cnt.ensure(bad.size() * 4); if (rc) return rc;
-  for (size_t i = 0; i < bad.size(); i++)
-    COLTT_CUDA(cudaMemcpyAsync((float*)c.fb_q.p + i * dim, d_queries + (size_t)bad[i] * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, st));
-  in_fallback = true;
-  rc = search_enqueue(c, st, (const float*)c.fb_q.p, bad.size(), k, nearest ? COLTT_SELECT_NEAREST : COLTT_SELECT_COMPAT, COLTT_MATH_EXACT,
-                      nullptr, 0, (Hit*)c.fb_out.p, (int*)c.fb_cnt.p, false);
-  in_fallback = false;
-  if (rc) return rc;
-  for (size_t i = 0; i < bad.size(); i++) {
-    COLTT_CUDA(cudaMemcpyAsync(d_out + (size_t)bad[i] * k, (Hit*)c.fb_out.p + i * (size_t)k, (size_t)k * sizeof(Hit), cudaMemcpyDeviceToDevice, st));
-    COLTT_CUDA(cudaMemcpyAsync(d_counts + bad[i], (int*)c.fb_cnt.p + i, 4, cudaMemcpyDeviceToDevice, st));
+  // Certificate check, on the device: the queries rerank.cu could not certify are compacted into a list
+  // and re-run by the exact kernel, which takes its query count from device memory — no host round trip;
+  // with nothing flagged the three launches below are one empty wave each.
+  rc = c.fb_cnt.ensure(16); if (rc) return rc;
+  rc = c.fb_q.ensure(nq * 4); if (rc) return rc;
+  COLTT_CUDA(cudaMemsetAsync(c.fb_cnt.p, 0, 4, st));
+  compact_flags_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>((const uint32_t*)c.flags.p, (uint32_t)nq, (uint32_t*)c.fb_q.p, (uint32_t*)c.fb_cnt.p);
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  {
+    const uint32_t k_eff = (uint32_t)k;   // fast path requires k <= n_rows
+    ScanPlan plan;
+    rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_rows, (uint32_t)nq, k_eff, n_sms, &plan); if (rc) return rc;
+    plan.grid_y = 1;                      // each CTA loops over the (few) flagged query groups
+    plan.warp_list_bytes = (size_t)plan.grid_x * 8 * nq * k_eff * sizeof(Hit);
+    rc = c.warp_lists.ensure(plan.warp_list_bytes); if (rc) return rc;
+    rc = c.cta_lists.ensure(plan.cta_list_bytes); if (rc) return rc;
+    rc = c.cta_counts.ensure(plan.cta_count_bytes); if (rc) return rc;
+    ScanParams sp{};
+    sp.rows = d_rows; sp.row_stride = row_stride; sp.dim = dim; sp.n_items = (uint32_t)n_rows; sp.subset = nullptr;
+    sp.row_norm2 = d_norm2; sp.ids = d_ids;
+    sp.queries = (const float*)c.q_deq.p; sp.q_norm2 = (const float*)c.q_n2.p; sp.q_stride = q_stride;
+    sp.nq = (uint32_t)nq; sp.k = k_eff; sp.nearest = nearest; sp.metric = cfg.metric;
+    sp.warp_lists = (Hit*)c.warp_lists.p; sp.cta_lists = (Hit*)c.cta_lists.p; sp.cta_counts = (int*)c.cta_counts.p;
+    sp.q_map = (const uint32_t*)c.fb_q.p; sp.n_active = (const uint32_t*)c.fb_cnt.p;
+    rc = launch_flat_scan(sp, plan, elem, st); if (rc) return rc;
+    MergeParams mp{};
+    mp.lists = (const Hit*)c.cta_lists.p; mp.counts = (const int*)c.cta_counts.p; mp.n_lists = plan.grid_x;
+    mp.nq = (uint32_t)nq; mp.k_in = k_eff; mp.k = k_eff; mp.nearest = nearest; mp.in_best_first = 1;
+    mp.out = d_out; mp.out_counts = d_counts; mp.out_stride = (uint32_t)k;
+    mp.q_map = (const uint32_t*)c.fb_q.p; mp.n_active = (const uint32_t*)c.fb_cnt.p;
+    rc = launch_merge_topk(mp, st); if (rc) return rc;
   }
+  // statistics only: how many queries took the exact re-run (read back lazily, never waited for here)
+  COLTT_CUDA(cudaMemcpyAsync(c.h_flags.p, c.fb_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+  c.fb_pending = true;
   return COLTT_OK;
 }
 
@@ -547,6 +568,7 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
   COLTT_CUDA(cudaMemcpyAsync(h_counts, c.counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
   COLTT_CUDA(cudaMemcpyAsync(h_hits, c.out.p, nq * (size_t)k * sizeof(Hit), cudaMemcpyDeviceToHost, st));
   COLTT_CUDA(cudaStreamSynchronize(st));
+  if (c.fb_pending) { fast_fallbacks += *(const uint32_t*)c.h_flags.p; c.fb_pending = false; }
   c.used = true;
   c.last_stream = st;
   cudaEventRecord(c.done, st);
@@ -754,8 +776,15 @@ COLTT_API int coltt_b200_debug_fast_scores(coltt_store* s_, const float* queries
 // [0] queries served by the FAST path, [1] of those re-run exactly because the margin was not certified
 COLTT_API int coltt_b200_store_fast_stats(coltt_store* s, uint64_t* out2) {
   if (!s || !out2) return fail(COLTT_ERR_INVALID, "null argument");
-  out2[0] = reinterpret_cast<Store*>(s)->fast_queries;
-  out2[1] = reinterpret_cast<Store*>(s)->fast_fallbacks;
+  Store* st = reinterpret_cast<Store*>(s);
+  {
+    std::lock_guard<std::mutex> g(st->pool_mu);
+    for (auto& c : st->pool)
+      if (c->fb_pending && (!c->used || cudaEventQuery(c->done) == cudaSuccess)) { st->fast_fallbacks += *(const uint32_t*)c->h_flags.p; c->fb_pending = false; }
+    cudaGetLastError();
+  }
+  out2[0] = st->fast_queries;
+  out2[1] = st->fast_fallbacks;
   return COLTT_OK;
 }
 

@@ -38,7 +38,7 @@ struct SearchCtx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t done = nullptr;       // recorded after the last enqueue that used this scratch
   cudaStream_t last_stream = nullptr;
-  bool used = false, have_times = false;
+  bool used = false, have_times = false, fb_pending = false;
   float ms[4] = {0, 0, 0, 0};
   DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf;
   PinnedBuf h_flags;

@@ -24,6 +24,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
   __shared__ uint32_t P_s, M_s, overflow_s, has_tau_s;
   __shared__ Hit tau_s;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  if (p.n_active && q >= *p.n_active) return;
+  const uint32_t q_out = p.q_map ? p.q_map[q] : q;
+  const uint32_t ostride = p.out_stride ? p.out_stride : p.k;
   const int rev = (!p.in_best_first && !p.nearest) ? 1 : 0;  // public T-order lists are worst-first for COMPAT
   Hit* sel = reinterpret_cast<Hit*>(smem);            // [k]      (fallback path)
   Hit* piv = sel + p.k;                                // [piv_cap]
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
     }
   }
   __syncthreads();
-  Hit* out = p.out + (size_t)q * p.k;
+  Hit* out = p.out + (size_t)q_out * ostride;
   if (overflow_s) {
     rank_merge_block(L, cnt, p.n_lists, p.k_in, p.k, p.nearest, sel, rev, list_stride, cnt_stride);
     __syncthreads();
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
       if (rank < n_out) out[p.nearest ? rank : n_out - 1 - rank] = me;
     }
   }
-  if (tid == 0) p.out_counts[q] = (int)n_out;
+  if (tid == 0) p.out_counts[q_out] = (int)n_out;
 }
 
 int launch_merge_topk(const MergeParams& p, cudaStream_t stream) {
