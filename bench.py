@@ -209,21 +209,40 @@ def main():
     cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(device=dev)
     if world > 1:
-        gathered = torch.zeros((world, nq, k, 4), dtype=torch.int32, device=dev)
-        gcnt = torch.zeros((world, nq), dtype=torch.int32, device=dev)
+        packed = torch.zeros((nq * k * 4 + nq,), dtype=torch.int32, device=dev)          # hits + counts of this shard
+        gathered_flat = torch.zeros((world * (nq * k * 4 + nq),), dtype=torch.int32, device=dev)
         fin = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
         fcnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
 
+    brk = os.environ.get("COLTT_BENCH_BREAKDOWN") == "1"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if brk else None
+    brk_parts = {"search": 0.0, "gather": 0.0, "merge": 0.0, "n": 0}
+
     def step_dev(i):
+        if brk:
+            ev[0].record(stream)
         _lib.check(L.coltt_b200_store_search_dev(sp._h, q_dev[i % n_qsets].data_ptr(), nq, k, cb.SELECT_NEAREST, math_mode,
                                                   out.data_ptr(), cnt.data_ptr(), stream.cuda_stream))
         if world > 1:
-            # the one exchange step of the sharded search: all-gather of per-shard top-k, then merge (K5)
+            # the one exchange step of the sharded search: all-gather of per-shard top-k (counts ride along in
+            # the same message), then the K5 merge on every rank
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, out)
-                dist.all_gather_into_tensor(gcnt, cnt)
-            _lib.check(L.coltt_b200_merge_topk_dev(local, gathered.data_ptr(), gcnt.data_ptr(), world, nq, k, k, cb.SELECT_NEAREST,
-                                                    fin.data_ptr(), fcnt.data_ptr(), stream.cuda_stream))
+                if brk:
+                    ev[1].record(stream)
+                packed[:nq * k * 4].copy_(out.view(-1), non_blocking=True)
+                packed[nq * k * 4:].copy_(cnt, non_blocking=True)
+                dist.all_gather_into_tensor(gathered_flat, packed)
+                if brk:
+                    ev[2].record(stream)
+            _lib.check(L.coltt_b200_merge_topk_dev2(local, gathered_flat.data_ptr(), world, nq, k, k, cb.SELECT_NEAREST, (nq * k * 4 + nq) * 4,
+                                                     nq * k * 16, fin.data_ptr(), fcnt.data_ptr(), stream.cuda_stream))
+            if brk:
+                ev[3].record(stream)
+                torch.cuda.synchronize(dev)
+                brk_parts["search"] += ev[0].elapsed_time(ev[1])
+                brk_parts["gather"] += ev[1].elapsed_time(ev[2])
+                brk_parts["merge"] += ev[2].elapsed_time(ev[3])
+                brk_parts["n"] += 1
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -265,14 +284,26 @@ def main():
     kern_ms = float(np.mean([x["scan"] for x in scan_ms]))
     parts = {kk: float(np.mean([x[kk] for x in scan_ms])) for kk in ("prep", "scan", "rerank", "merge")}
 
-    # ---- end to end through the host-pointer C-ABI (pinned staging inside the library) ------
+    # ---- end to end: host buffers in, host results out.  N=1: the host-pointer C-ABI call.  N>1: the sharded
+    # public API (coltt_b200.dist.ShardedSearch): H2D of the queries, per-shard search, all-gather, merge, D2H.
+    if world > 1:
+        from coltt_b200.dist import ShardedSearch, cuda_callables, unpack_hits
+        ls, mg = cuda_callables(sp, local, math_mode=math_mode)
+        sharded = ShardedSearch(ls, mg)
+
+        def e2e_step(i):
+            hits, c2 = sharded.search(q_host[i % n_qsets], k, cb.SELECT_NEAREST)
+            return unpack_hits(hits, c2)
+    else:
+        def e2e_step(i):
+            return sp.BatchVertexSearch(q_host[i % n_qsets], k)
     for i in range(min(args.warmup, 3)):
-        sp.BatchVertexSearch(q_host[i % n_qsets], k)
+        e2e_step(i)
     barrier()
     t1 = time.perf_counter()
     e2e_steps = max(3, args.steps // 3)
     for i in range(e2e_steps):
-        sp.BatchVertexSearch(q_host[i % n_qsets], k)
+        e2e_step(i)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t1
     if dist is not None:
@@ -280,6 +311,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * nq * e2e_steps / e2e_s
+    if brk and brk_parts["n"] and rank == 0:
+        print("[bench breakdown ms/step]", {kk: round(v / brk_parts["n"], 4) for kk, v in brk_parts.items() if kk != "n"}, file=sys.stderr, flush=True)
 
     if rank != 0:
         if dist is not None:

@@ -14,7 +14,7 @@ ABI_SYMBOLS = [
     "coltt_b200_last_error", "coltt_b200_version", "coltt_b200_device_count",
     "coltt_b200_store_create", "coltt_b200_store_destroy", "coltt_b200_store_size", "coltt_b200_store_dim",
     "coltt_b200_store_upsert", "coltt_b200_store_remove", "coltt_b200_store_search",
-    "coltt_b200_store_search_subset", "coltt_b200_store_search_dev", "coltt_b200_merge_topk_dev",
+    "coltt_b200_store_search_subset", "coltt_b200_store_search_dev", "coltt_b200_merge_topk_dev", "coltt_b200_merge_topk_dev2",
     "coltt_b200_store_export", "coltt_b200_store_import", "coltt_b200_store_get_row",
     "coltt_b200_hnsw_load", "coltt_b200_hnsw_destroy", "coltt_b200_hnsw_len", "coltt_b200_hnsw_search",
     "coltt_b200_hnsw_last_stats", "coltt_b200_store_last_timing", "coltt_b200_kernel_launches",
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.coltt_b200_store_search_subset.argtypes = [vp, f32p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_int, u64p, f32p, i32p]
     L.coltt_b200_store_search_dev.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.coltt_b200_merge_topk_dev.argtypes = [C.c_int, vp, vp, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.coltt_b200_merge_topk_dev2.argtypes = [C.c_int, vp, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp]
     L.coltt_b200_store_export.argtypes = [vp, vp, C.POINTER(C.c_size_t)]
     L.coltt_b200_store_import.argtypes = [vp, vp, C.c_size_t]
     L.coltt_b200_store_get_row.argtypes = [vp, C.c_uint64, vp, C.c_size_t]

@@ -125,6 +125,8 @@ struct MergeParams {
   const uint32_t* q_map;     // nullable: compact query index -> output row
   const uint32_t* n_active;  // nullable: number of queries, on the device
   uint32_t out_stride;       // hits per output row (0 = k)
+  size_t list_stride_hits;   // Hits between consecutive lists (0 = nq*k_in, the dense layout)
+  size_t count_stride;       // ints between consecutive lists' counts (0 = nq)
   Hit* out;                  // [nq][out_stride] in T order (ascending score, NaN last, then id)
   int* out_counts;           // [nq]
 };

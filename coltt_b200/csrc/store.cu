@@ -52,6 +52,9 @@ int sm100_device_count() {
 }
 
 int require_device(int device) {
+  // cudaGetDeviceProperties costs ~1 ms: validate each ordinal once (hot callers: the per-batch merge)
+  static std::atomic<int> ok_cache[64];
+  if (device >= 0 && device < 64 && ok_cache[device].load(std::memory_order_relaxed) == 1) return COLTT_OK;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
@@ -61,6 +64,7 @@ int require_device(int device) {
   cudaDeviceProp pr;
   COLTT_CUDA(cudaGetDeviceProperties(&pr, device));
   if (pr.major != 10) return fail(COLTT_ERR_NO_DEVICE, std::string("device is not sm_100 (Blackwell B200): ") + pr.name);
+  if (device < 64) ok_cache[device].store(1, std::memory_order_relaxed);
   return COLTT_OK;
 }
 
@@ -702,6 +706,25 @@ COLTT_API int coltt_b200_merge_topk_dev(int device, const void* d_lists, const v
   coltt::MergeParams mp{};
   mp.lists = (const coltt::Hit*)d_lists; mp.counts = (const int*)d_list_counts; mp.n_lists = n_lists; mp.nq = (uint32_t)nq;
   mp.k_in = (uint32_t)k_in; mp.k = (uint32_t)k; mp.nearest = select_mode == COLTT_SELECT_NEAREST; mp.in_best_first = 0;
+  mp.out = (coltt::Hit*)d_out; mp.out_counts = (int*)d_out_counts;
+  rc = coltt::launch_merge_topk(mp, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!stream) COLTT_CUDA(cudaStreamSynchronize(0));
+  return COLTT_OK;
+}
+// Variant for one packed message per rank: rank r's block starts at d_packed + r*rank_stride_bytes and holds
+// coltt_hit[nq][k_in] followed (at counts_offset_bytes) by int32 counts[nq].
+COLTT_API int coltt_b200_merge_topk_dev2(int device, const void* d_packed, int n_lists, size_t nq, int k_in, int k, int select_mode,
+                                         size_t rank_stride_bytes, size_t counts_offset_bytes, void* d_out, void* d_out_counts, void* stream) {
+  if (!d_packed || !d_out || !d_out_counts || n_lists <= 0 || k <= 0 || k_in <= 0) return fail(COLTT_ERR_INVALID, "bad merge arguments");
+  if (rank_stride_bytes % 16 || counts_offset_bytes % 4) return fail(COLTT_ERR_INVALID, "packed merge: misaligned strides");
+  int rc = coltt::require_device(device);
+  if (rc) return rc;
+  COLTT_CUDA(cudaSetDevice(device));
+  coltt::MergeParams mp{};
+  mp.lists = (const coltt::Hit*)d_packed; mp.counts = (const int*)((const uint8_t*)d_packed + counts_offset_bytes); mp.n_lists = n_lists;
+  mp.nq = (uint32_t)nq; mp.k_in = (uint32_t)k_in; mp.k = (uint32_t)k; mp.nearest = select_mode == COLTT_SELECT_NEAREST; mp.in_best_first = 0;
+  mp.list_stride_hits = rank_stride_bytes / 16; mp.count_stride = rank_stride_bytes / 4;
   mp.out = (coltt::Hit*)d_out; mp.out_counts = (int*)d_out_counts;
   rc = coltt::launch_merge_topk(mp, (cudaStream_t)stream);
   if (rc) return rc;

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
   const uint32_t q_out = p.q_map ? p.q_map[q] : q;
   const uint32_t ostride = p.out_stride ? p.out_stride : p.k;
   const int rev = (!p.in_best_first && !p.nearest) ? 1 : 0;  // public T-order lists are worst-first for COMPAT
+  const size_t lstr = p.list_stride_hits ? p.list_stride_hits : (size_t)p.nq * p.k_in;
+  const size_t cstr = p.count_stride ? p.count_stride : (size_t)p.nq;
   Hit* sel = reinterpret_cast<Hit*>(smem);            // [k]      (fallback path)
   Hit* piv = sel + p.k;                                // [piv_cap]
   Hit* surv = piv + piv_cap;                           // [surv_cap]
@@ -39,18 +41,18 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
     Hit* Ls = surv + surv_cap;                         // [n_lists][k_in]
     int* cnt_s = reinterpret_cast<int*>(Ls + (size_t)p.n_lists * p.k_in);
     for (int j = tid; j < p.n_lists; j += blockDim.x) {
-      int c = p.counts[(size_t)j * p.nq + q];
+      int c = p.counts[(size_t)j * cstr + q];
       cnt_s[j] = c > (int)p.k_in ? (int)p.k_in : c;
     }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)p.n_lists * p.k_in; i += blockDim.x) {
       uint32_t j = i / p.k_in, e = i - j * p.k_in;
-      if ((int)e < cnt_s[j]) Ls[i] = p.lists[((size_t)j * p.nq + q) * p.k_in + e];
+      if ((int)e < cnt_s[j]) Ls[i] = p.lists[(size_t)j * lstr + (size_t)q * p.k_in + e];
     }
     L = Ls; cnt = cnt_s; list_stride = p.k_in; cnt_stride = 1;
   } else {
     L = p.lists + (size_t)q * p.k_in; cnt = p.counts + q;
-    list_stride = (size_t)p.nq * p.k_in; cnt_stride = p.nq;
+    list_stride = lstr; cnt_stride = cstr;
   }
   __syncthreads();
   auto count_of = [&](int j) -> uint32_t { uint32_t c = (uint32_t)cnt[(size_t)j * cnt_stride]; return c > p.k_in ? p.k_in : c; };

@@ -62,13 +62,20 @@ class ShardedSearch:
         if self.world == 1:
             return self.merge(hits.unsqueeze(0), counts.unsqueeze(0), k, select_mode)
         nq = hits.shape[0]
-        # concatenated-along-dim-0 output: the layout both NCCL and gloo accept; viewed as [world, nq, ...]
-        gathered = torch.empty((self.world * nq,) + tuple(hits.shape[1:]), dtype=hits.dtype, device=hits.device)
-        gcounts = torch.empty((self.world * nq,), dtype=counts.dtype, device=counts.device)
+        # ONE message per shard: its [nq,k] hits followed by its counts (padded to a 16-byte multiple);
+        # the gathered buffer is rank-major, and the merge sees strided views of it (no repacking)
+        hflat = hits.reshape(-1)
+        n_h, n_c = hflat.numel(), (nq + 3) // 4 * 4
+        packed = torch.zeros((n_h + n_c,), dtype=hits.dtype, device=hits.device)
+        packed[:n_h].copy_(hflat)
+        packed[n_h:n_h + nq].copy_(counts.to(hits.dtype))
+        gathered = torch.empty((self.world * (n_h + n_c),), dtype=hits.dtype, device=hits.device)
         # the one exchange step: per-shard top-k of every rank to every rank
-        self.dist.all_gather_into_tensor(gathered, hits.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(gcounts, counts.contiguous(), group=self.group)
-        return self.merge(gathered.view((self.world, nq) + tuple(hits.shape[1:])), gcounts.view(self.world, nq), k, select_mode)
+        self.dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        g2 = gathered.view(self.world, n_h + n_c)
+        g_hits = g2[:, :n_h].unflatten(1, tuple(hits.shape))
+        g_counts = g2[:, n_h:n_h + nq]
+        return self.merge(g_hits, g_counts, k, select_mode)
 
 
 def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, stream=None):
@@ -96,8 +103,15 @@ def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, st
         world, nq = gathered.shape[0], gathered.shape[1]
         out = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
         cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
-        _lib.check(L.coltt_b200_merge_topk_dev(device_index, gathered.data_ptr(), gcounts.data_ptr(), world, nq, gathered.shape[2], k,
-                                                select_mode, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
+        if gathered.is_contiguous() and gcounts.is_contiguous():
+            _lib.check(L.coltt_b200_merge_topk_dev(device_index, gathered.data_ptr(), gcounts.data_ptr(), world, nq, gathered.shape[2], k,
+                                                    select_mode, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
+        else:   # strided views of the packed all-gather buffer: one block per shard, hits then counts
+            stride_b = gathered.stride(0) * 4
+            off_b = gcounts.data_ptr() - gathered.data_ptr()
+            assert gcounts.stride(0) * 4 == stride_b and off_b > 0
+            _lib.check(L.coltt_b200_merge_topk_dev2(device_index, gathered.data_ptr(), world, nq, gathered.shape[2], k, select_mode,
+                                                     stride_b, off_b, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
         return out, cnt
 
     return local_search, merge

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_fast.py -m gpu -q 2>&1 | tail -8) > gpurun_out/pytest_fast.log
-(timeout 300 python bench.py --steps 40 --warmup 5 --math fast --no-cpu 2>&1 | tail -1 | cut -c1-1500) > gpurun_out/bench_fast.log
-(timeout 600 python tools/probe_shapes.py 2>&1 | tail -40) > gpurun_out/probe.log
-tail -n 4 gpurun_out/pytest_fast.log; cat gpurun_out/bench_fast.log; cat gpurun_out/probe.log
+(timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 30 --warmup 5 --math fast > gpurun_out/bench_2gpu_full.log 2>&1)
+grep -E "metric" gpurun_out/bench_2gpu_full.log | cut -c1-1400; tail -n 3 gpurun_out/bench_2gpu_full.log | cut -c1-300
+(COLTT_BENCH_BREAKDOWN=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --math fast > gpurun_out/bench_2gpu_brk.log 2>&1)
+grep -E "breakdown|Error|error" gpurun_out/bench_2gpu_brk.log | head -5 | cut -c1-300

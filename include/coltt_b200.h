@@ -143,6 +143,12 @@ COLTT_API int coltt_b200_merge_topk_dev(int device, const void* d_lists, const v
                                         size_t nq, int k_in, int k, int select_mode, void* d_out, void* d_out_counts,
                                         void* stream);
 
+/* Same merge for ONE packed message per shard (what the all-gather delivers): shard r's block starts at
+ * d_packed + r*rank_stride_bytes and holds coltt_hit[nq][k_in], then at counts_offset_bytes int32 counts[nq]. */
+COLTT_API int coltt_b200_merge_topk_dev2(int device, const void* d_packed, int n_lists, size_t nq, int k_in, int k,
+                                         int select_mode, size_t rank_stride_bytes, size_t counts_offset_bytes, void* d_out,
+                                         void* d_out_counts, void* stream);
+
 /* vectorspace.SaveVertex / LoadVertex (edge/none_vectorstore.go:308-516; element widths
  * f16_vectorstore.go:338-343, f8_vectorstore.go:340): the reference's big-endian vertex blob.
  * Export writes metaCount = 0 for every vertex (metadata lives on the Go side); import skips

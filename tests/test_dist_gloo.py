@@ -23,8 +23,8 @@ def _numpy_merge(gathered, gcounts, k, select_mode):
     """T-order merge (ascending score, NaN last, then id): NEAREST keeps the first k, COMPAT the last k."""
     import torch
     from coltt_b200.dist import HIT_DTYPE
-    g = gathered.numpy().view(HIT_DTYPE).reshape(gathered.shape[0], gathered.shape[1], gathered.shape[2])
-    c = gcounts.numpy()
+    g = gathered.contiguous().numpy().view(HIT_DTYPE).reshape(gathered.shape[0], gathered.shape[1], gathered.shape[2])
+    c = gcounts.contiguous().numpy()
     nq = g.shape[1]
     out = np.zeros((nq, k), dtype=HIT_DTYPE)
     cnt = np.zeros(nq, dtype=np.int32)
