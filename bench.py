@@ -36,8 +36,8 @@ METRIC_NAME = "QPS @ recall@10, dim=768, 1M vecs"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
@@ -75,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -111,6 +111,15 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -277,7 +286,7 @@ def main():
 
     # ---- dominant-kernel time, per launch, with CUDA events on its stream (instrumented pass)
     scan_ms = []
-    for i in range(min(args.steps, 10)):
+    for i in range(min(args.steps, 20)):
         step_dev(i)
         torch.cuda.synchronize(dev)
         scan_ms.append(sp.last_timing_ms())
@@ -301,7 +310,7 @@ def main():
         e2e_step(i)
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(3, args.steps // 3)
+    e2e_steps = max(3, min(args.steps // 3, 300))
     for i in range(e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize(dev)
@@ -331,8 +340,11 @@ def main():
                 "traffic": None, "note": f"exact-order CUDA-core path: {passes} HBM passes (8 queries each); "
                                          f"{flops / (kern_ms / 1e3) / 1e12:.1f} TFLOP/s fp32 unfused"}
     else:
-        roof = {"bound": "hbm", "achieved": alg_bytes / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
-                "tensor_tflops": flops / (kern_ms / 1e3) / 1e12, "tensor_peak_tflops": peaks["tf"]}
+        kname = "gemm_filter_pair_kernel" if nq > 128 else "gemm_filter_kernel"
+        roof = {"bound": "hbm", "achieved": alg_bytes / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "traffic": ncu_traffic(kname), "kernel": kname, "algorithmic_bytes": alg_bytes,
+                "tensor_tflops": flops / (kern_ms / 1e3) / 1e12, "tensor_peak_tflops": peaks["tf"],
+                "tensor_frac": flops / (kern_ms / 1e3) / 1e12 / peaks["tf"]}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = peaks["src"]
     roof["kernel_ms"] = kern_ms

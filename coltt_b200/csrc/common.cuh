@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <string>
 
 #include "../../include/coltt_b200.h"
@@ -102,6 +103,27 @@ __host__ __device__ __forceinline__ uint32_t f8_compat_decode_bits(uint8_t in) {
   }
   coef &= 0x007fffffu;
   return sign | ((exp + (0x7f - 0xf)) << 23) | coef;
+}
+
+// ---- order-preserving float <-> uint32 (atomicMin/Max on bounds that may be negative) -------------
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
 }
 
 // ---- mbarrier / bulk-copy (TMA) PTX ----------------------------------------------------

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float lut_s[ELEM == ELEM_F8C ? 256 : 1];
   __shared__ int warp_cnt_s[kScanWarps][QT];
+  __shared__ uint32_t cta_kth_s[QT];   // best K-th bound any warp of this CTA has reached, order-encoded
 
   constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
   const uint32_t W = kScanWarps, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -49,8 +50,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   float* q_s = reinterpret_cast<float*>(smem);                        // [QT][q_stride]
   float* qn_s = q_s + (size_t)QT * p.q_stride;                        // [QT] (+pad to 8 floats)
   uint64_t* bars = reinterpret_cast<uint64_t*>(qn_s + 8);             // [W*S]
-  uintptr_t st = reinterpret_cast<uintptr_t>(bars + W * S);
-  uint8_t* stages = reinterpret_cast<uint8_t*>((st + 127) & ~uintptr_t(127));  // [W][S][16][RS]
+  // offsets only (no pointer->integer round trip): the compiler keeps the shared address space and emits LDS
+  const uint32_t stages_off = (uint32_t)(((size_t)QT * p.q_stride * 4 + 32 + (size_t)W * S * 8 + 127) / 128 * 128);
+  uint8_t* stages = smem + stages_off;                                // [W][S][16][RS]
 
   if (ELEM == ELEM_F8C)
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __uint_as_float(f8_compat_decode_bits((uint8_t)i));
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   }
   if (lane == 0)
     for (uint32_t s = 0; s < S; s++) mbar_init(smem_u32(bars + warp * S + s), 1);
+  if (threadIdx.x < QT) cta_kth_s[threadIdx.x] = p.nearest ? 0xffffffffu : 0u;   // "no bound yet"
   fence_mbar_init();
   __syncthreads();
 
@@ -117,10 +120,18 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   for (uint32_t t = 0; t < S && t < n_work; t++) issue(t);
 
   uint32_t gi = 0, c = 0;
+  float nb_pref = 0.0f;
+  uint32_t slot_pref = 0;
   for (uint32_t t = 0; t < n_work; t++) {
     if (c == 0) {
 #pragma unroll
       for (int qi = 0; qi < QT; qi++) acc[qi][0] = acc[qi][1] = acc[qi][2] = acc[qi][3] = 0.0f;
+      // ||row||^2 and the slot of this lane's row: fetched now, needed when the last chunk is done
+      const uint32_t item_p = (gw + gi * TW) * kRowsPerWarp + r;
+      if (item_p < p.n_items) {
+        slot_pref = p.subset ? p.subset[item_p] : item_p;
+        if (METRIC == COLTT_COSINE) nb_pref = p.row_norm2[slot_pref];
+      }
     }
     const uint32_t s = t % S;
     mbar_wait(bar0 + s * 8, (t / S) & 1);
@@ -157,8 +168,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
       // ---- row finished: reduce, tail, distance, top-K ---------------------------------
       const uint32_t item = (gw + gi * TW) * kRowsPerWarp + r;
       const bool valid = item < p.n_items;
-      const uint32_t slot = valid ? (p.subset ? p.subset[item] : item) : 0u;
-      const float nb = (METRIC == COLTT_COSINE && valid) ? p.row_norm2[slot] : 0.0f;
+      const uint32_t slot = valid ? slot_pref : 0u;
+      const float nb = (METRIC == COLTT_COSINE && valid) ? nb_pref : 0.0f;
 #pragma unroll
       for (int qi = 0; qi < QT; qi++) {
         float h = add_rn(add_rn(acc[qi][0], acc[qi][1]), add_rn(acc[qi][2], acc[qi][3]));  // avx.cpp:3-8
@@ -171,6 +182,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
           else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
         }
         const float score = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn_s[qi], nb) : sqrt_via_f64(tot);
+        {   // another warp of this CTA may already hold K rows better than ours: adopt its bound
+          const uint32_t shared_bits = cta_kth_s[qi];
+          if (p.nearest ? shared_bits != 0xffffffffu : shared_bits != 0u) {
+            const float sb = ord2f(shared_bits);
+            if (cnt[qi] < p.k) { /* own list not full: keep filling it, the merge needs best-first prefixes */ }
+            else kth[qi] = p.nearest ? fminf(kth[qi], sb) : fmaxf(kth[qi], sb);
+          }
+        }
         const bool pass = valid && g == 0 && (uint32_t)qi < nqt && (cnt[qi] < p.k || maybe_enters(score, kth[qi], p.nearest));
         uint32_t m = __ballot_sync(0xffffffffu, pass);
         if (m) {
@@ -182,6 +201,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
             const uint32_t sl = __shfl_sync(0xffffffffu, slot, src);
             const uint64_t id = p.ids[sl];
             warp_list_insert(L, p.k, cnt[qi], kth[qi], sc, sl, id, p.nearest);
+          }
+          if (cnt[qi] == p.k && lane == 0) {
+            if (p.nearest) atomicMin(&cta_kth_s[qi], f2ord(kth[qi]));
+            else atomicMax(&cta_kth_s[qi], f2ord(kth[qi]));
           }
         }
       }

@@ -91,17 +91,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-// order-preserving float <-> uint32 (for atomicMax on thresholds that may be negative)
-__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
-  uint32_t b;
-#ifdef __CUDA_ARCH__
-  b = __float_as_uint(f);
-#else
-  memcpy(&b, &f, 4);
-#endif
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-
 // K-major, 128B-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version(1)<<46 | SWIZZLE_128B(2)<<61
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {

@@ -20,15 +20,6 @@ static constexpr int kRerankThreads = 128;
 static constexpr uint32_t kRerankMaxCand = 1024;   // survivors gathered per query (keys only)
 static constexpr uint32_t kRerankRows = 64;        // rows re-scored exactly per query (>= 2 K')
 
-__host__ __device__ __forceinline__ float ord2f_(uint32_t u) {
-  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(b);
-#else
-  float f; memcpy(&f, &b, 4); return f;
-#endif
-}
-
 template <int ELEM, int METRIC>
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -53,7 +44,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   // ---- 1. gather the survivors of every filter column that clear the final threshold
   const uint32_t thr_bits = p.g_thr[q];
   const bool have_bound = thr_bits != 0;
-  const float B = have_bound ? ord2f_(thr_bits) : 0.0f;
+  const float B = have_bound ? ord2f(thr_bits) : 0.0f;
   for (uint32_t cta = tid; cta < p.grid_x; cta += blockDim.x) {   // one column per thread: count, then its few entries
     const uint32_t ccnt = p.cand_cnt[(size_t)q * p.grid_x + cta];
     if (ccnt == 0xffffffffu) { ovf_s = 1; continue; }              // that column overflowed on ties: exact path
