@@ -63,7 +63,9 @@ typedef enum coltt_quant {
  *   pops the minimum distance when over capacity, i.e. keeps the K LARGEST distances, returned
  *   ascending (edge/priority_queue.go:39-69).
  * COLTT_SELECT_NEAREST: keeps the K smallest distances, ascending (what HNSW and users expect).
- * Equal scores: lower id wins and sorts first (the reference is nondeterministic here, F6). */
+ * Both are windows of ONE total order T = (score ascending, NaN after every number, then id
+ * ascending): NEAREST returns the first K entries of T, COMPAT the last K, both listed in T order.
+ * (The reference is nondeterministic among equal scores — Go map iteration, F6 — T pins it.) */
 typedef enum coltt_select { COLTT_SELECT_COMPAT = 0, COLTT_SELECT_NEAREST = 1 } coltt_select;
 
 /* COLTT_MATH_EXACT: CUDA-core kernel that reproduces the reference AVX evaluation order
