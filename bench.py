@@ -201,7 +201,7 @@ def main():
     assert L.coltt_b200_device_count() >= 1, "no sm_100 GPU: coltt_b200 has no CPU fallback"
 
     n, d, nq, k = args.rows, args.dim, args.batch, args.k
-    math_mode = {"auto": cb.MATH_FAST if os.environ.get("COLTT_BENCH_FAST", "0") == "1" else cb.MATH_EXACT,
+    math_mode = {"auto": cb.MATH_FAST,   # tcgen05 filter + exact re-rank: bit-identical results to EXACT (tests/test_gpu_fast.py)
                  "exact": cb.MATH_EXACT, "fast": cb.MATH_FAST}[args.math]
     t0 = time.perf_counter()
     rows = gen_rows(n, d, BASE_SEED + rank)

@@ -14,6 +14,17 @@ static constexpr int kBN = 256;            // shard rows per tile (MMA N): one 1
 static constexpr int kBK = 64;             // fp16 elements per K block of the resident query tile (128-byte swizzle rows)
 static constexpr int kBKB = 32;            // fp16 elements per shard-tile stage (64-byte swizzle rows)
 
+// Role timers (clock64 around every wait) are compiled in only with -DCOLTT_K2_PROF=1: the reads sit on the
+// single-thread MMA issue path, where they cost more than the work they measure.
+#ifndef COLTT_K2_PROF
+#define COLTT_K2_PROF 0
+#endif
+#if COLTT_K2_PROF
+#define K2_NOW() clock64()
+#else
+#define K2_NOW() 0ll
+#endif
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -156,7 +167,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
   GemmCand* my_buf = p.cand_buf + ((size_t)buf_slot * C) * 128 + ql;   // [cta][slot][128 queries], written rarely
   float* my_pub = p.pub + (size_t)col * p.nq + q;                        // pub[column][query]
   uint32_t ti = 0;
-  long long w_tfull = 0, t_start_e = clock64(), c_bar = 0, c_hot = 0, c_slow = 0, c_sweep = 0, n_slow = 0;
+  long long w_tfull = 0, t_start_e = K2_NOW(), c_bar = 0, c_hot = 0, c_slow = 0, c_sweep = 0, n_slow = 0;
 
   auto coef_store = [&](uint32_t idx, uint32_t row, float n2) {
     float a = 0.0f, b = NEG_INF;
@@ -181,29 +192,27 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
   for (uint32_t t = tile0; t < n_tiles; t += tile_stride, ti++) {
     const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
     const uint32_t row0 = t * kBN;
-    const long long cb0 = clock64();
+    const long long cb0 = K2_NOW();
     coef_store(et, row0 + et, n2_a);
     named_bar_sync(1, kEpiThreads);                      // coefficients of this tile visible
-    c_bar += clock64() - cb0;
+    c_bar += K2_NOW() - cb0;
     {
       const uint32_t ra = (t + tile_stride) * kBN + et;
       n2_a = ra < p.n_rows ? p.row_norm2[ra] : 0.0f;
     }
-    const long long ce0 = clock64();
+    const long long ce0 = K2_NOW();
     mbar_wait(smem_u32(tfull_bar + buf), bph);
-    w_tfull += clock64() - ce0;
+    w_tfull += K2_NOW() - ce0;
     tc_fence_after();
+    const uint32_t tbase = tmem_base + ((quarter * 32) << 16) + buf * kBN + set * CHUNKS * 32;
+    const bool drain_only = (p.dbg_flags & 1u) != 0;     // pipeline-speed probe
+    uint32_t v[32];
+    tmem_ld32(tbase, v);
 #pragma unroll 1
-    for (uint32_t half = set * CHUNKS; half < (set + 1) * CHUNKS; half++) {
-      uint32_t v[32];
-      const long long cl0 = clock64();
-      tmem_ld32(tmem_base + ((quarter * 32) << 16) + buf * kBN + half * 32, v);
+    for (uint32_t hc = 0; hc < CHUNKS; hc++) {
+      const uint32_t half = set * CHUNKS + hc;
+      const long long cl0 = K2_NOW();
       tmem_wait_ld();
-      if (half == (set + 1) * CHUNKS - 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_tempty(buf);               // this warp is done with the accumulator of tile ti
-      }
       if (p.dbg_acc && q_valid) {
 #pragma unroll
         for (int c = 0; c < 32; c++) {
@@ -211,12 +220,10 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
           if (row < p.n_rows) p.dbg_acc[(size_t)q * p.n_rows + row] = __uint_as_float(v[c]);
         }
       }
-      if (p.dbg_flags & 1u) continue;                    // pipeline-speed probe: drain only
       // hot path: 32 FFMA + a max tree + one vote; no per-element branches
       const float4* ca = reinterpret_cast<const float4*>(coef_a + half * 32);
       const float4* cb = reinterpret_cast<const float4*>(coef_b + half * 32);
       float key[32];
-      float kmax = NEG_INF;
 #pragma unroll
       for (int c4 = 0; c4 < 8; c4++) {
         const float4 a4 = ca[c4], b4 = cb[c4];
@@ -224,10 +231,22 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
         key[4 * c4 + 1] = fmaf(__uint_as_float(v[4 * c4 + 1]), a4.y, b4.y);
         key[4 * c4 + 2] = fmaf(__uint_as_float(v[4 * c4 + 2]), a4.z, b4.z);
         key[4 * c4 + 3] = fmaf(__uint_as_float(v[4 * c4 + 3]), a4.w, b4.w);
-        kmax = fmaxf(kmax, fmaxf(fmaxf(key[4 * c4 + 0], key[4 * c4 + 1]), fmaxf(key[4 * c4 + 2], key[4 * c4 + 3])));
       }
+      // v[] is dead: the next 32 columns stream out of tensor memory while this chunk is ranked
+      if (hc + 1 < CHUNKS) {
+        tmem_ld32(tbase + (hc + 1) * 32, v);
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty(buf);               // this warp is done with the accumulator of tile ti
+      }
+      if (drain_only) continue;
+      float kmax = NEG_INF;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; c4++)
+        kmax = fmaxf(kmax, fmaxf(fmaxf(key[4 * c4 + 0], key[4 * c4 + 1]), fmaxf(key[4 * c4 + 2], key[4 * c4 + 3])));
       const bool mine = kmax > thr;
-      const long long ch1 = clock64();
+      const long long ch1 = K2_NOW();
       c_hot += ch1 - cl0;
       if (__any_sync(0xffffffffu, mine)) {
         // rare path, kept small: pass mask, then each lane walks its own set bits; the key of column c
@@ -279,15 +298,15 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
             }
           }
         }
-        c_slow += clock64() - ch1;
+        c_slow += K2_NOW() - ch1;
       }
     }
-    const long long cs0 = clock64();
+    const long long cs0 = K2_NOW();
     named_bar_sync(2, kEpiThreads);                      // everyone is done reading this tile's coefficients
-    c_bar += clock64() - cs0;
+    c_bar += K2_NOW() - cs0;
     // Cross-column bound on a doubling schedule (tiles 1,2,4,8,...): the bound moves like 1/rows-seen.
     if (sweeping && !overflowed && ti == next_sweep) {
-      const long long cw0 = clock64();
+      const long long cw0 = K2_NOW();
       next_sweep = ti * 2;
       float gmax[KP];
 #pragma unroll
@@ -303,12 +322,12 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
 #pragma unroll
       for (int i = 1; i < KP; i++) G = fminf(G, gmax[i]);
       thr = fmaxf(thr, G);
-      c_sweep += clock64() - cw0;
+      c_sweep += K2_NOW() - cw0;
     }
   }
   if (p.dbg_prof && et == 0) {   // set 0, quarter 2's first lane
     p.dbg_prof[(size_t)prof_slot * 8 + 5] = (unsigned long long)w_tfull;
-    p.dbg_prof[(size_t)prof_slot * 8 + 6] = (unsigned long long)(clock64() - t_start_e);
+    p.dbg_prof[(size_t)prof_slot * 8 + 6] = (unsigned long long)(K2_NOW() - t_start_e);
     p.dbg_prof[(size_t)prof_slot * 8 + 7] = (unsigned long long)c_bar;
     p.dbg_prof2[(size_t)prof_slot * 8 + 0] = (unsigned long long)0;
     p.dbg_prof2[(size_t)prof_slot * 8 + 1] = (unsigned long long)c_hot;

@@ -87,32 +87,35 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       mbar_arrive_expect_tx(smem_u32(a_bar), KB * ABLK_BYTES);
       for (uint32_t kb = 0; kb < KB; kb++)
         tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)(kb * kBK), (int)q_tile0, smem_u32(a_bar));
-      uint32_t it = 0;
-      long long w_empty = 0, t_start = clock64();
+      uint32_t s = 0, ph = 0;
+      long long w_empty = 0, t_start = K2_NOW();
+      const bool do_pf = (p.dbg_flags & 2u) == 0;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
       // L2 prefetch runs one tile ahead with the 128-byte-wide view of the shard, so the short ring only
       // has to cover L2 latency
       {
         const uint32_t t0 = blockIdx.x;
-        if (t0 < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) { tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN)); tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN + 128)); }
+        if (do_pf && t0 < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) { tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN)); tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN + 128)); }
       }
       for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint32_t tp = t + gridDim.x;
-        for (uint32_t st = 0; st < NSTEP; st++, it++) {
-          if (tp < n_tiles && (st & 1) == 0) {
-            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), (int)(tp * kBN));
-            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), (int)(tp * kBN + 128));
+        const bool pf = do_pf && t + gridDim.x < n_tiles;
+        const int row = (int)(t * kBN), row_pf = (int)((t + gridDim.x) * kBN);
+        for (uint32_t st = 0; st < NSTEP; st++) {
+          if (pf && (st & 1) == 0) {
+            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf);
+            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf + 128);
           }
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          const long long c0 = clock64();
-          while (!mbar_try_wait(smem_u32(empty_bar + s), ph ^ 1)) __nanosleep(32);
-          w_empty += clock64() - c0;
-          mbar_arrive_expect_tx(smem_u32(full_bar + s), STAGE_BYTES);
-          tma_load_2d(smem_u32(b_stages + (size_t)s * STAGE_BYTES), &tmap, (int)(st * kBKB), (int)(t * kBN), smem_u32(full_bar + s));
+          const long long c0 = K2_NOW();
+          mbar_wait(empty0 + s * 8, ph ^ 1);
+          w_empty += K2_NOW() - c0;
+          mbar_arrive_expect_tx(full0 + s * 8, STAGE_BYTES);
+          tma_load_2d(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
+          if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
       if (p.dbg_prof) {
         p.dbg_prof[(size_t)cta_lin * 8 + 0] = (unsigned long long)w_empty;
-        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(clock64() - t_start);
+        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(K2_NOW() - t_start);
       }
     }
   } else if (warp == 1) {
@@ -120,33 +123,36 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // The whole warp walks the loop (warp-uniform control flow); one elected lane issues tcgen05.mma / commit.
     // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b F16 K-major, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
-    uint32_t it = 0, ti = 0;
-    long long w_tempty = 0, w_full = 0, t_start = clock64();
+    uint32_t s = 0, ph = 0, ti = 0;
+    long long w_tempty = 0, w_full = 0, t_start = K2_NOW();
     mbar_wait(smem_u32(a_bar), 0);
     tc_fence_after();
-    const uint32_t a_addr = smem_u32(a_smem);
+    // single-thread critical path: ring position, phase and descriptors advance by constant adds
+    const uint64_t a_desc0 = make_desc_sw128(smem_u32(a_smem));
+    const uint64_t b_desc0 = make_desc_sw64(smem_u32(b_stages));
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ti++) {
       const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
-      const long long c0 = clock64();
-      while (!mbar_try_wait(smem_u32(tempty_bar + buf), bph ^ 1)) __nanosleep(20);   // epilogue drained this accumulator
-      w_tempty += clock64() - c0;
+      const long long c0 = K2_NOW();
+      mbar_wait(smem_u32(tempty_bar + buf), bph ^ 1);    // epilogue drained this accumulator
+      w_tempty += K2_NOW() - c0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * kBN;
-      for (uint32_t st = 0; st < NSTEP; st++, it++) {
-        const uint32_t s = it % NS, ph = (it / NS) & 1;
-        const long long c1 = clock64();
-        while (!mbar_try_wait(smem_u32(full_bar + s), ph)) __nanosleep(20);
-        w_full += clock64() - c1;
+      uint64_t a_desc = a_desc0;
+      for (uint32_t st = 0; st < NSTEP; st++) {
+        const long long c1 = K2_NOW();
+        mbar_wait(full0 + s * 8, ph);
+        w_full += K2_NOW() - c1;
         tc_fence_after();
-        const uint32_t b_addr = smem_u32(b_stages + (size_t)s * STAGE_BYTES);
-        const uint32_t a_blk = a_addr + (st >> 1) * ABLK_BYTES + (st & 1) * 64;   // 32 elements = 64 B into the 128 B swizzle row
+        const uint64_t b_desc = b_desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
         if (elect_one()) {
-#pragma unroll
-          for (uint32_t j = 0; j < kBKB / 16; j++)
-            umma_f16_ss(d_tmem, make_desc_sw128(a_blk + j * 32), make_desc_sw64(b_addr + j * 32), idesc, (st | j) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(empty_bar + s));           // frees the smem stage when these MMAs retire
+          umma_f16_ss(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
+          umma_f16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);     // +32 B: the next 16 K elements
+          umma_commit(empty0 + s * 8);                    // frees the smem stage when these MMAs retire
         }
         __syncwarp();
+        a_desc += (st & 1) ? (uint64_t)((ABLK_BYTES - 64) >> 4) : 4ull;   // 32 elements = 64 B into the 128 B swizzle row, then the next K block
+        if (++s == NS) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(smem_u32(tfull_bar + buf));   // accumulator complete
       __syncwarp();
@@ -154,7 +160,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (p.dbg_prof && lane == 0) {
       p.dbg_prof[(size_t)cta_lin * 8 + 2] = (unsigned long long)w_tempty;
       p.dbg_prof[(size_t)cta_lin * 8 + 3] = (unsigned long long)w_full;
-      p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(clock64() - t_start);
+      p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(K2_NOW() - t_start);
     }
   } else {
     auto arrive = [&](uint32_t buf) { mbar_arrive(smem_u32(tempty_bar + buf)); };
@@ -201,6 +207,8 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
     return fail(COLTT_ERR_UNSUPPORTED, "FAST: query tile does not fit shared memory (dim > 768 fp16)");
   uint32_t ns = (uint32_t)((total - a_bytes - misc) / stage);
   if (ns > 8) ns = 8;
+  static const char* ns_env = getenv("COLTT_FAST_NS");     // debug: shrink the stage ring
+  if (ns_env && atoi(ns_env) >= 2 && (uint32_t)atoi(ns_env) < ns) ns = (uint32_t)atoi(ns_env);
   plan->kblocks = kblocks;
   plan->kprime = kprime;
   plan->cand_cap = cap;

@@ -75,58 +75,66 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
   if (warp == 0) {
     // ================= TMA producer (both CTAs: own half of every shard tile) =================
     if (lane == 0) {
-      uint32_t it = 0;
-      long long w_empty = 0, t_start = clock64();
+      uint32_t s = 0, ph = 0;
+      long long w_empty = 0, t_start = K2_NOW();
       const int row_off = (int)(rank * HALF_ROWS);
-      if (pair < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(pair * kBN) + row_off);
+      const bool do_pf = (p.dbg_flags & 2u) == 0;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
+      if (do_pf && pair < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(pair * kBN) + row_off);
       for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
-        const uint32_t tp = t + n_pairs;
-        for (uint32_t st = 0; st < NSTEP; st++, it++) {
-          if (tp < n_tiles && (st & 1) == 0) tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), (int)(tp * kBN) + row_off);
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          const long long c0 = clock64();
-          while (!mbar_try_wait(smem_u32(empty_bar + s), ph ^ 1)) __nanosleep(32);
-          w_empty += clock64() - c0;
+        const bool pf = do_pf && t + n_pairs < n_tiles;
+        const int row = (int)(t * kBN) + row_off, row_pf = (int)((t + n_pairs) * kBN) + row_off;
+        for (uint32_t st = 0; st < NSTEP; st++) {
+          if (pf && (st & 1) == 0) tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf);
+          const long long c0 = K2_NOW();
+          mbar_wait(empty0 + s * 8, ph ^ 1);
+          w_empty += K2_NOW() - c0;
           // the leader's barrier collects both halves: it expects 2 x STAGE_BYTES, each CTA's load signals it
-          if (rank == 0) mbar_arrive_expect_tx(smem_u32(full_bar + s), 2 * STAGE_BYTES);
-          tma_load_2d_pair(smem_u32(b_stages + (size_t)s * STAGE_BYTES), &tmap, (int)(st * kBKB), (int)(t * kBN) + row_off, smem_u32(full_bar + s));
+          if (rank == 0) mbar_arrive_expect_tx(full0 + s * 8, 2 * STAGE_BYTES);
+          tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
+          if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
       if (p.dbg_prof) {
         p.dbg_prof[(size_t)cta_lin * 8 + 0] = (unsigned long long)w_empty;
-        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(clock64() - t_start);
+        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(K2_NOW() - t_start);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
+    // This loop is the single-thread critical path of the kernel: ring position, phase and both operand
+    // descriptors advance by constant adds (no division, no descriptor rebuild, no timers) so that one
+    // iteration (wait, 2 x tcgen05.mma, commit) issues in well under the 2 x 128 cycles the MMAs take.
     if (rank == 0) {
       // M = 256 (M>>4 = 16 at bit 24), N = 256
       const uint32_t idesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((256u >> 4) << 24);
-      uint32_t it = 0, ti = 0;
-      long long w_tempty = 0, w_full = 0, t_start = clock64();
-      const uint32_t a_addr = smem_u32(a_smem);
+      uint32_t s = 0, ph = 0, ti = 0;
+      long long w_tempty = 0, w_full = 0, t_start = K2_NOW();
+      const uint64_t a_desc0 = make_desc_sw128(smem_u32(a_smem));
+      const uint64_t b_desc0 = make_desc_sw64(smem_u32(b_stages));
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       for (uint32_t t = pair; t < n_tiles; t += n_pairs, ti++) {
         const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
-        const long long c0 = clock64();
-        while (!mbar_try_wait(smem_u32(tempty_bar + buf), bph ^ 1)) __nanosleep(20);   // both CTAs' epilogues drained it
-        w_tempty += clock64() - c0;
+        const long long c0 = K2_NOW();
+        mbar_wait(smem_u32(tempty_bar + buf), bph ^ 1);    // both CTAs' epilogues drained it
+        w_tempty += K2_NOW() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kBN;
-        for (uint32_t st = 0; st < NSTEP; st++, it++) {
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          const long long c1 = clock64();
-          while (!mbar_try_wait(smem_u32(full_bar + s), ph)) __nanosleep(20);
-          w_full += clock64() - c1;
+        uint64_t a_desc = a_desc0;                           // (start address >> 4) lives in the low 14 bits
+        for (uint32_t st = 0; st < NSTEP; st++) {
+          const long long c1 = K2_NOW();
+          mbar_wait(full0 + s * 8, ph);
+          w_full += K2_NOW() - c1;
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(b_stages + (size_t)s * STAGE_BYTES);
-          const uint32_t a_blk = a_addr + (st >> 1) * ABLK_BYTES + (st & 1) * 64;
+          const uint64_t b_desc = b_desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
           if (elect_one()) {
-#pragma unroll
-            for (uint32_t j = 0; j < kBKB / 16; j++)
-              umma_f16_ss_pair(d_tmem, make_desc_sw128(a_blk + j * 32), make_desc_sw64(b_addr + j * 32), idesc, (st | j) != 0 ? 1u : 0u);
-            umma_commit_pair(smem_u32(empty_bar + s), 3);          // stage free in both CTAs
+            umma_f16_ss_pair(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
+            umma_f16_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);       // +32 B: the next 16 K elements
+            umma_commit_pair(empty0 + s * 8, 3);             // stage free in both CTAs
           }
           __syncwarp();
+          a_desc += (st & 1) ? (uint64_t)((ABLK_BYTES - 64) >> 4) : 4ull;    // +64 B inside a K block, then the next block
+          if (++s == NS) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit_pair(smem_u32(tfull_bar + buf), 3);   // accumulator ready in both CTAs
         __syncwarp();
@@ -134,7 +142,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
       if (p.dbg_prof && lane == 0) {
         p.dbg_prof[(size_t)cta_lin * 8 + 2] = (unsigned long long)w_tempty;
         p.dbg_prof[(size_t)cta_lin * 8 + 3] = (unsigned long long)w_full;
-        p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(clock64() - t_start);
+        p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(K2_NOW() - t_start);
       }
     }
   } else {

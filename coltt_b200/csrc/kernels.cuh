@@ -84,7 +84,7 @@ struct GemmParams {
   unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
   unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
   uint32_t mma_split;        // independent accumulation chains per tile (1, 2 or 4)
-  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe)
+  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe); bit1: no L2 prefetch; bit2: spin-wait (no nanosleep)
 };
 struct GemmPlan {
   uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;

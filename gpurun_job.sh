@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_flat.py tests/test_gpu_fast.py -m gpu -q 2>&1 | tail -8) > gpurun_out/pytest_flat.log
-(timeout 600 python tools/probe_shapes.py 2>&1 | tail -16) > gpurun_out/probe.log
-(timeout 600 python tools/probe_hnsw.py 2>&1 | tail -3) > gpurun_out/probe_hnsw.log
-tail -n 4 gpurun_out/pytest_flat.log; cat gpurun_out/probe.log; cat gpurun_out/probe_hnsw.log
+(timeout 900 python -m pytest tests/test_gpu_fast.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/pytest_fast.log
+run() { echo "== $*"; env "$@" timeout 300 python tools/probe_k2.py 2>&1 | grep -E "K2 N=" ; }
+(
+run A=1
+run COLTT_DEBUG_FLAGS=1
+run NQ=128
+run COLTT_FAST_NS=3
+) > gpurun_out/k2_knobs2.log 2>&1
+tail -3 gpurun_out/pytest_fast.log; cat gpurun_out/k2_knobs2.log
+(timeout 600 python bench.py --steps 200 --warmup 5 2>&1 | tail -2) > gpurun_out/bench_fast.log; cat gpurun_out/bench_fast.log
