@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcoltt_b200.so")
+LIB_PATH = os.environ.get("COLTT_B200_LIB") or os.path.join(_HERE, "lib", "libcoltt_b200.so")   # env override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 # every symbol include/coltt_b200.h declares (tests assert the library exports all of them)

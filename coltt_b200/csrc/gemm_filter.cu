@@ -82,40 +82,35 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // Whole warp walks the loop (warp-uniform values stay in uniform registers), one elected lane issues.  The
+    // ring is shorter than the L2 round trip, so "stage free" -> "load issued" is on the critical path: the load
+    // goes out first, the L2 prefetch of the next tile (same K slice, one tile ahead) after it.
+    if (elect_one()) {
       // the query tile: A operand, loaded once (rows beyond nq are zero-filled by TMA)
       mbar_arrive_expect_tx(smem_u32(a_bar), KB * ABLK_BYTES);
       for (uint32_t kb = 0; kb < KB; kb++)
         tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)(kb * kBK), (int)q_tile0, smem_u32(a_bar));
-      uint32_t s = 0, ph = 0;
-      long long w_empty = 0, t_start = K2_NOW();
-      const bool do_pf = (p.dbg_flags & 2u) == 0;
-      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
-      // L2 prefetch runs one tile ahead with the 128-byte-wide view of the shard, so the short ring only
-      // has to cover L2 latency
-      {
-        const uint32_t t0 = blockIdx.x;
-        if (do_pf && t0 < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) { tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN)); tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(t0 * kBN + 128)); }
-      }
-      for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const bool pf = do_pf && t + gridDim.x < n_tiles;
-        const int row = (int)(t * kBN), row_pf = (int)((t + gridDim.x) * kBN);
-        for (uint32_t st = 0; st < NSTEP; st++) {
-          if (pf && (st & 1) == 0) {
-            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf);
-            tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf + 128);
-          }
-          const long long c0 = K2_NOW();
-          mbar_wait(empty0 + s * 8, ph ^ 1);
-          w_empty += K2_NOW() - c0;
+    }
+    __syncwarp();
+    uint32_t s = 0, ph = 0;
+    const bool do_pf = (p.dbg_flags & 2u) == 0;
+    const uint32_t pf_mask = p.pf_inner / kBKB - 1;          // pf_inner / kBKB is a power of two
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
+    if (do_pf && blockIdx.x < n_tiles && elect_one())
+      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), (int)(blockIdx.x * kBN));
+    __syncwarp();
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int row = (int)(t * kBN), row_pf = row + (int)(gridDim.x * kBN);
+      const bool pf = do_pf && t + gridDim.x < n_tiles;
+      for (uint32_t st = 0; st < NSTEP; st++) {
+        mbar_wait(empty0 + s * 8, ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full0 + s * 8, STAGE_BYTES);
           tma_load_2d(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
-          if (++s == NS) { s = 0; ph ^= 1; }
+          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), row_pf);
         }
-      }
-      if (p.dbg_prof) {
-        p.dbg_prof[(size_t)cta_lin * 8 + 0] = (unsigned long long)w_empty;
-        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(K2_NOW() - t_start);
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -266,9 +261,18 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   rc = encode_map(&tmq, p_in.q_f16, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride * 2, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   // L2 prefetch view of the shard: whole 128-byte lines, 128 rows per request
-  rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, kBK, 128, CU_TENSOR_MAP_SWIZZLE_NONE);
+  static const char* pfi_env = getenv("COLTT_PF_INNER");
+  static const char* pfd_env = getenv("COLTT_PF_DIST");
+  uint32_t pf_inner = pfi_env ? (uint32_t)atoi(pfi_env) : 128u, pf_dist = pfd_env ? (uint32_t)atoi(pfd_env) : 1u;
+  if (pf_inner != 32 && pf_inner != 64 && pf_inner != 128 && pf_inner != 256) pf_inner = 64;
+  if (pf_dist < 1 || pf_dist > 4096) pf_dist = 16;
+  rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, pf_inner, plan.pair ? kBN / 2 : kBN, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   GemmParams p = p_in;
+  p.rows = static_cast<const uint8_t*>(d_rows);
+  p.row_stride = row_stride;
+  p.pf_inner = pf_inner;
+  p.pf_dist = pf_dist;
   p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.cand_out_cap = plan.cand_out_cap; p.n_stages = plan.n_stages;
   if (plan.pair) {
     plan.grid_x = 2 * cols;

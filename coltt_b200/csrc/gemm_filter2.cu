@@ -74,30 +74,31 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs: own half of every shard tile) =================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      long long w_empty = 0, t_start = K2_NOW();
-      const int row_off = (int)(rank * HALF_ROWS);
-      const bool do_pf = (p.dbg_flags & 2u) == 0;
-      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
-      if (do_pf && pair < n_tiles) for (uint32_t kb = 0; kb < KB; kb++) tma_prefetch_2d(&tmap_pf, (int)(kb * kBK), (int)(pair * kBN) + row_off);
-      for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
-        const bool pf = do_pf && t + n_pairs < n_tiles;
-        const int row = (int)(t * kBN) + row_off, row_pf = (int)((t + n_pairs) * kBN) + row_off;
-        for (uint32_t st = 0; st < NSTEP; st++) {
-          if (pf && (st & 1) == 0) tma_prefetch_2d(&tmap_pf, (int)((st >> 1) * kBK), row_pf);
-          const long long c0 = K2_NOW();
-          mbar_wait(empty0 + s * 8, ph ^ 1);
-          w_empty += K2_NOW() - c0;
+    // The ring (4 x 8 KB per CTA) is shorter than the L2 round trip, so the time from "stage free" to "load
+    // issued" is on the kernel's critical path exactly like the MMA issue loop: the whole warp walks the loop
+    // (warp-uniform values stay in uniform registers), one elected lane issues, the load goes out first and
+    // the L2 prefetch of the next tile (same K slice, one tile ahead) after it.
+    uint32_t s = 0, ph = 0;
+    const int row_off = (int)(rank * HALF_ROWS);
+    const bool do_pf = (p.dbg_flags & 2u) == 0;
+    const uint32_t pf_mask = p.pf_inner / kBKB - 1;          // pf_inner / kBKB is a power of two
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
+    if (do_pf && pair < n_tiles && elect_one())
+      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), (int)(pair * kBN) + row_off);
+    __syncwarp();
+    for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+      const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
+      const bool pf = do_pf && t + n_pairs < n_tiles;
+      for (uint32_t st = 0; st < NSTEP; st++) {
+        mbar_wait(empty0 + s * 8, ph ^ 1);
+        if (elect_one()) {
           // the leader's barrier collects both halves: it expects 2 x STAGE_BYTES, each CTA's load signals it
           if (rank == 0) mbar_arrive_expect_tx(full0 + s * 8, 2 * STAGE_BYTES);
           tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
-          if (++s == NS) { s = 0; ph ^= 1; }
+          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), row_pf);
         }
-      }
-      if (p.dbg_prof) {
-        p.dbg_prof[(size_t)cta_lin * 8 + 0] = (unsigned long long)w_empty;
-        p.dbg_prof[(size_t)cta_lin * 8 + 1] = (unsigned long long)(K2_NOW() - t_start);
+        __syncwarp();
+        if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {

@@ -73,6 +73,8 @@ struct GemmParams {
   const __half* q_f16;       // [nq][q_stride] lowered queries, zero padded to kblocks*64
   uint32_t q_stride;
   const float* row_norm2;    // [n_rows]
+  const uint8_t* rows;       // the shard's row matrix (linear L2 prefetch; the operands themselves go through TMA)
+  uint32_t row_stride;       // bytes
   int metric, nearest;
   uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over CTAs), zero-initialised
   float* pub;                // [grid_x][nq] best key each CTA has seen per query, initialised to NaN
@@ -84,7 +86,8 @@ struct GemmParams {
   unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
   unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
   uint32_t mma_split;        // independent accumulation chains per tile (1, 2 or 4)
-  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe); bit1: no L2 prefetch; bit2: spin-wait (no nanosleep)
+  uint32_t pf_inner, pf_dist; // L2 prefetch box width (fp16 elements per row, multiple of 32) and lead in stages
+  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe); bit1: no L2 prefetch; bit4: no evict_first hint on the operand loads
 };
 struct GemmPlan {
   uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
