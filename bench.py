@@ -286,10 +286,12 @@ def main():
 
     # ---- dominant-kernel time, per launch, with CUDA events on its stream (instrumented pass)
     scan_ms = []
+    sp.set_timing(True)          # per-phase events are off during the timed regions above and below
     for i in range(min(args.steps, 20)):
         step_dev(i)
         torch.cuda.synchronize(dev)
         scan_ms.append(sp.last_timing_ms())
+    sp.set_timing(False)
     kern_ms = float(np.mean([x["scan"] for x in scan_ms]))
     parts = {kk: float(np.mean([x[kk] for x in scan_ms])) for kk in ("prep", "scan", "rerank", "merge")}
 

@@ -29,6 +29,20 @@ __device__ __forceinline__ float load1(const uint8_t* row, uint32_t idx, const f
 }
 
 
+// dot += q*r exactly as the reference's unfused `dot = dot + v1*v2` (avx.cpp:60) rounds it.  On the fp16 ("bf16")
+// stores both operands are decoded binary16 values: at most 11 significant bits each and magnitudes >= 2^-24,
+// so q*r has <= 22 significant bits and lies far inside the fp32 normal range — the product is exact in fp32
+// and round(q*r + acc) == round(round(q*r) + acc).  One FFMA therefore produces the reference's bits at half
+// the issue cost (tests/test_oracle.py::test_fp16_products_are_exact_in_fp32 pins the premise).
+// fp32 rows keep the two roundings, and so does the f8-compat store: its decoder leaves a stray mantissa bit and
+// fp32-subnormal values for codes >= 0x80 (float8.go:233-266), whose products underflow.
+// (L2's (q-r)^2 has no such property: q-r may need > 24 bits.)
+template <int ELEM>
+__device__ __forceinline__ float dot_step(float acc, float q, float r) {
+  if (ELEM == ELEM_F16) return __fmaf_rn(q, r, acc);
+  return add_rn(acc, mul_rn(q, r));
+}
+
 // lane -> (row within a 16-row group, half g): the 8 lanes of each quarter-warp touch 8 different rows
 __device__ __forceinline__ uint32_t lane_row16(uint32_t lane) { return (lane & 7) + 8 * (lane >> 4); }
 __device__ __forceinline__ uint32_t lane_half(uint32_t lane) { return (lane >> 3) & 1; }

@@ -150,10 +150,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
       for (int qi = 0; qi < QT; qi++) {
         const float4 qv = *reinterpret_cast<const float4*>(qb + (size_t)qi * p.q_stride + i8 * 8);
         if (METRIC == COLTT_COSINE) {
-          acc[qi][0] = add_rn(acc[qi][0], mul_rn(qv.x, rv[0]));  // avx.cpp:60 dot += v1*v2
-          acc[qi][1] = add_rn(acc[qi][1], mul_rn(qv.y, rv[1]));
-          acc[qi][2] = add_rn(acc[qi][2], mul_rn(qv.z, rv[2]));
-          acc[qi][3] = add_rn(acc[qi][3], mul_rn(qv.w, rv[3]));
+          acc[qi][0] = dot_step<ELEM>(acc[qi][0], qv.x, rv[0]);  // avx.cpp:60 dot += v1*v2
+          acc[qi][1] = dot_step<ELEM>(acc[qi][1], qv.y, rv[1]);
+          acc[qi][2] = dot_step<ELEM>(acc[qi][2], qv.z, rv[2]);
+          acc[qi][3] = dot_step<ELEM>(acc[qi][3], qv.w, rv[3]);
         } else {
           float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
           acc[qi][0] = add_rn(acc[qi][0], mul_rn(d0, d0));        // avx.cpp:21-23
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
         for (uint32_t d = full8; d < p.dim; d++) {  // scalar tail, avx.cpp:27-31 / :68-72
           float rv = load1<ELEM>(rowp, d - e0, lut_s);
           float qv = q_s[(size_t)qi * p.q_stride + d];
-          if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
+          if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
           else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
         }
         const float score = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn_s[qi], nb) : sqrt_via_f64(tot);
@@ -299,7 +299,7 @@ static int launch_qt(const ScanParams& p, const ScanPlan& plan, cudaStream_t str
 #define COLTT_LAUNCH(QT)                                                                                         \
   {                                                                                                              \
     auto kfn = flat_scan_kernel<ELEM, METRIC, QT>;                                                               \
-    COLTT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));    \
+    { int arc = kernel_attrs(kfn, plan.smem_bytes); if (arc) return arc; }    \
     kfn<<<grid, block, plan.smem_bytes, stream>>>(p);                                                            \
     count_launch();                                                                                              \
   }

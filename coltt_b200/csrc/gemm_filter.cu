@@ -249,25 +249,42 @@ uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows) {
   return (plan.n_cols < n_tiles ? plan.n_cols : n_tiles) * kEpiSets;
 }
 
-int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const void* d_rows, uint32_t row_stride, cudaStream_t stream) {
-  CUtensorMap tm, tmq, tmpf;
+int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const void* d_rows, uint32_t row_stride, cudaStream_t stream,
+                       GemmMapCache* cache) {
+  static_assert(sizeof(CUtensorMap) == 128, "GemmMapCache holds CUtensorMap as 128 opaque bytes");
+  GemmMapCache local;
+  GemmMapCache& mc = cache ? *cache : local;
+  CUtensorMap& tm = *reinterpret_cast<CUtensorMap*>(mc.maps[0]);
+  CUtensorMap& tmq = *reinterpret_cast<CUtensorMap*>(mc.maps[1]);
+  CUtensorMap& tmpf = *reinterpret_cast<CUtensorMap*>(mc.maps[2]);
   GemmPlan plan = plan_in;
   const uint32_t n_tiles = (p_in.n_rows + kBN - 1) / kBN;
   const uint32_t cols = gemm_filter_cols(plan, p_in.n_rows) / kEpiSets;   // CTAs (or pairs) along x
-  // shard tile stages: 256 (or 128 per CTA of a pair) rows x 32 fp16 (64 B), 64B swizzle
-  int rc = encode_map(&tm, d_rows, p_in.dim, p_in.n_rows, row_stride, kBKB, plan.pair ? kBN / 2 : kBN, CU_TENSOR_MAP_SWIZZLE_64B);
-  if (rc) return rc;
-  // queries: [nq][q_stride] fp16, zero padded to kblocks*64 columns; box = 64 x 128 rows, 128B swizzle
-  rc = encode_map(&tmq, p_in.q_f16, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride * 2, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  // L2 prefetch view of the shard: whole 128-byte lines, 128 rows per request
   static const char* pfi_env = getenv("COLTT_PF_INNER");
   static const char* pfd_env = getenv("COLTT_PF_DIST");
   uint32_t pf_inner = pfi_env ? (uint32_t)atoi(pfi_env) : 128u, pf_dist = pfd_env ? (uint32_t)atoi(pfd_env) : 1u;
   if (pf_inner != 32 && pf_inner != 64 && pf_inner != 128 && pf_inner != 256) pf_inner = 64;
   if (pf_dist < 1 || pf_dist > 4096) pf_dist = 16;
-  rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, pf_inner, plan.pair ? kBN / 2 : kBN, CU_TENSOR_MAP_SWIZZLE_NONE);
-  if (rc) return rc;
+  const uint32_t box_rows = plan.pair ? kBN / 2 : kBN;
+  int rc;
+  if (mc.rows != d_rows || mc.n_rows != p_in.n_rows || mc.dim != p_in.dim || mc.row_stride != row_stride || mc.box_rows != box_rows ||
+      mc.pf_inner != pf_inner) {
+    mc.rows = nullptr;
+    // shard tile stages: 256 (or 128 per CTA of a pair) rows x 32 fp16 (64 B), 64B swizzle
+    rc = encode_map(&tm, d_rows, p_in.dim, p_in.n_rows, row_stride, kBKB, box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    // L2 prefetch view of the shard: whole 128-byte lines, 128 rows per request
+    rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, pf_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    mc.rows = d_rows; mc.n_rows = p_in.n_rows; mc.dim = p_in.dim; mc.row_stride = row_stride; mc.box_rows = box_rows; mc.pf_inner = pf_inner;
+  }
+  if (mc.q != p_in.q_f16 || mc.nq != p_in.nq || mc.q_stride != p_in.q_stride) {
+    mc.q = nullptr;
+    // queries: [nq][q_stride] fp16, zero padded to kblocks*64 columns; box = 64 x 128 rows, 128B swizzle
+    rc = encode_map(&tmq, p_in.q_f16, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride * 2, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    mc.q = p_in.q_f16; mc.nq = p_in.nq; mc.q_stride = p_in.q_stride;
+  }
   GemmParams p = p_in;
   p.rows = static_cast<const uint8_t*>(d_rows);
   p.row_stride = row_stride;
@@ -281,10 +298,10 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   (void)n_tiles;
   dim3 grid(cols, plan.grid_y);
   if (plan.kprime == 16) {
-    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    { int arc = kernel_attrs(gemm_filter_kernel<16>, plan.smem_bytes); if (arc) return arc; }
     gemm_filter_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
   } else {
-    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    { int arc = kernel_attrs(gemm_filter_kernel<32>, plan.smem_bytes); if (arc) return arc; }
     gemm_filter_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
   }
   count_launch();

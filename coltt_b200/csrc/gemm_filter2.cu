@@ -161,10 +161,10 @@ int launch_gemm_filter_pair(const CUtensorMap& tm, const CUtensorMap& tmq, const
                             cudaStream_t stream) {
   dim3 grid(plan.grid_x, plan.grid_y);
   if (plan.kprime == 16) {
-    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    { int arc = kernel_attrs(gemm_filter_pair_kernel<16>, plan.smem_bytes); if (arc) return arc; }
     gemm_filter_pair_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
   } else {
-    COLTT_CUDA(cudaFuncSetAttribute(gemm_filter_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+    { int arc = kernel_attrs(gemm_filter_pair_kernel<32>, plan.smem_bytes); if (arc) return arc; }
     gemm_filter_pair_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
   }
   count_launch();

@@ -452,10 +452,10 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   p.ef = ef; p.visited = (uint32_t*)h->visited.p; p.visited_words = words; p.out = (Hit*)h->out.p; p.out_counts = (int*)h->counts.p;
   p.out_stride = (uint32_t)k; p.stats = h->d_stats;
   if (h->metric == COLTT_COSINE) {
-    COLTT_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<COLTT_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int arc = kernel_attrs(hnsw_search_kernel<COLTT_COSINE>, smem); if (arc) return arc; }
     hnsw_search_kernel<COLTT_COSINE><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
   } else {
-    COLTT_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<COLTT_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int arc = kernel_attrs(hnsw_search_kernel<COLTT_EUCLIDEAN>, smem); if (arc) return arc; }
     hnsw_search_kernel<COLTT_EUCLIDEAN><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
   }
   count_launch();

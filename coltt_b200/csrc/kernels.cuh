@@ -25,6 +25,9 @@ struct PrepParams {
   uint32_t deq_stride;
   __half* f16_out;        // nullable: fp16 copy [n][f16_stride], zero padded
   uint32_t f16_stride;
+  uint32_t* fill_ptr[3];  // nullable: 32-bit words to initialise in the same launch (search scratch)
+  size_t fill_words[3];
+  uint32_t fill_value[3];
 };
 int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream);
 
@@ -93,8 +96,17 @@ struct GemmPlan {
   uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
   size_t smem_bytes;
 };
+// The three TMA descriptors of a launch (shard tiles, query tile, L2-prefetch view), kept with the search scratch
+// and re-encoded only when the tensor they describe changes (cuTensorMapEncodeTiled is host work per search).
+struct GemmMapCache {
+  alignas(64) unsigned char maps[3][128];   // CUtensorMap x3 (opaque here: this header does not pull in <cuda.h>)
+  const void* rows = nullptr;
+  const void* q = nullptr;
+  uint32_t n_rows = 0, dim = 0, row_stride = 0, box_rows = 0, pf_inner = 0, nq = 0, q_stride = 0;
+};
 int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
-int launch_gemm_filter(const GemmParams& p, const GemmPlan& plan, const void* d_rows, uint32_t row_stride, cudaStream_t stream);
+int launch_gemm_filter(const GemmParams& p, const GemmPlan& plan, const void* d_rows, uint32_t row_stride, cudaStream_t stream,
+                       GemmMapCache* cache = nullptr);
 uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows);
 
 struct RerankParams {
@@ -112,6 +124,11 @@ struct RerankParams {
   uint32_t out_stride;
   int* out_counts;           // [nq]
   uint32_t* flags;           // [nq] 1 = margin not certified: the caller re-runs that query EXACT
+  // The last CTA to finish compacts the flagged queries for the exact re-run that follows in the stream:
+  uint32_t* done_ctr;        // arrival counter, zero before the launch; the last CTA resets it
+  uint32_t* q_map;           // [nq] out: the flagged queries
+  uint32_t* n_bad;           // [1]  out: how many (always written)
+  unsigned long long* stat_fallbacks;  // nullable: running total of flagged queries (statistics)
 };
 int launch_rerank(const RerankParams& p, cudaStream_t stream);
 

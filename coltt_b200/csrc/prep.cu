@@ -7,7 +7,7 @@
 //                                     here computed once per row at ingest, same lane order, 4 B/row)
 // One warp per vector.  The Normalize sum is inherently sequential (its rounding sequence is
 // part of the parity contract), so lane 0 walks the row out of shared memory; everything
-// else is lane-parallel.  HBM traffic: reads dim*4 B, writes dim*elem B (+ optional fp32/fp16
+// else (including the rounded squares the chain adds up) is lane-parallel.  HBM traffic: reads dim*4 B, writes dim*elem B (+ optional fp32/fp16
 // query copies) per vector — an ingest-time cost, not on the search path.
 #include "kernels.cuh"
 #include "store.h"
@@ -20,18 +20,35 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t dim = p.dim;
-  float* x = smem_f + (size_t)warp * p.smem_stride;
+  float* x = smem_f + (size_t)warp * 2 * p.smem_stride;
+  float* sq = x + p.smem_stride;   // x[d]*x[d], rounded: the products are lane-parallel, only the adds are a chain
+
+  // Scratch initialisation for the search that follows (the FAST path's bound / count / published-maximum
+  // arrays): folded into this launch so that no memset nodes sit between the query prep and the scan.
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    uint32_t* fp = p.fill_ptr[f];
+    if (fp)
+      for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < p.fill_words[f]; w += (size_t)gridDim.x * blockDim.x) fp[w] = p.fill_value[f];
+  }
 
   for (size_t i = (size_t)blockIdx.x * warps_per_block + warp; i < p.n; i += (size_t)gridDim.x * warps_per_block) {
     const float* src = p.in + i * (size_t)p.in_stride;
-    for (uint32_t d = lane; d < dim; d += 32) x[d] = src[d];
+    for (uint32_t d = lane; d < dim; d += 32) { const float v = src[d]; x[d] = v; sq[d] = mul_rn(v, v); }
+    for (uint32_t d = dim + lane; d < p.smem_stride; d += 32) sq[d] = 0.0f;
     __syncwarp();
 
     if (p.normalize) {
       float norm = 0.0f;
       if (lane == 0) {
-        // edge/vectorstore.go:176-178: for i := range v { norm += v[i] * v[i] }  (unfused, in order)
-        for (uint32_t d = 0; d < dim; d++) norm = add_rn(norm, mul_rn(x[d], x[d]));
+        // edge/vectorstore.go:176-178: for i := range v { norm += v[i] * v[i] }  (unfused, in order).
+        // The rounded products were formed above by all lanes; this chain is the sequence of adds only.
+        const uint32_t d4 = dim / 4 * 4;
+        for (uint32_t d = 0; d < d4; d += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sq + d);
+          norm = add_rn(add_rn(add_rn(add_rn(norm, s4.x), s4.y), s4.z), s4.w);
+        }
+        for (uint32_t d = d4; d < dim; d++) norm = add_rn(norm, sq[d]);
       }
       norm = __shfl_sync(0xffffffffu, norm, 0);
       if (norm == 0.0f) {
@@ -98,7 +115,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
 int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream) {
   if (p.n == 0) return COLTT_OK;
   // warps per block bounded by shared memory: one fp32 copy of the vector per warp
-  const size_t per_warp = (size_t)p.smem_stride * sizeof(float);
+  if (p.smem_stride % 4) return fail(COLTT_ERR_INVALID, "prep: smem_stride must be a multiple of 4 floats");
+  const size_t per_warp = (size_t)p.smem_stride * sizeof(float) * 2;   // the vector and its squares
   int warps = 8;
   while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
   if (per_warp * warps > 227 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "dim too large for the ingest kernel");
@@ -106,7 +124,7 @@ int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream) {
   const size_t blocks_needed = (p.n + warps - 1) / warps;
   const int grid = (int)(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
   auto k = elem == ELEM_F32 ? prep_rows_kernel<ELEM_F32> : (elem == ELEM_F16 ? prep_rows_kernel<ELEM_F16> : prep_rows_kernel<ELEM_F8C>);
-  COLTT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { int arc = kernel_attrs(k, smem); if (arc) return arc; }
   k<<<grid, warps * 32, smem, stream>>>(p);
   count_launch();
   COLTT_CUDA(cudaGetLastError());

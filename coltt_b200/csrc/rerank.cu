@@ -9,51 +9,95 @@
 //   scores differ by at most eps (fp32 accumulation-order error over exact fp16 x fp16 products),
 //   so the answer is provably the EXACT answer when the exact K-th score clears B by eps.
 // Queries that cannot be certified (heavy ties at the threshold) are flagged and re-run on the
-// exact path by the caller.  Traffic: ~2K rows of dim*2 bytes per query — negligible next to the scan.
+// exact path by the caller (the last CTA to finish compacts them into a list).  Traffic: ~2K rows of dim*2 bytes per query — negligible next to the scan.
 #include "exact_math.cuh"
 #include "store.h"
 #include "topk.cuh"
 
 namespace coltt {
 
-static constexpr int kRerankThreads = 128;
+static constexpr int kRerankThreads = 256;
 static constexpr uint32_t kRerankMaxCand = 1024;   // survivors gathered per query (keys only)
 static constexpr uint32_t kRerankRows = 64;        // rows re-scored exactly per query (>= 2 K')
+
+// shared-memory layout (byte offsets from the dynamic base; offsets, not rounded pointers, so that every access
+// stays in the shared address space and compiles to LDS/STS)
+struct RerankSmem {
+  uint32_t q, row, key, sel, score, n2, id, rows, total;
+  __host__ __device__ RerankSmem(uint32_t q_stride, uint32_t row_stride) {
+    q = 0;                                   // float  [q_stride]        (bulk-copied: 16-byte multiple)
+    row = q + q_stride * 4;                  // u32    [kRerankMaxCand]
+    key = row + kRerankMaxCand * 4;          // float  [kRerankMaxCand]
+    sel = key + kRerankMaxCand * 4;          // u32    [kRerankRows]
+    score = sel + kRerankRows * 4;           // float  [kRerankRows]
+    n2 = score + kRerankRows * 4;            // float  [kRerankRows]     ||row||^2 of the selected rows
+    id = n2 + kRerankRows * 4;               // u64    [kRerankRows]
+    rows = (id + kRerankRows * 8 + 127u) & ~127u;   // bytes [kRerankRows][row_stride + 16]
+    total = rows + kRerankRows * (row_stride + 16);
+  }
+};
 
 template <int ELEM, int METRIC>
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint32_t n_s, ovf_s;
+  __shared__ uint32_t n_s, ovf_s, last_s;
   __shared__ float kth_s, bound_s;
-  __shared__ __align__(8) uint64_t bar_s;
-  float* q_s = reinterpret_cast<float*>(smem);                       // [q_stride]
-  uint32_t* row_s = reinterpret_cast<uint32_t*>(q_s + p.q_stride);   // [kRerankMaxCand]
-  float* key_s = reinterpret_cast<float*>(row_s + kRerankMaxCand);   // [kRerankMaxCand]
-  uint32_t* sel_row = reinterpret_cast<uint32_t*>(key_s + kRerankMaxCand);  // [kRerankRows]
-  float* score_s = reinterpret_cast<float*>(sel_row + kRerankRows);  // [kRerankRows]
-  uint64_t* id_s = reinterpret_cast<uint64_t*>(score_s + kRerankRows);      // [kRerankRows]
-  uint8_t* rows_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(id_s + kRerankRows) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t bar_s[2];   // [0] query copy, [1] row copies
+  const RerankSmem L(p.q_stride, p.row_stride);
+  float* q_s = reinterpret_cast<float*>(smem + L.q);
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(smem + L.row);
+  float* key_s = reinterpret_cast<float*>(smem + L.key);
+  uint32_t* sel_row = reinterpret_cast<uint32_t*>(smem + L.sel);
+  float* score_s = reinterpret_cast<float*>(smem + L.score);
+  float* n2_s = reinterpret_cast<float*>(smem + L.n2);
+  uint64_t* id_s = reinterpret_cast<uint64_t*>(smem + L.id);
+  uint8_t* rows_s = smem + L.rows;
   const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
   const uint32_t RS = p.row_stride + 16;   // padded shared-memory row stride (bank-conflict free, as in flat_scan.cu)
 
-  if (tid == 0) { n_s = 0; ovf_s = 0; kth_s = 0.0f; mbar_init(smem_u32(&bar_s), 1); fence_mbar_init(); }
-  for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
+  if (tid == 0) {
+    n_s = 0; ovf_s = 0; kth_s = 0.0f;
+    mbar_init(smem_u32(&bar_s[0]), 1);
+    mbar_init(smem_u32(&bar_s[1]), 1);
+    fence_mbar_init();
+    // the query streams into shared memory while the survivors are gathered and ranked
+    mbar_arrive_expect_tx(smem_u32(&bar_s[0]), p.q_stride * 4);
+    bulk_g2s(smem_u32(q_s), p.queries + (size_t)q * p.q_stride, p.q_stride * 4, smem_u32(&bar_s[0]));
+  }
+  // padding keys: never better than anything, never tie-break ahead of anything
+  for (uint32_t e = tid; e < kRerankMaxCand; e += blockDim.x) { key_s[e] = __int_as_float(0xff800000); row_s[e] = 0xffffffffu; }
   __syncthreads();
 
-  // ---- 1. gather the survivors of every filter column that clear the final threshold
+  // ---- 1. gather the survivors of every filter column that clear the final threshold.  One column per
+  //         thread, two columns in flight: count, then its few entries four at a time
   const uint32_t thr_bits = p.g_thr[q];
   const bool have_bound = thr_bits != 0;
   const float B = have_bound ? ord2f(thr_bits) : 0.0f;
-  for (uint32_t cta = tid; cta < p.grid_x; cta += blockDim.x) {   // one column per thread: count, then its few entries
-    const uint32_t ccnt = p.cand_cnt[(size_t)q * p.grid_x + cta];
-    if (ccnt == 0xffffffffu) { ovf_s = 1; continue; }              // that column overflowed on ties: exact path
-    const GemmCand* src = p.cand_in + ((size_t)q * p.grid_x + cta) * p.cand_cap;
-    for (uint32_t s = 0; s < ccnt && s < p.cand_cap; s++) {
-      const GemmCand c = src[s];
-      if (!have_bound || c.key >= B || c.key != c.key) {
-        const uint32_t pos = atomicAdd(&n_s, 1u);
-        if (pos < kRerankMaxCand) { row_s[pos] = c.row; key_s[pos] = c.key; }
+  for (uint32_t c0 = tid; c0 < p.grid_x; c0 += 2 * blockDim.x) {
+    uint32_t ccnt[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t cta = c0 + u * blockDim.x;
+      ccnt[u] = cta < p.grid_x ? p.cand_cnt[(size_t)q * p.grid_x + cta] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t cta = c0 + u * blockDim.x;
+      if (ccnt[u] == 0xffffffffu) { ovf_s = 1; continue; }           // that column overflowed on ties: exact path
+      const uint32_t cn = ccnt[u] < p.cand_cap ? ccnt[u] : p.cand_cap;
+      const GemmCand* src = p.cand_in + ((size_t)q * p.grid_x + cta) * p.cand_cap;
+      for (uint32_t s0 = 0; s0 < cn; s0 += 4) {
+        GemmCand e4[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) if (s0 + v < cn) e4[v] = src[s0 + v];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          if (s0 + v < cn && (!have_bound || e4[v].key >= B || e4[v].key != e4[v].key)) {
+            const uint32_t pos = atomicAdd(&n_s, 1u);
+            if (pos < kRerankMaxCand) { row_s[pos] = e4[v].row; key_s[pos] = e4[v].key; }
+          }
+        }
       }
     }
   }
@@ -66,26 +110,39 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   const uint32_t M = n < kRerankRows ? n : kRerankRows;
   if (tid == 0) bound_s = have_bound ? B : __int_as_float(0xff800000);
   __syncthreads();
+  const uint32_t n4 = (n + 3) & ~3u;         // the padding entries rank behind everything
   for (uint32_t e = tid; e < n; e += blockDim.x) {
     const float ke = key_s[e];
     const uint32_t re = row_s[e];
     uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; j++) {
-      const float kj = key_s[j];
-      rank += (kj > ke || (kj == ke && row_s[j] < re)) ? 1u : 0u;
+    for (uint32_t j = 0; j < n4; j += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(key_s + j);
+      rank += (k4.x > ke ? 1u : 0u) + (k4.y > ke ? 1u : 0u) + (k4.z > ke ? 1u : 0u) + (k4.w > ke ? 1u : 0u);
+      if (k4.x == ke || k4.y == ke || k4.z == ke || k4.w == ke) {   // ties are rare: the row order decides
+        const uint4 r4 = *reinterpret_cast<const uint4*>(row_s + j);
+        rank += (k4.x == ke && r4.x < re ? 1u : 0u) + (k4.y == ke && r4.y < re ? 1u : 0u) + (k4.z == ke && r4.z < re ? 1u : 0u) +
+                (k4.w == ke && r4.w < re ? 1u : 0u);
+      }
     }
     if (rank < M) sel_row[rank] = re;
     if (rank == M && n > M) bound_s = fmaxf(bound_s, ke);   // single writer: ranks are unique
   }
   __syncthreads();
 
-  // ---- 3. fetch the M rows with one bulk async copy each (all in flight at once), then re-score them
-  //         from shared memory with the exact AVX-order arithmetic of flat_scan.cu
-  if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bar_s), M * p.row_stride);
+  // ---- 3. fetch the M rows with one bulk async copy each (all in flight at once; their norms and ids are
+  //         fetched by the same threads meanwhile), then re-score them from shared memory with the exact
+  //         AVX-order arithmetic of flat_scan.cu
+  if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bar_s[1]), M * p.row_stride);
   __syncthreads();
-  for (uint32_t j = tid; j < M; j += blockDim.x)
-    bulk_g2s(smem_u32(rows_s + (size_t)j * RS), p.rows + (size_t)sel_row[j] * p.row_stride, p.row_stride, smem_u32(&bar_s));
-  if (M) mbar_wait(smem_u32(&bar_s), 0);
+  for (uint32_t j = tid; j < M; j += blockDim.x) {
+    const uint32_t row = sel_row[j];
+    bulk_g2s(smem_u32(rows_s + (size_t)j * RS), p.rows + (size_t)row * p.row_stride, p.row_stride, smem_u32(&bar_s[1]));
+    n2_s[j] = METRIC == COLTT_COSINE ? p.row_norm2[row] : 0.0f;
+    id_s[j] = p.ids[row];
+  }
+  mbar_wait(smem_u32(&bar_s[0]), 0);
+  if (M) mbar_wait(smem_u32(&bar_s[1]), 0);
+  __syncthreads();      // n2_s / id_s of every selected row are in place
   const uint32_t r = lane_row16(lane), g = lane_half(lane);
   const uint32_t full8 = (p.dim / 8) * 8;
   const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
@@ -100,8 +157,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
       load4<ELEM>(rowp + (size_t)(e + 4 * g) * ES, nullptr, rv);
       const float4 qv = *reinterpret_cast<const float4*>(q_s + e + 4 * g);
       if (METRIC == COLTT_COSINE) {
-        acc[0] = add_rn(acc[0], mul_rn(qv.x, rv[0])); acc[1] = add_rn(acc[1], mul_rn(qv.y, rv[1]));
-        acc[2] = add_rn(acc[2], mul_rn(qv.z, rv[2])); acc[3] = add_rn(acc[3], mul_rn(qv.w, rv[3]));
+        acc[0] = dot_step<ELEM>(acc[0], qv.x, rv[0]); acc[1] = dot_step<ELEM>(acc[1], qv.y, rv[1]);
+        acc[2] = dot_step<ELEM>(acc[2], qv.z, rv[2]); acc[3] = dot_step<ELEM>(acc[3], qv.w, rv[3]);
       } else {
         float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
         acc[0] = add_rn(acc[0], mul_rn(d0, d0)); acc[1] = add_rn(acc[1], mul_rn(d1, d1));
@@ -114,14 +171,10 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
     for (uint32_t d = full8; d < p.dim; d++) {
       float rv = load1<ELEM>(rowp, d, nullptr);
       float qv = q_s[d];
-      if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
+      if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
       else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
     }
-    if (valid && g == 0) {
-      const uint32_t row = sel_row[j];
-      score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[row]) : sqrt_via_f64(tot);
-      id_s[j] = p.ids[row];
-    }
+    if (valid && g == 0) score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, n2_s[j]) : sqrt_via_f64(tot);
   }
   __syncthreads();
 
@@ -167,18 +220,36 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
       if (n_out < p.k) ok = false;  // the filter keeps K' >= K rows once it has a bound: fewer means trouble
     }
     p.flags[q] = ok ? 0u : 1u;
+    // ---- 6. last CTA out builds the list of uncertified queries (replaces a separate compaction launch,
+    //         a memset of its counter and a device->host copy of the statistic)
+    __threadfence();
+    last_s = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    n_s = 0;
+  }
+  __syncthreads();
+  if (last_s) {
+    __threadfence();
+    for (uint32_t j = tid; j < p.nq; j += blockDim.x)
+      if (__ldcg(p.flags + j)) p.q_map[atomicAdd(&n_s, 1u)] = j;
+    __syncthreads();
+    if (tid == 0) {
+      *p.n_bad = n_s;
+      if (p.stat_fallbacks && n_s) atomicAdd(p.stat_fallbacks, (unsigned long long)n_s);
+      *p.done_ctr = 0;      // ready for the next launch on this scratch (stream-ordered)
+    }
   }
 }
 
 int launch_rerank(const RerankParams& p, cudaStream_t stream) {
   if (p.nq == 0) return COLTT_OK;
-  const size_t smem = (size_t)p.q_stride * 4 + (size_t)kRerankMaxCand * 8 + (size_t)kRerankRows * 16 + 128 + (size_t)kRerankRows * (p.row_stride + 16);
+  const size_t smem = RerankSmem(p.q_stride, p.row_stride).total;
   if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "rerank: rows too wide for shared memory");
   const bool cosine = p.metric == COLTT_COSINE;
 #define COLTT_RR(E, M)                                                                                    \
   {                                                                                                       \
-    COLTT_CUDA(cudaFuncSetAttribute(rerank_kernel<E, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    rerank_kernel<E, M><<<p.nq, kRerankThreads, smem, stream>>>(p);                                        \
+    auto kfn = rerank_kernel<E, M>;                                                                       \
+    { int arc = kernel_attrs(kfn, smem); if (arc) return arc; }                                           \
+    kfn<<<p.nq, kRerankThreads, smem, stream>>>(p);                                                        \
   }
   if (p.elem == ELEM_F16) { if (cosine) COLTT_RR(ELEM_F16, COLTT_COSINE) else COLTT_RR(ELEM_F16, COLTT_EUCLIDEAN) }
   else if (p.elem == ELEM_F32) { if (cosine) COLTT_RR(ELEM_F32, COLTT_COSINE) else COLTT_RR(ELEM_F32, COLTT_EUCLIDEAN) }

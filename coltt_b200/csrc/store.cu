@@ -111,16 +111,32 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int kernel_attrs(const void* fn, size_t dyn_smem_bytes) {
+  struct Key { const void* fn; int dev; bool operator==(const Key& o) const { return fn == o.fn && dev == o.dev; } };
+  struct KeyHash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.fn) ^ ((size_t)k.dev * 0x9e3779b97f4a7c15ull); } };
+  static std::mutex mu;
+  static std::unordered_map<Key, size_t, KeyHash> seen;   // largest dynamic size configured so far
+  int dev = 0;
+  COLTT_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  auto it = seen.find(Key{fn, dev});
+  if (it == seen.end()) {
+    static const bool carve = [] { const char* e = getenv("COLTT_CARVEOUT"); return !e || atoi(e) != 0; }();
+    if (carve) COLTT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    it = seen.emplace(Key{fn, dev}, (size_t)48 * 1024).first;   // the limit every kernel has without opting in
+  }
+  if (dyn_smem_bytes > it->second) {
+    COLTT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem_bytes));
+    it->second = dyn_smem_bytes;
+  }
+  return COLTT_OK;
+}
+
 SearchCtx::~SearchCtx() {
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
   if (done) cudaEventDestroy(done);
   if (stream) cudaStreamDestroy(stream);
-}
-
-__global__ void compact_flags_kernel(const uint32_t* flags, uint32_t nq, uint32_t* q_map, uint32_t* n_bad) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < nq && flags[q]) q_map[atomicAdd(n_bad, 1u)] = q;
 }
 
 __global__ void scatter_ids_kernel(const uint64_t* src, const uint32_t* slots, uint64_t* dst, size_t n) {
@@ -135,6 +151,7 @@ Store::~Store() {
   if (d_rows) cudaFree(d_rows);
   if (d_norm2) cudaFree(d_norm2);
   if (d_ids) cudaFree(d_ids);
+  if (d_stat) cudaFree(d_stat);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -164,6 +181,8 @@ int Store::create(const coltt_store_cfg* cfg, Store** out) {
   COLTT_CUDA(cudaGetDeviceProperties(&pr, cfg->device));
   s->n_sms = pr.multiProcessorCount;
   COLTT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  COLTT_CUDA(cudaMalloc(&s->d_stat, 8));
+  COLTT_CUDA(cudaMemset(s->d_stat, 0, 8));
   if (cfg->capacity_hint) {
     rc = s->reserve(cfg->capacity_hint);
     if (rc) return rc;
@@ -299,7 +318,6 @@ std::unique_ptr<SearchCtx> Store::acquire_ctx(cudaStream_t user_stream) {
       SearchCtx& c = *pool[i];
       const bool same = user_stream && c.used && c.last_stream == user_stream;
       const bool finished = !c.used || cudaEventQuery(c.done) == cudaSuccess;
-      if (finished && c.fb_pending) { fast_fallbacks += *(const uint32_t*)c.h_flags.p; c.fb_pending = false; }
       if (same || finished) {
         auto out = std::move(pool[i]);
         pool.erase(pool.begin() + i);
@@ -423,7 +441,11 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_out_cap * sizeof(GemmCand)); if (rc) return rc;
   rc = c.cand_cnt.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
-  rc = c.h_flags.ensure(nq * 4); if (rc) return rc;
+  if (!c.fb_cnt.p) {   // [0] flagged-query count, [1] rerank's arrival counter (zero between launches)
+    rc = c.fb_cnt.ensure(16); if (rc) return rc;
+    COLTT_CUDA(cudaMemsetAsync(c.fb_cnt.p, 0, 16, st));
+  }
+  rc = c.fb_q.ensure(nq * 4); if (rc) return rc;
   rc = c.pub.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.cand_buf.ensure((size_t)gp.grid_x * gp.grid_y * 2 * gp.cand_cap * 128 * sizeof(GemmCand)); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[0], st);
@@ -433,10 +455,12 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
   pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
   pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride;
+  // scratch initialisation rides in the prep launch: bound = 0, counts = 0, published maxima = -NaN ("nothing yet":
+  // never greater than anything)
+  pp.fill_ptr[0] = (uint32_t*)c.g_thr.p;    pp.fill_words[0] = nq;                    pp.fill_value[0] = 0u;
+  pp.fill_ptr[1] = (uint32_t*)c.cand_cnt.p; pp.fill_words[1] = nq * (size_t)n_cols;  pp.fill_value[1] = 0u;
+  pp.fill_ptr[2] = (uint32_t*)c.pub.p;      pp.fill_words[2] = nq * (size_t)n_cols;  pp.fill_value[2] = 0xffffffffu;
   rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
-  COLTT_CUDA(cudaMemsetAsync(c.g_thr.p, 0, nq * 4, st));
-  COLTT_CUDA(cudaMemsetAsync(c.cand_cnt.p, 0, nq * (size_t)n_cols * 4, st));
-  COLTT_CUDA(cudaMemsetAsync(c.pub.p, 0xff, nq * (size_t)n_cols * 4, st));  // 0xffffffff = -NaN: never > anything, i.e. "nothing yet"
   if (timed) cudaEventRecord(c.ev[1], st);
   GemmParams g{};
   g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
@@ -456,7 +480,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
       g.dbg_prof2 = g.dbg_prof + (size_t)gp.grid_x * gp.grid_y * 8;
     }
   }
-  rc = launch_gemm_filter(g, gp, d_rows, row_stride, st); if (rc) return rc;
+  rc = launch_gemm_filter(g, gp, d_rows, row_stride, st, &c.maps); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
   r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
@@ -465,6 +489,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.rows = d_rows; r.row_norm2 = d_norm2; r.ids = d_ids;
   r.cand_in = (const GemmCand*)c.cand.p; r.cand_cnt = (const uint32_t*)c.cand_cnt.p; r.g_thr = (const uint32_t*)c.g_thr.p;
   r.out = d_out; r.out_stride = (uint32_t)k; r.out_counts = d_counts; r.flags = (uint32_t*)c.flags.p;
+  r.n_bad = (uint32_t*)c.fb_cnt.p; r.done_ctr = (uint32_t*)c.fb_cnt.p + 1; r.q_map = (uint32_t*)c.fb_q.p; r.stat_fallbacks = d_stat;
   rc = launch_rerank(r, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[3], st);
   if (g.dbg_prof) {
@@ -488,16 +513,11 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   }
   *used_fast = true;
   fast_queries += nq;
-  // Certificate check, on the device: the queries rerank.cu could not certify are compacted into a list
-  // and re-run by the exact kernel, which takes its query count from device memory — no host round trip;
-  // with nothing flagged the three launches below are one empty wave each.
-  rc = c.fb_cnt.ensure(16); if (rc) return rc;
-  rc = c.fb_q.ensure(nq * 4); if (rc) return rc;
-  COLTT_CUDA(cudaMemsetAsync(c.fb_cnt.p, 0, 4, st));
-  compact_flags_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>((const uint32_t*)c.flags.p, (uint32_t)nq, (uint32_t*)c.fb_q.p, (uint32_t*)c.fb_cnt.p);
-  count_launch();
-  COLTT_CUDA(cudaGetLastError());
-  {
+  // Certificate check, on the device: the queries rerank.cu could not certify were compacted into a list by
+  // its last CTA and are re-run by the exact kernel, which takes its query count from device memory — no host
+  // round trip; with nothing flagged the two launches below are one empty wave each.
+  static const bool no_tail = getenv("COLTT_DEBUG_NOTAIL") != nullptr;   // timing probe only: results unverified
+  if (!no_tail) {
     const uint32_t k_eff = (uint32_t)k;   // fast path requires k <= n_rows
     ScanPlan plan;
     rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_rows, (uint32_t)nq, k_eff, n_sms, &plan); if (rc) return rc;
@@ -521,9 +541,6 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
     mp.q_map = (const uint32_t*)c.fb_q.p; mp.n_active = (const uint32_t*)c.fb_cnt.p;
     rc = launch_merge_topk(mp, st); if (rc) return rc;
   }
-  // statistics only: how many queries took the exact re-run (read back lazily, never waited for here)
-  COLTT_CUDA(cudaMemcpyAsync(c.h_flags.p, c.fb_cnt.p, 4, cudaMemcpyDeviceToHost, st));
-  c.fb_pending = true;
   return COLTT_OK;
 }
 
@@ -539,6 +556,7 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
   struct Rel { Store* s; std::unique_ptr<SearchCtx>* c; ~Rel() { s->release_ctx(std::move(*c)); } } rel{this, &ctx};
   SearchCtx& c = *ctx;
   cudaStream_t st = c.stream;
+  const bool timed = timing.load(std::memory_order_relaxed);
   int rc;
   // candidate ids -> slots (the Go map lookup `if node, ok := vertices[shard][uid]; ok`,
   // none_vectorstore.go:203); unknown and repeated ids are dropped
@@ -565,19 +583,18 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
   std::memcpy(c.h_q.p, queries, nq * (size_t)dim * 4);
   COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, c.h_q.p, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
   rc = search_enqueue(c, st, (const float*)c.q_in.p, nq, k, select_mode, math_mode, use_subset ? (const uint32_t*)c.subset.p : nullptr,
-                      n_sub, (Hit*)c.out.p, (int*)c.counts.p, true);
+                      n_sub, (Hit*)c.out.p, (int*)c.counts.p, timed);
   if (rc) return rc;
   Hit* h_hits = (Hit*)c.h_out.p;
   int* h_counts = (int*)((uint8_t*)c.h_out.p + nq * (size_t)k * sizeof(Hit));
   COLTT_CUDA(cudaMemcpyAsync(h_counts, c.counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
   COLTT_CUDA(cudaMemcpyAsync(h_hits, c.out.p, nq * (size_t)k * sizeof(Hit), cudaMemcpyDeviceToHost, st));
   COLTT_CUDA(cudaStreamSynchronize(st));
-  if (c.fb_pending) { fast_fallbacks += *(const uint32_t*)c.h_flags.p; c.fb_pending = false; }
   c.used = true;
   c.last_stream = st;
   cudaEventRecord(c.done, st);
   const bool had_rows = (use_subset ? n_sub : n_rows) != 0;
-  if (had_rows) {
+  if (had_rows && timed) {
     c.have_times = true;
     cudaEventElapsedTime(&c.ms[0], c.ev[0], c.ev[1]);
     cudaEventElapsedTime(&c.ms[1], c.ev[1], c.ev[2]);
@@ -605,8 +622,9 @@ int Store::search_dev(const void* d_queries, size_t nq, int k, int select_mode, 
   if (!ctx) return fail(COLTT_ERR_CUDA, "could not create a search context");
   struct Rel { Store* s; std::unique_ptr<SearchCtx>* c; ~Rel() { s->release_ctx(std::move(*c)); } } rel{this, &ctx};
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  const bool timed = timing.load(std::memory_order_relaxed);
   // timings of the previous use of this scratch become readable once that work has finished
-  if (ctx->used && n_rows && cudaEventQuery(ctx->ev[3]) == cudaSuccess) {
+  if (timed && ctx->timed_last && ctx->used && n_rows && cudaEventQuery(ctx->ev[3]) == cudaSuccess) {
     cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
     ctx->ms[2] = 0.0f;
@@ -614,14 +632,15 @@ int Store::search_dev(const void* d_queries, size_t nq, int k, int select_mode, 
     ctx->have_times = true;
   }
   cudaGetLastError();
-  int rc = search_enqueue(*ctx, st, (const float*)d_queries, nq, k, select_mode, math_mode, nullptr, 0, (Hit*)d_out, (int*)d_counts, true);
+  int rc = search_enqueue(*ctx, st, (const float*)d_queries, nq, k, select_mode, math_mode, nullptr, 0, (Hit*)d_out, (int*)d_counts, timed);
+  ctx->timed_last = timed;
   ctx->used = true;
   ctx->last_stream = st;
   cudaEventRecord(ctx->done, st);
   if (rc) return rc;
   if (!stream_) {  // own stream: synchronous call
     COLTT_CUDA(cudaStreamSynchronize(st));
-    if (n_rows) {
+    if (n_rows && timed) {
       cudaEventElapsedTime(&ctx->ms[0], ctx->ev[0], ctx->ev[1]);
       cudaEventElapsedTime(&ctx->ms[1], ctx->ev[1], ctx->ev[2]);
       ctx->ms[2] = 0.0f;
@@ -750,7 +769,7 @@ COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n) {
     // an asynchronous search_dev leaves its events in the pooled scratch: harvest finished ones
     std::lock_guard<std::mutex> g(st->pool_mu);
     for (auto& c : st->pool) {
-      if (c->used && cudaEventQuery(c->ev[3]) == cudaSuccess && cudaEventQuery(c->ev[0]) == cudaSuccess) {
+      if (c->used && c->timed_last && cudaEventQuery(c->ev[3]) == cudaSuccess && cudaEventQuery(c->ev[0]) == cudaSuccess) {
         float a, b, d;
         if (cudaEventElapsedTime(&a, c->ev[0], c->ev[1]) == cudaSuccess && cudaEventElapsedTime(&b, c->ev[1], c->ev[2]) == cudaSuccess &&
             cudaEventElapsedTime(&d, c->ev[2], c->ev[3]) == cudaSuccess) {
@@ -761,6 +780,11 @@ COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n) {
     cudaGetLastError();
   }
   for (int i = 0; i < n && i < 4; i++) ms[i] = st->last_ms[i];
+  return COLTT_OK;
+}
+COLTT_API int coltt_b200_store_set_timing(coltt_store* s, int on) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  reinterpret_cast<Store*>(s)->timing.store(on != 0, std::memory_order_relaxed);
   return COLTT_OK;
 }
 COLTT_API uint64_t coltt_b200_kernel_launches(void) { return coltt::launch_count(); }
@@ -800,12 +824,10 @@ COLTT_API int coltt_b200_debug_fast_scores(coltt_store* s_, const float* queries
 COLTT_API int coltt_b200_store_fast_stats(coltt_store* s, uint64_t* out2) {
   if (!s || !out2) return fail(COLTT_ERR_INVALID, "null argument");
   Store* st = reinterpret_cast<Store*>(s);
-  {
-    std::lock_guard<std::mutex> g(st->pool_mu);
-    for (auto& c : st->pool)
-      if (c->fb_pending && (!c->used || cudaEventQuery(c->done) == cudaSuccess)) { st->fast_fallbacks += *(const uint32_t*)c->h_flags.p; c->fb_pending = false; }
-    cudaGetLastError();
-  }
+  unsigned long long fb = 0;
+  COLTT_CUDA(cudaSetDevice(st->device));
+  COLTT_CUDA(cudaMemcpy(&fb, st->d_stat, 8, cudaMemcpyDeviceToHost));   // counted on the device by rerank.cu
+  st->fast_fallbacks = fb;
   out2[0] = st->fast_queries;
   out2[1] = st->fast_fallbacks;
   return COLTT_OK;

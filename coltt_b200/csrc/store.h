@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -9,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace coltt {
 
@@ -16,6 +19,14 @@ const char* last_error_cstr();
 int sm100_device_count();
 int require_device(int device);
 void count_launch(int n = 1);
+// Kernel attributes, set once per (kernel, device) instead of on every launch (cudaFuncSetAttribute takes the
+// context lock: a dozen calls per search were a measurable part of the host time of a 0.4 ms step):
+//  * the dynamic shared-memory limit, raised only when a launch needs more than any before it;
+//  * the maximum shared-memory carve-out for every kernel of the pipeline, so that consecutive launches with
+//    different dynamic sizes do not make the SMs switch L1/shared configuration between kernels.
+int kernel_attrs(const void* fn, size_t dyn_smem_bytes);
+template <class F>
+inline int kernel_attrs(F* fn, size_t dyn_smem_bytes) { return kernel_attrs(reinterpret_cast<const void*>(fn), dyn_smem_bytes); }
 uint64_t launch_count();
 
 struct DeviceBuf {
@@ -38,11 +49,11 @@ struct SearchCtx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t done = nullptr;       // recorded after the last enqueue that used this scratch
   cudaStream_t last_stream = nullptr;
-  bool used = false, have_times = false, fb_pending = false;
+  bool used = false, have_times = false, timed_last = false;
   float ms[4] = {0, 0, 0, 0};
   DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf;
-  PinnedBuf h_flags;
   PinnedBuf h_q, h_out;
+  GemmMapCache maps;                // TMA descriptors of the last FAST launch on this scratch
   ~SearchCtx();
 };
 
@@ -54,6 +65,8 @@ struct Store {
   uint8_t* d_rows = nullptr;
   float* d_norm2 = nullptr;
   uint64_t* d_ids = nullptr;
+  unsigned long long* d_stat = nullptr;            // queries the FAST path re-ran exactly (counted on the device)
+  std::atomic<bool> timing{false};                 // record per-phase CUDA events around searches (diagnostics)
   std::vector<uint64_t> h_ids;                     // slot -> id
   std::unordered_map<uint64_t, uint32_t> id2slot;  // id -> slot
   std::shared_mutex mu;                            // searches shared, mutations exclusive

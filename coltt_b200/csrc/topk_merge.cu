@@ -143,11 +143,11 @@ int launch_merge_topk(const MergeParams& p, cudaStream_t stream) {
   const size_t base = ((size_t)p.k + piv_cap + surv_cap) * sizeof(Hit);
   const size_t staged = base + (size_t)p.n_lists * p.k_in * sizeof(Hit) + (size_t)p.n_lists * sizeof(int);
   if (staged <= 200 * 1024) {
-    COLTT_CUDA(cudaFuncSetAttribute(merge_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+    { int arc = kernel_attrs(merge_topk_kernel<true>, staged); if (arc) return arc; }
     merge_topk_kernel<true><<<p.nq, kMergeThreads, staged, stream>>>(p, piv_per_list, piv_cap, surv_cap);
   } else {
     if (base > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "merge: too many lists for shared memory");
-    COLTT_CUDA(cudaFuncSetAttribute(merge_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    { int arc = kernel_attrs(merge_topk_kernel<false>, base); if (arc) return arc; }
     merge_topk_kernel<false><<<p.nq, kMergeThreads, base, stream>>>(p, piv_per_list, piv_cap, surv_cap);
   }
   count_launch();

@@ -82,7 +82,11 @@ class VectorSpace:
             _lib.lib().coltt_b200_store_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the binding module may already be torn down
+            pass
 
     # -- vectorspace getters (edge/vectorstore.go:43-48)
     def Quantization(self) -> int:
@@ -185,7 +189,12 @@ class VectorSpace:
         _lib.check(_lib.lib().coltt_b200_store_get_row(self._h, Id, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def set_timing(self, on: bool = True) -> None:
+        """Record per-phase CUDA events around searches (off by default: they sit between sub-ms kernels)."""
+        _lib.check(_lib.lib().coltt_b200_store_set_timing(self._h, 1 if on else 0))
+
     def last_timing_ms(self):
+        """Phase times of the last search made while set_timing(True) was in effect."""
         ms = (C.c_float * 4)()
         _lib.check(_lib.lib().coltt_b200_store_last_timing(self._h, ms, 4))
         return {"prep": ms[0], "scan": ms[1], "rerank": ms[2], "merge": ms[3]}

@@ -181,6 +181,9 @@ COLTT_API int coltt_b200_hnsw_last_stats(coltt_hnsw* h, uint64_t* dist_evals, ui
  * with CUDA events on the stream they ran on: [0] query prep, [1] scan/GEMM, [2] rerank,
  * [3] merge.  n = number of floats the caller provides. */
 COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n);
+/* Per-phase events are recorded only while timing is on (default off: the event records sit between
+ * kernels of a sub-millisecond search). */
+COLTT_API int coltt_b200_store_set_timing(coltt_store* s, int on);
 /* Kernels this library has launched in this process so far (bench.py's gpu_launches). */
 COLTT_API uint64_t coltt_b200_kernel_launches(void);
 

@@ -261,3 +261,28 @@ def test_hnsw_build_search_commit_roundtrip(oracle):
         fi, _ = flat.search(q, 10, select_mode=oracle.NEAREST)
         hits += len(set(hi.tolist()) & set(fi.tolist()))
     assert hits / 200 > 0.9
+
+
+def test_fp16_products_are_exact_in_fp32(oracle):
+    """Premise of the one-FFMA dot step on the fp16 stores (csrc/exact_math.cuh dot_step): the product of two
+    decoded fp16 values is exactly representable in fp32, so fma(q, r, acc) == (q*r rounded) + acc,
+    i.e. the reference's unfused `dot += v1*v2` (avx.cpp:60).  Checked exhaustively over exponent extremes and on
+    2M random pairs: the fp64 product (always exact for 11-bit x 11-bit significands) survives a round trip to fp32."""
+    all16 = np.arange(65536, dtype=np.uint16).view(np.float16)
+    finite = all16[np.isfinite(all16)].astype(np.float64)
+    r = np.random.Generator(np.random.Philox(7))
+    a = r.choice(finite, 2_000_000)
+    b = r.choice(finite, 2_000_000)
+    # extremes: smallest subnormals, largest normals, against everything
+    ext = np.array([2.0 ** -24, 3 * 2.0 ** -24, 1023 * 2.0 ** -24, 2.0 ** -14, 65504.0, 2047 * 2.0 ** -10], np.float64)
+    a = np.concatenate([a, np.repeat(ext, len(finite))])
+    b = np.concatenate([b, np.tile(finite, len(ext))])
+    prod = a * b
+    with np.errstate(over="raise", under="raise"):
+        p32 = prod.astype(np.float32)
+    assert np.array_equal(p32.astype(np.float64), prod)
+    assert np.all((prod == 0) | (np.abs(prod) >= 2.0 ** -126))       # never an fp32 subnormal
+    # ... and the f8-compat decoder does NOT have the property (stray mantissa bit, fp32 subnormals for codes >= 0x80):
+    # that store keeps the two-rounding path
+    dec = np.asarray(oracle.f8_to_f32(np.arange(256, dtype=np.uint8)), np.float32)
+    assert not np.array_equal(dec.astype(np.float16).astype(np.float32), dec)

@@ -10,6 +10,7 @@ rows = np.empty((n, d), np.float32)
 for i in range(0, n, 100_000):
     rows[i:i + 100_000] = g.standard_normal((min(100_000, n - i), d), dtype=np.float32)
 sp = cb.VectorSpace("p", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_BF16), capacity_hint=n, select_mode=cb.SELECT_NEAREST)
+sp.set_timing(True)
 sp.ChangedVertices(np.arange(n, dtype=np.uint64) + 1, rows)
 qs = g.standard_normal((nq, d), dtype=np.float32)
 ts = []

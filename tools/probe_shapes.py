@@ -13,6 +13,7 @@ for i in range(0, n, 100_000):
 ids = np.arange(n, dtype=np.uint64) + 1
 for quant, name in ((cb.Quantization_BF16, "fp16"), (cb.Quantization_None, "fp32"), (cb.Quantization_F8, "f8c")):
     sp = cb.VectorSpace("p", cb.Metadata(d, cb.Distance_Cosine, quant), capacity_hint=n, select_mode=cb.SELECT_NEAREST)
+    sp.set_timing(True)
     sp.ChangedVertices(ids, rows)
     es = {cb.Quantization_BF16: 2, cb.Quantization_None: 4, cb.Quantization_F8: 1}[quant]
     for nq in (1, 8, 64, 128, 256):
