@@ -10,19 +10,10 @@
 #include <cstring>
 
 #include "kernels.cuh"
+#include "hnsw.h"
 #include "store.h"
 
 namespace coltt {
-
-// pkg/sharding/shard.go:34-41 ShardVertex: FNV-1a over the little-endian id bytes, mod c.
-static inline uint64_t shard_vertex(uint64_t x, uint64_t c) {
-  uint64_t h = 14695981039346656037ull;
-  for (int i = 0; i < 8; i++) {
-    h ^= (x >> (8 * i)) & 0xff;
-    h *= 1099511628211ull;
-  }
-  return h % c;
-}
 
 template <int ELEM>
 __global__ void __launch_bounds__(256) norm2_stored_kernel(const uint8_t* rows, uint32_t row_stride, uint32_t dim, size_t n,

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "exact_math.cuh"
+#include "hnsw.h"
 #include "store.h"
 
 namespace coltt {
@@ -267,26 +268,6 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
 }
 
 // ------------------------------------------------------------------------------------------
-int launch_norm2_stored_f32(const uint8_t* rows, uint32_t row_stride, uint32_t dim, size_t n, float* norm2, cudaStream_t stream);
-
-struct Hnsw {
-  int device = 0, metric = 0, n_sms = 148;
-  uint32_t dim = 0, row_stride = 0, n = 0, entry = 0;
-  int32_t ef_default = 20, m = 16, m_max = 16, m_max0 = 32, search_algo = 0;
-  uint8_t* d_rows = nullptr; float* d_norm2 = nullptr; uint64_t* d_ids = nullptr; int32_t* d_level = nullptr;
-  uint32_t *d_vbase = nullptr, *d_edge_off = nullptr, *d_edge_nbr = nullptr;
-  unsigned long long* d_stats = nullptr;
-  cudaStream_t stream = nullptr;
-  std::mutex mu;
-  DeviceBuf q_in, q_deq, q_n2, visited, out, counts;
-  uint64_t last_evals = 0, last_exp = 0;
-  ~Hnsw() {
-    cudaSetDevice(device);
-    for (void* ptr : {(void*)d_rows, (void*)d_norm2, (void*)d_ids, (void*)d_level, (void*)d_vbase, (void*)d_edge_off, (void*)d_edge_nbr, (void*)d_stats})
-      if (ptr) cudaFree(ptr);
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
 
 struct BlobR {
   const uint8_t* p; size_t n, pos = 0; bool ok = true;
@@ -299,17 +280,34 @@ struct BlobR {
   void skip(size_t k) { if (pos + k > n) ok = false; else pos += k; }
 };
 
-template <class T>
-static int upload(T** dst, const std::vector<T>& v) {
-  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  COLTT_CUDA(cudaMalloc((void**)dst, bytes));
-  if (!v.empty()) COLTT_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+// CSR over (vertex, level) from per-list edge vectors: neighbours sorted by id (the deterministic iteration
+// order), duplicates dropped; edge distances ride along for Commit.
+int hnsw_install_graph(Hnsw* h, const std::vector<uint32_t>& vbase, std::vector<std::vector<HnswEdge>>& lists) {
+  const uint32_t n = h->n;
+  std::vector<uint32_t> edge_off(vbase[n] + 1, 0), edge_nbr;
+  std::vector<uint32_t> edge_dist;
+  for (uint32_t i = 0; i < vbase[n]; i++) {
+    auto& lst = lists[i];
+    std::sort(lst.begin(), lst.end(), [](const HnswEdge& a, const HnswEdge& b) { return a.id < b.id; });
+    lst.erase(std::unique(lst.begin(), lst.end(), [](const HnswEdge& a, const HnswEdge& b) { return a.id == b.id; }), lst.end());
+    edge_off[i] = (uint32_t)edge_nbr.size();
+    for (auto& e : lst) { edge_nbr.push_back(e.slot); edge_dist.push_back(e.dist_bits); }
+  }
+  edge_off[vbase[n]] = (uint32_t)edge_nbr.size();
+  int rc;
+  for (void* ptr : {(void*)h->d_vbase, (void*)h->d_edge_off, (void*)h->d_edge_nbr, (void*)h->d_edge_dist})
+    if (ptr) cudaFree(ptr);
+  h->d_vbase = h->d_edge_off = h->d_edge_nbr = h->d_edge_dist = nullptr;
+  if ((rc = upload(&h->d_vbase, vbase)) || (rc = upload(&h->d_edge_off, edge_off)) || (rc = upload(&h->d_edge_nbr, edge_nbr)) ||
+      (rc = upload(&h->d_edge_dist, edge_dist)))
+    return rc;
+  h->n_edges = edge_nbr.size();
   return COLTT_OK;
 }
 
 // Hnsw.Load(header=true): hnsw_commit.go:164-278 with hnsw_config.go:203-245 (config) and
 // metadata.go:43-105 (per-vertex metadata records are skipped by length).
-static int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
+int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   int rc = require_device(device);
   if (rc) return rc;
   COLTT_CUDA(cudaSetDevice(device));
@@ -317,9 +315,9 @@ static int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   std::unique_ptr<Hnsw> h(new Hnsw());
   h->device = device;
   h->search_algo = (int32_t)r.be(4);
-  r.be(4);  // levelMultiplier (insert-time only)
+  h->level_mult_bits = (uint32_t)r.be(4);  // levelMultiplier (insert-time only; kept for Commit)
   h->ef_default = (int32_t)r.be(4);
-  r.be(4);  // efConstruction
+  h->ef_construction = (int32_t)r.be(4);
   h->m = (int32_t)r.be(4); h->m_max = (int32_t)r.be(4); h->m_max0 = (int32_t)r.be(4);
   h->dim = (uint32_t)r.be(4);
   const uint8_t di = (uint8_t)r.be(1);
@@ -368,7 +366,7 @@ static int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   const uint32_t n = (uint32_t)ids.size();
   std::vector<uint32_t> vbase(n + 1, 0);
   for (uint32_t v = 0; v < n; v++) vbase[v + 1] = vbase[v] + (uint32_t)levels[v] + 1;
-  std::vector<std::vector<std::pair<uint64_t, uint32_t>>> lists(vbase[n]);  // (neighbour id, slot)
+  std::vector<std::vector<HnswEdge>> lists(vbase[n]);
   for (int sh = 0; sh < 16 && r.ok; sh++)
     for (size_t i = 0; i < shard_slots[sh].size() && r.ok; i++) {
       const uint64_t id = r.be(8);
@@ -380,32 +378,23 @@ static int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
         auto& lst = lists[vbase[v] + l];
         for (uint32_t j = 0; j < ne && r.ok; j++) {
           const uint64_t nid = r.be(8);
-          r.be(4);  // stored edge distance: not needed by Search
+          const uint32_t dbits = (uint32_t)r.be(4);   // stored edge distance: not needed by Search, kept for Commit
           auto nt = id2slot.find(nid);
           if (nt == id2slot.end()) { r.ok = false; break; }
-          lst.emplace_back(nid, nt->second);
+          lst.push_back(HnswEdge{nid, nt->second, dbits});
         }
       }
     }
   if (!r.ok) return fail(COLTT_ERR_FORMAT, "truncated or inconsistent HNSW commit blob (edges)");
-  std::vector<uint32_t> edge_off(vbase[n] + 1, 0), edge_nbr;
-  for (uint32_t i = 0; i < vbase[n]; i++) {
-    auto& lst = lists[i];
-    std::sort(lst.begin(), lst.end());  // ascending neighbour id: the deterministic iteration order
-    lst.erase(std::unique(lst.begin(), lst.end()), lst.end());
-    edge_off[i] = (uint32_t)edge_nbr.size();
-    for (auto& e : lst) edge_nbr.push_back(e.second);
-  }
-  edge_off[vbase[n]] = (uint32_t)edge_nbr.size();
   h->n = n;
+  for (int32_t l : levels) h->max_level = std::max(h->max_level, l);
   if (n) {
     auto it = id2slot.find(ep_id);
     if (it == id2slot.end()) return fail(COLTT_ERR_FORMAT, "entrypoint id not among the vertices");
     h->entry = it->second;
   }
-  if ((rc = upload(&h->d_rows, rows)) || (rc = upload(&h->d_ids, ids)) || (rc = upload(&h->d_level, levels)) ||
-      (rc = upload(&h->d_vbase, vbase)) || (rc = upload(&h->d_edge_off, edge_off)) || (rc = upload(&h->d_edge_nbr, edge_nbr)))
-    return rc;
+  if ((rc = upload(&h->d_rows, rows)) || (rc = upload(&h->d_ids, ids)) || (rc = upload(&h->d_level, levels))) return rc;
+  if ((rc = hnsw_install_graph(h.get(), vbase, lists))) return rc;
   COLTT_CUDA(cudaMalloc((void**)&h->d_norm2, std::max<size_t>(n, 1) * 4));
   if (n) {
     rc = launch_norm2_stored_f32(h->d_rows, h->row_stride, h->dim, n, h->d_norm2, h->stream);

@@ -235,6 +235,7 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
   if (n == 0) return COLTT_OK;
   if (!ids || !vecs) return fail(COLTT_ERR_INVALID, "null argument");
   std::unique_lock<std::shared_mutex> lk(mu);
+  if (anonymous) return fail(COLTT_ERR_UNSUPPORTED, "store was filled from device memory: search only");
   COLTT_CUDA(cudaSetDevice(device));
   std::unordered_map<uint64_t, size_t> last;
   last.reserve(n * 2);
@@ -284,10 +285,42 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
   return COLTT_OK;
 }
 
+__global__ void iota_ids_kernel(uint64_t* ids, size_t base, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[base + i] = base + i;
+}
+
+// Bulk ingest of rows that already live on the device (the HNSW builder's temporary per-level shards):
+// Normalize + Lower + ||row||^2 exactly as upsert does, ids = slot numbers.  The host id map is not maintained,
+// so the store is search-only afterwards.
+int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats) {
+  if (n == 0) return COLTT_OK;
+  if (!d_vecs || stride_floats < dim) return fail(COLTT_ERR_INVALID, "append_dev: bad argument");
+  std::unique_lock<std::shared_mutex> lk(mu);
+  if (n_rows && !anonymous) return fail(COLTT_ERR_UNSUPPORTED, "append_dev on a store with host-mapped ids");
+  COLTT_CUDA(cudaSetDevice(device));
+  int rc = reserve(n_rows + n);
+  if (rc) return rc;
+  PrepParams pp{};
+  pp.in = d_vecs; pp.n = n; pp.in_stride = stride_floats; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
+  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slot_base = (uint32_t)n_rows;
+  pp.norm2_out = d_norm2; pp.norm2_by_slot = 1;
+  rc = launch_prep_rows(pp, elem, stream);
+  if (rc) return rc;
+  iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ids, n_rows, n);
+  COLTT_CUDA(cudaGetLastError());
+  COLTT_CUDA(cudaStreamSynchronize(stream));
+  n_rows += n;
+  anonymous = true;
+  return COLTT_OK;
+}
+
 int Store::remove(const uint64_t* ids, size_t n) {
   if (n == 0) return COLTT_OK;
   if (!ids) return fail(COLTT_ERR_INVALID, "null argument");
   std::unique_lock<std::shared_mutex> lk(mu);
+  if (anonymous) return fail(COLTT_ERR_UNSUPPORTED, "store was filled from device memory: search only");
   COLTT_CUDA(cudaSetDevice(device));
   for (size_t i = 0; i < n; i++) {
     auto it = id2slot.find(ids[i]);

@@ -86,6 +86,8 @@ struct Store {
   int reserve(size_t rows);
   int upsert(const uint64_t* ids, const float* vecs, size_t n);
   int remove(const uint64_t* ids, size_t n);
+  int append_dev(const float* d_vecs, size_t n, uint32_t stride_floats);   // internal: rows already on the device, ids = slots
+  bool anonymous = false;                          // filled by append_dev: no host id map, search only
   int search_host(const float* queries, size_t nq, const uint64_t* cand_ids, size_t n_cand, bool use_subset, int k,
                   int select_mode, int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts);
   int search_dev(const void* d_queries, size_t nq, int k, int select_mode, int math_mode, void* d_out, void* d_counts,

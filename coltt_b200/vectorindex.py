@@ -4,8 +4,12 @@
     vectorindex.Hnsw.Search   core/vectorindex/hnsw.go:243-278         -> Hnsw.Search(query, k)
     vectorindex.SearchResult  core/vectorindex/hnsw_search_result.go   -> list of SearchResultItem
 
-Insert/Remove (graph construction) stay with the reference for now; an index built and
-Commit()ed by the Go side is loaded onto the GPU and searched there.
+    n x vectorindex.Hnsw.Insert  core/vectorindex/hnsw.go:104-167         -> Hnsw.Build(ids, vecs, ...) (bulk, on the GPU)
+    vectorindex.Hnsw.Commit   core/vectorindex/hnsw_commit.go:69-162   -> Hnsw.Commit()
+
+An index built and Commit()ed by the Go side is loaded onto the GPU and searched there; an initial load can
+instead be built on the GPU (csrc/hnsw_build.cu) and handed back to the Go side as a Commit blob.  Incremental
+Insert/Remove stay with the reference.
 """
 from __future__ import annotations
 
@@ -39,12 +43,52 @@ class Hnsw:
         _lib.check(_lib.lib().coltt_b200_hnsw_load(buf, len(blob), device, C.byref(h)))
         return Hnsw(h)
 
+    @staticmethod
+    def Build(ids, vecs, metric: int = 0, m: int = 16, ef: int = 20, ef_construction: int = 200, levels=None, seed: int = 0xC0177,
+              device: int = 0) -> "Hnsw":
+        """Bulk equivalent of NewHnsw(dim, space, WithM(m), ...) followed by Insert(id, vec, md, level) for every row
+        (hnsw.go:56-83,104-167).  `levels` = the vertexLevel per row the caller would pass to Insert, or None to draw
+        them as Hnsw.RandomLevel does (hnsw.go:280-282) from `seed`."""
+        v = np.ascontiguousarray(vecs, dtype=np.float32)
+        i = np.ascontiguousarray(ids, dtype=np.uint64)
+        if v.ndim != 2 or v.shape[0] != i.shape[0]:
+            raise ValueError("ids / vecs shape mismatch")
+        cfg = _lib.HnswBuildCfg(v.shape[1], int(metric), int(m), int(ef), int(ef_construction), int(device), int(seed))
+        lv = None
+        if levels is not None:
+            lv = np.ascontiguousarray(levels, dtype=np.int32)
+            if lv.shape[0] != i.shape[0]:
+                raise ValueError("levels shape mismatch")
+        h = C.c_void_p()
+        _lib.check(_lib.lib().coltt_b200_hnsw_build(C.byref(cfg), i.ctypes.data_as(_u64p), v.ctypes.data_as(_f32p),
+                                                     lv.ctypes.data_as(_i32p) if lv is not None else None, v.shape[0], C.byref(h)))
+        return Hnsw(h)
+
+    def Commit(self) -> bytes:
+        """Hnsw.Commit(w, header=true): the reference's index blob (loadable by the Go side and by Hnsw.Load)."""
+        n = C.c_size_t(0)
+        _lib.check(_lib.lib().coltt_b200_hnsw_commit(self._h, None, C.byref(n)))
+        buf = (C.c_uint8 * max(n.value, 1))()
+        _lib.check(_lib.lib().coltt_b200_hnsw_commit(self._h, buf, C.byref(n)))
+        return bytes(memoryview(buf)[: n.value])
+
+    def build_stats(self):
+        ms = (C.c_double * 4)()
+        ne, ml = C.c_uint64(0), C.c_int32(0)
+        _lib.check(_lib.lib().coltt_b200_hnsw_build_stats(self._h, ms, C.byref(ne), C.byref(ml)))
+        return {"ingest_ms": ms[0], "knn_ms": ms[1], "edge_dist_ms": ms[2], "host_graph_ms": ms[3], "n_edges": int(ne.value),
+                "max_level": int(ml.value)}
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().coltt_b200_hnsw_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def Len(self) -> int:
         n = C.c_uint64(0)

@@ -176,6 +176,28 @@ COLTT_API int coltt_b200_hnsw_search(coltt_hnsw* h, const float* queries, size_t
 /* Counters of the last search call: distance evaluations and expansions (for the roofline). */
 COLTT_API int coltt_b200_hnsw_last_stats(coltt_hnsw* h, uint64_t* dist_evals, uint64_t* expansions);
 
+/* Bulk construction (replaces n x Hnsw.Insert, core/vectorindex/hnsw.go:104-167, for an initial load): per level,
+ * the m nearest neighbours of every member by brute force on the tensor cores, exact fp32 edge distances, back
+ * edges and pruneNeighbors (hnsw.go:449-474) — see csrc/hnsw_build.cu.  `levels` may be NULL (drawn as
+ * RandomLevel does, hnsw.go:280-282, from `seed`) or hold the vertexLevel the Go side would pass to Insert.
+ * Defaults as hnsw_config.go:135-162 when a field is <= 0: m 16 (mMax = m, mMax0 = 2m), ef 20, efConstruction 200.
+ * The graph is a valid Hnsw (searchable here and, through coltt_b200_hnsw_commit, loadable by the Go side) but not
+ * the one sequential insertion would produce. */
+typedef struct coltt_hnsw_build_cfg {
+  uint32_t dim;
+  int32_t metric;          /* coltt_metric */
+  int32_t m, ef, ef_construction;
+  int32_t device;
+  uint64_t seed;
+} coltt_hnsw_build_cfg;
+COLTT_API int coltt_b200_hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids, const float* vecs /* n x dim, un-normalized */,
+                                    const int32_t* levels /* nullable */, size_t n, coltt_hnsw** out);
+/* Hnsw.Commit(w, header=true) (hnsw_commit.go:69-162): the reference's big-endian index blob; vertex metadata
+ * count is written as 0 (metadata lives on the Go side).  Pass buf = NULL to query the size in *len. */
+COLTT_API int coltt_b200_hnsw_commit(coltt_hnsw* h, void* buf, size_t* len);
+/* Bulk-build wall times in ms: [0] ingest, [1] kNN search, [2] edge distances, [3] host graph assembly. */
+COLTT_API int coltt_b200_hnsw_build_stats(coltt_hnsw* h, double* ms4, uint64_t* n_edges, int32_t* max_level);
+
 /* ---- timing (replaces pprof for this path) ---------------------------------
  * Device time in milliseconds of the kernels of the last search on this handle, measured
  * with CUDA events on the stream they ran on: [0] query prep, [1] scan/GEMM, [2] rerank,
