@@ -364,6 +364,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 16 + nq * 4,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "kernel_ms": parts, "roofline": roof, "clocks": clocks}
+    if math_mode == cb.MATH_FAST:
+        fs = (C.c_uint64 * 2)()
+        _lib.check(L.coltt_b200_store_fast_stats(sp._h, fs))
+        # queries answered by the tensor-core filter, and how many of them the certificate sent to the exact re-run
+        line["fast_path"] = {"queries": int(fs[0]), "exact_reruns": int(fs[1]), "rerun_rate": (fs[1] / fs[0]) if fs[0] else None}
 
     if not args.no_cpu and world == 1:
         from oracle import oracle as orc

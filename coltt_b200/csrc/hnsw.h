@@ -24,6 +24,7 @@ struct Hnsw {
   std::mutex mu;
   DeviceBuf q_in, q_deq, q_n2, visited, out, counts;
   uint64_t last_evals = 0, last_exp = 0;
+  uint64_t build_fast_queries = 0, build_fast_fallbacks = 0;   // bulk build: searches served by the FAST path / re-run exactly
   double build_ms[4] = {0, 0, 0, 0};            // bulk build: ingest, kNN search, exact edge distances, host graph assembly
   ~Hnsw() {
     cudaSetDevice(device);

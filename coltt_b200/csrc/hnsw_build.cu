@@ -384,6 +384,12 @@ static int hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids_in, c
       if (e != cudaSuccess) return fail(COLTT_ERR_CUDA, std::string("bulk build: neighbour search failed: ") + cudaGetErrorString(e));
       COLTT_CUDA(cudaGetLastError());
     }
+    {
+      unsigned long long fb = 0;
+      COLTT_CUDA(cudaMemcpy(&fb, shard->d_stat, 8, cudaMemcpyDeviceToHost));
+      h->build_fast_queries += shard->fast_queries;
+      h->build_fast_fallbacks += fb;
+    }
     shard.reset();
     const double tb = now_ms();
     lr.nbr.resize(m * (size_t)M);
@@ -498,6 +504,12 @@ COLTT_API int coltt_b200_hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint6
 COLTT_API int coltt_b200_hnsw_commit(coltt_hnsw* h, void* buf, size_t* len) {
   if (!h || !len) return fail(COLTT_ERR_INVALID, "null argument");
   return coltt::hnsw_commit(reinterpret_cast<Hnsw*>(h), buf, len);
+}
+COLTT_API int coltt_b200_hnsw_build_fast_stats(coltt_hnsw* h, uint64_t* out2) {
+  if (!h || !out2) return fail(COLTT_ERR_INVALID, "null argument");
+  out2[0] = reinterpret_cast<Hnsw*>(h)->build_fast_queries;
+  out2[1] = reinterpret_cast<Hnsw*>(h)->build_fast_fallbacks;
+  return COLTT_OK;
 }
 COLTT_API int coltt_b200_hnsw_build_stats(coltt_hnsw* h, double* ms4, uint64_t* n_edges, int32_t* max_level) {
   if (!h || !ms4) return fail(COLTT_ERR_INVALID, "null argument");

@@ -76,8 +76,10 @@ class Hnsw:
         ms = (C.c_double * 4)()
         ne, ml = C.c_uint64(0), C.c_int32(0)
         _lib.check(_lib.lib().coltt_b200_hnsw_build_stats(self._h, ms, C.byref(ne), C.byref(ml)))
+        fs = (C.c_uint64 * 2)()
+        _lib.check(_lib.lib().coltt_b200_hnsw_build_fast_stats(self._h, fs))
         return {"ingest_ms": ms[0], "knn_ms": ms[1], "edge_dist_ms": ms[2], "host_graph_ms": ms[3], "n_edges": int(ne.value),
-                "max_level": int(ml.value)}
+                "max_level": int(ml.value), "fast_queries": int(fs[0]), "fast_fallbacks": int(fs[1])}
 
     def close(self):
         if getattr(self, "_h", None):

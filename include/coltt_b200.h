@@ -197,6 +197,8 @@ COLTT_API int coltt_b200_hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint6
 COLTT_API int coltt_b200_hnsw_commit(coltt_hnsw* h, void* buf, size_t* len);
 /* Bulk-build wall times in ms: [0] ingest, [1] kNN search, [2] edge distances, [3] host graph assembly. */
 COLTT_API int coltt_b200_hnsw_build_stats(coltt_hnsw* h, double* ms4, uint64_t* n_edges, int32_t* max_level);
+/* [0] construction searches served by the tensor-core filter, [1] of those re-run exactly (margin not certified). */
+COLTT_API int coltt_b200_hnsw_build_fast_stats(coltt_hnsw* h, uint64_t* out2);
 
 /* ---- timing (replaces pprof for this path) ---------------------------------
  * Device time in milliseconds of the kernels of the last search on this handle, measured
