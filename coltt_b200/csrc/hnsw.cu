@@ -31,16 +31,22 @@
 namespace coltt {
 
 static constexpr int kHnswThreads = 128;
-static constexpr uint32_t kHnswBatch = 64;       // neighbour rows scored per pass (16 per warp)
-static constexpr uint32_t kCandCap = 8192;       // candidate min-heap capacity (shared memory)
+static constexpr uint32_t kHnswChunkMax = 32;    // neighbour rows gathered and scored per pass (8 per warp)
+static constexpr uint32_t kCandCapMin = 1024;    // candidate min-heap capacity (shared memory): first attempt
+static constexpr uint32_t kCandCapMax = 8192;    //   ... and the re-run after an overflow
+static constexpr uint32_t kNoSlot = 0xffffffffu;
 
 struct HnswParams {
   const uint8_t* rows; uint32_t row_stride; uint32_t dim; uint32_t q_stride;
   const float* row_norm2; const uint64_t* ids; const int32_t* level;
   const uint32_t* vbase; const uint32_t* edge_off; const uint32_t* edge_nbr;
+  const uint32_t* nbr0; uint32_t nbr0_stride;   // level-0 adjacency at a fixed stride, kNoSlot-terminated
   uint32_t n; uint32_t entry; int metric;
   const float* queries; const float* q_norm2;   // prepared (normalized) queries [nq][q_stride]
   uint32_t nq; uint32_t k; uint32_t ef;
+  uint32_t chunk_rows;                          // rows per gather pass (<= kHnswChunkMax)
+  uint32_t rs;                                  // shared-memory row stride in bytes (== 32 mod 128: conflict-free LDS.64)
+  uint32_t cand_cap;
   uint32_t* visited;                            // [nq][words] bitmap, zeroed by the caller
   uint32_t visited_words;
   Hit* out; int* out_counts; uint32_t out_stride;
@@ -49,201 +55,243 @@ struct HnswParams {
 
 // Go container/heap (src/container/heap/heap.go: up / down), keyed on priority only —
 // core/vectorindex/priority_queue.go:160-199: min queue Less = a<b, max queue Less = a>b.
+// Entries are {priority bits, slot} pairs (one LDS.64 each).  up/down move a hole instead of swapping:
+// the comparisons made and the final array are exactly those of Go's swap-based loops.
 struct SmemHeap {
-  float* prio; uint32_t* slot; uint32_t n; bool is_max;
-  __device__ __forceinline__ bool less(uint32_t i, uint32_t j) const { return is_max ? prio[i] > prio[j] : prio[i] < prio[j]; }
-  __device__ __forceinline__ void swap(uint32_t i, uint32_t j) {
-    float p = prio[i]; prio[i] = prio[j]; prio[j] = p;
-    uint32_t s = slot[i]; slot[i] = slot[j]; slot[j] = s;
-  }
-  __device__ void up(uint32_t j) {
+  uint2* e; uint32_t n; bool is_max;
+  __device__ __forceinline__ bool less(float a, float b) const { return is_max ? a > b : a < b; }
+  __device__ __forceinline__ float top() const { return __uint_as_float(e[0].x); }
+  __device__ __forceinline__ void up(uint32_t j, uint2 x) {
+    const float xp = __uint_as_float(x.x);
     while (j > 0) {
-      uint32_t i = (j - 1) / 2;
-      if (i == j || !less(j, i)) break;
-      swap(i, j);
+      const uint32_t i = (j - 1) / 2;
+      const uint2 par = e[i];
+      if (!less(xp, __uint_as_float(par.x))) break;
+      e[j] = par;
       j = i;
     }
+    e[j] = x;
   }
-  __device__ void down(uint32_t i0, uint32_t m) {
-    uint32_t i = i0;
+  __device__ __forceinline__ void down(uint32_t i, uint32_t m, uint2 x) {
+    const float xp = __uint_as_float(x.x);
     for (;;) {
-      uint32_t j1 = 2 * i + 1;
+      const uint32_t j1 = 2 * i + 1;
       if (j1 >= m) break;
-      uint32_t j = j1, j2 = j1 + 1;
-      if (j2 < m && less(j2, j1)) j = j2;
-      if (!less(j, i)) break;
-      swap(i, j);
+      uint2 c = e[j1];
+      uint32_t j = j1;
+      if (j1 + 1 < m) {
+        const uint2 c2 = e[j1 + 1];
+        if (less(__uint_as_float(c2.x), __uint_as_float(c.x))) { c = c2; j = j1 + 1; }
+      }
+      if (!less(__uint_as_float(c.x), xp)) break;
+      e[i] = c;
       i = j;
     }
+    e[i] = x;
   }
-  __device__ void push(float p, uint32_t s) { prio[n] = p; slot[n] = s; n++; up(n - 1); }
-  __device__ void pop(float& p, uint32_t& s) {
-    uint32_t m = n - 1;
-    swap(0, m);
-    down(0, m);
-    p = prio[m]; s = slot[m];
+  __device__ __forceinline__ void push(float p, uint32_t s) { up(n, make_uint2(__float_as_uint(p), s)); n++; }
+  // heap.Pop: Swap(0, n-1); down(0, n-1); remove the last
+  __device__ __forceinline__ void pop(float& p, uint32_t& s) {
+    const uint32_t m = n - 1;
+    const uint2 t = e[0];
+    if (m > 0) down(0, m, e[m]);
+    p = __uint_as_float(t.x); s = t.y;
     n = m;
   }
 };
 
+// One CTA per query.  Warp 0 drives the walk: lane 0 replays the reference's sequential logic (Go heaps, the
+// greedy scan) over the pass that was just scored and decides the next pass; the whole warp then fetches that
+// neighbour list, test-and-sets the visited bits, compacts the unvisited slots (ballot: list order is kept) and
+// issues one cp.async.bulk (UBLKCP) per row, so every row of an expansion is in flight at once.  All four warps
+// score the rows out of shared memory (4 lanes per row, 2 AVX-lane chains each: the exact avx.cpp arithmetic of
+// flat_scan.cu).  lowerBound is frozen per expansion in the reference (hnsw.go:357), which is what makes the
+// batch legal.  Two CTA barriers per pass; passes whose neighbours are all visited never leave warp 0.
+enum { CMD_STOP = 0, CMD_ONE = 1, CMD_LIST = 2, CMD_L0 = 3 };
+enum { ST_ENTRY = 0, ST_GREEDY = 1, ST_ENTRY2 = 2, ST_SEARCH = 3 };
+
 template <int METRIC>
 __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  float* q_s = reinterpret_cast<float*>(smem);                       // [q_stride]
-  float* cand_p = q_s + p.q_stride;                                  // [kCandCap]
-  uint32_t* cand_s = reinterpret_cast<uint32_t*>(cand_p + kCandCap);
-  float* res_p = reinterpret_cast<float*>(cand_s + kCandCap);        // [ef+1]
-  uint32_t* res_s = reinterpret_cast<uint32_t*>(res_p + (p.ef + 1));
-  uint32_t* nb_slot = res_s + (p.ef + 1);                            // [kHnswBatch]
-  float* nb_dist = reinterpret_cast<float*>(nb_slot + kHnswBatch);   // [kHnswBatch]
-  uint32_t* nb_raw = reinterpret_cast<uint32_t*>(nb_dist + kHnswBatch);  // [kHnswBatch]
-  __shared__ uint32_t sh_cur, sh_cnt, sh_state;
-  __shared__ float sh_lb, sh_min;
-  __shared__ unsigned long long sh_evals, sh_exp;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* rows_s = smem;                                                        // [chunk_rows][rs]
+  float* q_s = reinterpret_cast<float*>(smem + (size_t)p.chunk_rows * p.rs);    // [q_stride]
+  uint2* cand_e = reinterpret_cast<uint2*>(q_s + p.q_stride);                    // [cand_cap]
+  uint2* res_e = cand_e + p.cand_cap;                                            // [ef+1]
+  uint32_t* nb_slot = reinterpret_cast<uint32_t*>(res_e + (p.ef + 1));          // [kHnswChunkMax]
+  float* nb_dist = reinterpret_cast<float*>(nb_slot + kHnswChunkMax);            // [kHnswChunkMax]
+  __shared__ uint32_t sh_cnt, sh_state;
+  __shared__ __align__(8) uint64_t sh_bar;
 
   const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar = smem_u32(&sh_bar);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); sh_state = 0; sh_cnt = 0; }
   for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
-  if (tid == 0) { sh_evals = 0; sh_exp = 0; }
   __syncthreads();
   const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
   const uint32_t full8 = (p.dim / 8) * 8;
-  const uint32_t r = lane_row16(lane), g = lane_half(lane);
+  const uint32_t cw = p.chunk_rows;
   uint32_t* vis = p.visited + (size_t)q * p.visited_words;
+  uint32_t phase = 0;
 
-  // exact distances of nb_slot[0..m) -> nb_dist[] (pkg/distance via avx.cpp order; see flat_scan.cu)
-  auto batch_dist = [&](uint32_t m) {
-    const uint32_t j = warp * 16 + r;
-    if (warp * 16 < m) {
-      const bool valid = j < m;
-      const uint32_t row = valid ? nb_slot[j] : nb_slot[0];
-      const uint8_t* rowp = p.rows + (size_t)row * p.row_stride;
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-      for (uint32_t e = 0; e < full8; e += 8) {
-        float rv[4];
-        load4<ELEM_F32>(rowp + (size_t)(e + 4 * g) * 4, nullptr, rv);
-        const float4 qv = *reinterpret_cast<const float4*>(q_s + e + 4 * g);
-        if (METRIC == COLTT_COSINE) {
-          acc[0] = add_rn(acc[0], mul_rn(qv.x, rv[0])); acc[1] = add_rn(acc[1], mul_rn(qv.y, rv[1]));
-          acc[2] = add_rn(acc[2], mul_rn(qv.z, rv[2])); acc[3] = add_rn(acc[3], mul_rn(qv.w, rv[3]));
-        } else {
-          float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
-          acc[0] = add_rn(acc[0], mul_rn(d0, d0)); acc[1] = add_rn(acc[1], mul_rn(d1, d1));
-          acc[2] = add_rn(acc[2], mul_rn(d2, d2)); acc[3] = add_rn(acc[3], mul_rn(d3, d3));
-        }
-      }
-      float h = add_rn(add_rn(acc[0], acc[1]), add_rn(acc[2], acc[3]));
-      float o = __shfl_xor_sync(0xffffffffu, h, 8);
-      float tot = g == 0 ? add_rn(h, o) : add_rn(o, h);
-      for (uint32_t d = full8; d < p.dim; d++) {
-        float rv = load1<ELEM_F32>(rowp, d, nullptr), qv = q_s[d];
-        if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
-        else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
-      }
-      if (valid && g == 0) nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[row]) : sqrt_via_f64(tot);
-    }
-    __syncthreads();
-  };
+  // lane-0 state of warp 0
+  unsigned long long evals = 0, exps = 0;
+  SmemHeap cand{cand_e, 0, false}, res{res_e, 0, true};
+  int stage = ST_ENTRY, l = 0;
+  uint32_t ep = p.entry, best = kNoSlot, c0 = 0, e1 = 0, prev_m = 0, cur = 0, chunk = 0;
+  bool need_list = true, chunk_more = false, started = false;
+  float min_d = 0.0f, lb = 0.0f;
 
-  // ---- entrypoint distance (hnsw.go:253) and greedy descent through the upper levels (:254-256)
-  uint32_t ep = p.entry;
-  if (tid == 0) nb_slot[0] = ep;
-  __syncthreads();
-  batch_dist(1);
-  float min_d = nb_dist[0];
-  if (tid == 0) sh_evals += 1;
-  for (int l = p.level[ep]; l > 0; l--) {
-    for (;;) {  // greedyClosestNeighbor, hnsw.go:320-343
-      const uint32_t vb = p.vbase[ep];
-      const uint32_t e0 = p.edge_off[vb + l], e1 = p.edge_off[vb + l + 1];
-      if (tid == 0) { sh_cur = 0xffffffffu; sh_min = min_d; }
-      __syncthreads();
-      for (uint32_t c0 = e0; c0 < e1; c0 += kHnswBatch) {
-        const uint32_t m = e1 - c0 < kHnswBatch ? e1 - c0 : kHnswBatch;
-        if (tid < m) nb_slot[tid] = p.edge_nbr[c0 + tid];
-        __syncthreads();
-        batch_dist(m);
-        if (tid == 0) {
-          for (uint32_t i = 0; i < m; i++)
-            if (nb_dist[i] < sh_min) { sh_min = nb_dist[i]; sh_cur = nb_slot[i]; }
-          sh_evals += m;
-        }
-        __syncthreads();
-      }
-      const uint32_t closest = sh_cur;
-      min_d = sh_min;
-      __syncthreads();
-      if (closest == 0xffffffffu) break;
-      ep = closest;
-    }
-  }
-
-  // ---- searchLevel(query, ep, ef, 0), hnsw.go:345-389
-  SmemHeap cand{cand_p, cand_s, 0, false}, res{res_p, res_s, 0, true};
-  if (tid == 0) nb_slot[0] = ep;
-  __syncthreads();
-  batch_dist(1);                                   // entrypointDistance is recomputed (:346)
-  if (tid == 0) {
-    sh_evals += 1;
-    cand.push(nb_dist[0], ep);
-    res.push(nb_dist[0], ep);
-    atomicOr(vis + (ep >> 5), 1u << (ep & 31));
-    sh_state = 0;
-  }
-  __syncthreads();
   for (;;) {
-    if (tid == 0) {
-      if (cand.n == 0) sh_state = 1;
-      else {
-        float cp; uint32_t cs;
-        cand.pop(cp, cs);
-        const float lb = res.prio[0];               // resultVertices.Peek() (:357)
-        if (cp > lb) sh_state = 1;                  // (:359-361)
-        else { sh_cur = cs; sh_lb = lb; sh_exp += 1; }
+    if (warp == 0) {
+      uint32_t m = 0;
+      for (;;) {
+        uint32_t kind = CMD_STOP, a = 0, b = 0;
+        if (lane == 0) {
+          uint32_t stop = 1;
+          // ---- fold the pass that was just scored (nb_slot / nb_dist [0, prev_m)) into the walk
+          if (!started) {
+            started = true;                                   // nothing scored yet: first pass = the entrypoint (hnsw.go:253)
+          } else if (stage == ST_ENTRY) {
+            min_d = nb_dist[0];
+            evals += 1;
+            l = p.level[ep];
+            stage = ST_GREEDY;
+          } else if (stage == ST_GREEDY) {                    // greedyClosestNeighbor, hnsw.go:320-343
+            for (uint32_t i = 0; i < prev_m; i++)
+              if (nb_dist[i] < min_d) { min_d = nb_dist[i]; best = nb_slot[i]; }
+            evals += prev_m;
+          } else if (stage == ST_ENTRY2) {                    // searchLevel(query, ep, ef, 0): hnsw.go:346-352
+            evals += 1;
+            cand.push(nb_dist[0], ep);
+            res.push(nb_dist[0], ep);
+            atomicOr(vis + (ep >> 5), 1u << (ep & 31));
+            __threadfence_block();
+            stage = ST_SEARCH;
+          } else {                                            // hnsw.go:364-384
+            evals += prev_m;
+            for (uint32_t i = 0; i < prev_m; i++) {
+              const float d = nb_dist[i];
+              if (d < lb || res.n < p.ef) {                   // (:374)
+                if (cand.n >= p.cand_cap) { stop = 2; break; }
+                cand.push(d, nb_slot[i]);
+                res.push(d, nb_slot[i]);
+                if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
+              }
+            }
+          }
+          prev_m = 0;
+          // ---- decide the next pass
+          if (stop == 2) {
+            kind = CMD_STOP;
+          } else if (stage == ST_ENTRY) {
+            kind = CMD_ONE; a = ep;
+          } else {
+            if (stage == ST_GREEDY) {
+              for (;;) {
+                if (need_list) {
+                  if (l <= 0) { stage = ST_ENTRY2; break; }
+                  const uint32_t vb = p.vbase[ep];
+                  c0 = p.edge_off[vb + l]; e1 = p.edge_off[vb + l + 1];
+                  need_list = false;
+                }
+                if (c0 < e1) {
+                  kind = CMD_LIST; a = c0; b = e1 - c0 < cw ? e1 : c0 + cw;
+                  c0 = b;
+                  break;
+                }
+                if (best == kNoSlot) l--;                     // no strictly closer neighbour: next level down (:338-340)
+                else { ep = best; best = kNoSlot; }           // move and scan again
+                need_list = true;
+              }
+            }
+            if (stage == ST_ENTRY2) {
+              kind = CMD_ONE; a = ep;                         // entrypointDistance is recomputed (:346)
+            } else if (stage == ST_SEARCH) {
+              if (!chunk_more) {
+                if (cand.n == 0) kind = CMD_STOP;             // (:354)
+                else {
+                  float cp; uint32_t cs;
+                  cand.pop(cp, cs);
+                  lb = res.top();                             // resultVertices.Peek() (:357)
+                  if (cp > lb) kind = CMD_STOP;               // (:359-361)
+                  else { cur = cs; chunk = 0; exps += 1; kind = CMD_L0; }
+                }
+              } else kind = CMD_L0;
+              a = cur; b = chunk;
+            }
+          }
+          if (kind == CMD_STOP) sh_state = stop;
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        a = __shfl_sync(0xffffffffu, a, 0);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (kind == CMD_STOP) { m = 0; break; }
+        uint32_t s = kNoSlot;
+        bool valid = false;
+        if (kind == CMD_ONE) { s = a; valid = lane == 0; }
+        else if (kind == CMD_LIST) {
+          valid = a + lane < b;
+          if (valid) s = p.edge_nbr[a + lane];
+        } else {
+          // visited test-and-set for the whole chunk (:368-371), in parallel; the ballot below keeps list order
+          const uint32_t off = b * cw + lane;
+          if (lane < cw && off < p.nbr0_stride) s = p.nbr0[(size_t)a * p.nbr0_stride + off];
+          const bool listed = s != kNoSlot;
+          const uint32_t lm = __ballot_sync(0xffffffffu, listed);
+          if (listed) {
+            const uint32_t old = atomicOr(vis + (s >> 5), 1u << (s & 31));
+            valid = !((old >> (s & 31)) & 1u);
+          }
+          chunk_more = (uint32_t)__popc(lm) == cw && (b + 1) * cw < p.nbr0_stride;
+          chunk = b + 1;
+        }
+        // compact the valid slots into nb_slot[] and start their row copies
+        const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t pos = __popc(mask & ((1u << lane) - 1u));
+        m = __popc(mask);
+        if (valid) nb_slot[pos] = s;
+        if (lane == 0 && m) mbar_arrive_expect_tx(bar, m * p.row_stride);
+        __syncwarp();
+        if (valid) bulk_g2s(smem_u32(rows_s + (size_t)pos * p.rs), p.rows + (size_t)s * p.row_stride, p.row_stride, bar);
+        if (m) break;
       }
+      if (lane == 0) { sh_cnt = m; prev_m = m; }
     }
     __syncthreads();
     if (sh_state) break;
-    const uint32_t cur = sh_cur;
-    const float lb = sh_lb;
-    const uint32_t vb = p.vbase[cur];
-    const uint32_t e0 = p.edge_off[vb], e1 = p.edge_off[vb + 1];
-    for (uint32_t c0 = e0; c0 < e1; c0 += kHnswBatch) {
-      const uint32_t m_raw = e1 - c0 < kHnswBatch ? e1 - c0 : kHnswBatch;
-      // visited test-and-set for the whole chunk (:368-371), in parallel; order is restored below
-      if (tid < m_raw) {
-        const uint32_t s = p.edge_nbr[c0 + tid];
-        const uint32_t old = atomicOr(vis + (s >> 5), 1u << (s & 31));
-        nb_raw[tid] = (old >> (s & 31)) & 1u ? 0xffffffffu : s;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t m = 0;
-        for (uint32_t i = 0; i < m_raw; i++)
-          if (nb_raw[i] != 0xffffffffu) nb_slot[m++] = nb_raw[i];
-        sh_cnt = m;
-      }
-      __syncthreads();
-      const uint32_t m = sh_cnt;
-      if (m) {
-        batch_dist(m);
-        if (tid == 0) {
-          sh_evals += m;
-          for (uint32_t i = 0; i < m; i++) {
-            const float d = nb_dist[i];
-            if (d < lb || res.n < p.ef) {            // (:374)
-              if (cand.n >= kCandCap) { sh_state = 2; break; }
-              cand.push(d, nb_slot[i]);
-              res.push(d, nb_slot[i]);
-              if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
-            }
-          }
+    const uint32_t m = sh_cnt;
+    // ---- all warps: exact distances of the m gathered rows -> nb_dist[]
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (warp * 8 < m) {
+      const uint32_t j = warp * 8 + (lane >> 2), h = lane & 3;
+      const bool valid = j < m;
+      const uint8_t* rowp = rows_s + (size_t)(valid ? j : 0) * p.rs;
+      float a0 = 0.0f, a1 = 0.0f;                 // AVX lanes 2h and 2h+1
+#pragma unroll 8
+      for (uint32_t e = 0; e < full8; e += 8) {
+        const float2 rv = *reinterpret_cast<const float2*>(rowp + (size_t)(e + 2 * h) * 4);
+        const float2 qv = *reinterpret_cast<const float2*>(q_s + e + 2 * h);
+        if (METRIC == COLTT_COSINE) {
+          a0 = add_rn(a0, mul_rn(qv.x, rv.x)); a1 = add_rn(a1, mul_rn(qv.y, rv.y));
+        } else {
+          const float d0 = sub_rn(qv.x, rv.x), d1 = sub_rn(qv.y, rv.y);
+          a0 = add_rn(a0, mul_rn(d0, d0)); a1 = add_rn(a1, mul_rn(d1, d1));
         }
       }
-      __syncthreads();
-      if (sh_state == 2) break;
+      // ((l0+l1)+(l2+l3)) + ((l4+l5)+(l6+l7)): the reduction tree of flat_scan.cu (avx.cpp:26-31,66-73)
+      float t = add_rn(a0, a1);
+      t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      float tot = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      for (uint32_t d = full8; d < p.dim; d++) {
+        const float rv = reinterpret_cast<const float*>(rowp)[d], qv = q_s[d];
+        if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
+        else { const float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
+      }
+      if (valid && h == 0)
+        nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[nb_slot[j]]) : sqrt_via_f64(tot);
     }
-    if (sh_state == 2) break;
+    __syncthreads();
   }
   // ---- selectNeighbors(k) (hnsw.go:391-397) and the back-to-front fill (:268-275)
   if (tid == 0) {
@@ -262,8 +310,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
       }
       p.out_counts[q] = (int)n_out;
     }
-    atomicAdd(p.stats + 0, sh_evals);
-    atomicAdd(p.stats + 1, sh_exp);
+    atomicAdd(p.stats + 0, evals);
+    atomicAdd(p.stats + 1, exps);
   }
 }
 
@@ -295,12 +343,20 @@ int hnsw_install_graph(Hnsw* h, const std::vector<uint32_t>& vbase, std::vector<
   }
   edge_off[vbase[n]] = (uint32_t)edge_nbr.size();
   int rc;
-  for (void* ptr : {(void*)h->d_vbase, (void*)h->d_edge_off, (void*)h->d_edge_nbr, (void*)h->d_edge_dist})
+  // level-0 lists again at a fixed stride (one dependent load per expansion instead of vbase -> edge_off -> edge_nbr)
+  uint32_t deg0 = 0;
+  for (uint32_t v = 0; v < n; v++) deg0 = std::max(deg0, edge_off[vbase[v] + 1] - edge_off[vbase[v]]);
+  const uint32_t stride0 = std::max(32u, (deg0 + 31) / 32 * 32);
+  std::vector<uint32_t> nbr0((size_t)n * stride0, 0xffffffffu);
+  for (uint32_t v = 0; v < n; v++)
+    std::copy(edge_nbr.begin() + edge_off[vbase[v]], edge_nbr.begin() + edge_off[vbase[v] + 1], nbr0.begin() + (size_t)v * stride0);
+  for (void* ptr : {(void*)h->d_vbase, (void*)h->d_edge_off, (void*)h->d_edge_nbr, (void*)h->d_edge_dist, (void*)h->d_nbr0})
     if (ptr) cudaFree(ptr);
-  h->d_vbase = h->d_edge_off = h->d_edge_nbr = h->d_edge_dist = nullptr;
+  h->d_vbase = h->d_edge_off = h->d_edge_nbr = h->d_edge_dist = h->d_nbr0 = nullptr;
   if ((rc = upload(&h->d_vbase, vbase)) || (rc = upload(&h->d_edge_off, edge_off)) || (rc = upload(&h->d_edge_nbr, edge_nbr)) ||
-      (rc = upload(&h->d_edge_dist, edge_dist)))
+      (rc = upload(&h->d_edge_dist, edge_dist)) || (rc = upload(&h->d_nbr0, nbr0)))
     return rc;
+  h->nbr0_stride = stride0;
   h->n_edges = edge_nbr.size();
   return COLTT_OK;
 }
@@ -417,8 +473,33 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   }
   const uint32_t ef = (uint32_t)std::max(ef_in > 0 ? ef_in : h->ef_default, k);   // gomath.MaxInt(ef, k) hnsw.go:258
   const uint32_t q_stride = (h->dim + 7) / 8 * 8;
-  const size_t smem = (size_t)q_stride * 4 + (size_t)kCandCap * 8 + (size_t)(ef + 1) * 8 + kHnswBatch * 12;
-  if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
+  // Shared memory per CTA = gathered rows + query + both heaps.  Two CTAs per SM when the batch has more queries
+  // than SMs (the walk is latency bound: a second resident query hides the first one's serial heap work).
+  const uint32_t rs = (h->row_stride + 127) / 128 * 128 + 32;
+  const size_t sm_total = 227 * 1024;
+  uint32_t cand_cap = kCandCapMin;
+  while (cand_cap < 8 * ef && cand_cap < kCandCapMax) cand_cap *= 2;
+  static const int env_chunk = getenv("COLTT_HNSW_CHUNK") ? atoi(getenv("COLTT_HNSW_CHUNK")) : 0;
+  static const int env_ctas = getenv("COLTT_HNSW_CTAS") ? atoi(getenv("COLTT_HNSW_CTAS")) : 0;
+  uint32_t chunk_rows = 0;
+  size_t smem = 0;
+  auto plan = [&](uint32_t cap) -> bool {
+    const size_t fixed = (size_t)q_stride * 4 + (size_t)cap * 8 + (size_t)(ef + 1) * 8 + kHnswChunkMax * 8;
+    int ctas = env_ctas > 0 ? env_ctas : (nq > (size_t)h->n_sms ? 2 : 1);
+    for (; ctas >= 1; ctas--) {
+      const size_t budget = sm_total / ctas - 1024 - 128;     // 1 KB reserved per CTA + the static shared variables
+      if (budget <= fixed) continue;
+      uint32_t c = (uint32_t)std::min<size_t>((budget - fixed) / rs, kHnswChunkMax);
+      if (env_chunk > 0) c = std::min<uint32_t>(c, (uint32_t)env_chunk);
+      if (c >= 8 || (ctas == 1 && c >= 1)) {
+        chunk_rows = c;
+        smem = fixed + (size_t)c * rs;
+        return true;
+      }
+    }
+    return false;
+  };
+  if (!plan(cand_cap)) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
   const uint32_t words = (h->n + 31) / 32;
   cudaStream_t st = h->stream;
   int rc;
@@ -432,30 +513,38 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   pp.norm2_out = (float*)h->q_n2.p; pp.deq_out = (float*)h->q_deq.p; pp.deq_stride = q_stride;
   rc = launch_prep_rows(pp, ELEM_F32, st);
   if (rc) return rc;
-  COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
-  COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), st));
   HnswParams p{};
   p.rows = h->d_rows; p.row_stride = h->row_stride; p.dim = h->dim; p.q_stride = q_stride; p.row_norm2 = h->d_norm2; p.ids = h->d_ids;
   p.level = h->d_level; p.vbase = h->d_vbase; p.edge_off = h->d_edge_off; p.edge_nbr = h->d_edge_nbr; p.n = h->n; p.entry = h->entry;
+  p.nbr0 = h->d_nbr0; p.nbr0_stride = h->nbr0_stride;
   p.metric = h->metric; p.queries = (const float*)h->q_deq.p; p.q_norm2 = (const float*)h->q_n2.p; p.nq = (uint32_t)nq; p.k = (uint32_t)k;
   p.ef = ef; p.visited = (uint32_t*)h->visited.p; p.visited_words = words; p.out = (Hit*)h->out.p; p.out_counts = (int*)h->counts.p;
-  p.out_stride = (uint32_t)k; p.stats = h->d_stats;
-  if (h->metric == COLTT_COSINE) {
-    { int arc = kernel_attrs(hnsw_search_kernel<COLTT_COSINE>, smem); if (arc) return arc; }
-    hnsw_search_kernel<COLTT_COSINE><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
-  } else {
-    { int arc = kernel_attrs(hnsw_search_kernel<COLTT_EUCLIDEAN>, smem); if (arc) return arc; }
-    hnsw_search_kernel<COLTT_EUCLIDEAN><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
-  }
-  count_launch();
-  COLTT_CUDA(cudaGetLastError());
+  p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = rs;
   std::vector<Hit> hits(nq * (size_t)k);
   unsigned long long stats[3];
-  COLTT_CUDA(cudaMemcpyAsync(hits.data(), h->out.p, hits.size() * sizeof(Hit), cudaMemcpyDeviceToHost, st));
-  COLTT_CUDA(cudaMemcpyAsync(out_counts, h->counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
-  COLTT_CUDA(cudaMemcpyAsync(stats, h->d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
-  COLTT_CUDA(cudaStreamSynchronize(st));
-  if (stats[2]) return fail(COLTT_ERR_UNSUPPORTED, "HNSW candidate queue overflowed its shared-memory capacity (ef too large)");
+  for (;;) {
+    p.chunk_rows = chunk_rows; p.cand_cap = cand_cap;
+    COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
+    COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), st));
+    if (h->metric == COLTT_COSINE) {
+      { int arc = kernel_attrs(hnsw_search_kernel<COLTT_COSINE>, smem); if (arc) return arc; }
+      hnsw_search_kernel<COLTT_COSINE><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
+    } else {
+      { int arc = kernel_attrs(hnsw_search_kernel<COLTT_EUCLIDEAN>, smem); if (arc) return arc; }
+      hnsw_search_kernel<COLTT_EUCLIDEAN><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
+    }
+    count_launch();
+    COLTT_CUDA(cudaGetLastError());
+    COLTT_CUDA(cudaMemcpyAsync(hits.data(), h->out.p, hits.size() * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+    COLTT_CUDA(cudaMemcpyAsync(out_counts, h->counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    COLTT_CUDA(cudaMemcpyAsync(stats, h->d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+    COLTT_CUDA(cudaStreamSynchronize(st));
+    if (!stats[2]) break;
+    // a candidate queue outgrew its shared-memory heap: run the batch again with the largest one
+    if (cand_cap >= kCandCapMax || !plan(kCandCapMax))
+      return fail(COLTT_ERR_UNSUPPORTED, "HNSW candidate queue overflowed its shared-memory capacity (ef too large)");
+    cand_cap = kCandCapMax;
+  }
   h->last_evals = stats[0];
   h->last_exp = stats[1];
   for (size_t q = 0; q < nq; q++)

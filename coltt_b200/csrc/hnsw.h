@@ -19,6 +19,8 @@ struct Hnsw {
   uint8_t* d_rows = nullptr; float* d_norm2 = nullptr; uint64_t* d_ids = nullptr; int32_t* d_level = nullptr;
   uint32_t *d_vbase = nullptr, *d_edge_off = nullptr, *d_edge_nbr = nullptr;
   uint32_t* d_edge_dist = nullptr;              // fp32 bits of every edge's stored distance (Commit only)
+  uint32_t* d_nbr0 = nullptr;                   // level-0 neighbours [n][nbr0_stride], 0xffffffff-terminated (search only)
+  uint32_t nbr0_stride = 32;
   unsigned long long* d_stats = nullptr;
   cudaStream_t stream = nullptr;
   std::mutex mu;
@@ -29,7 +31,7 @@ struct Hnsw {
   ~Hnsw() {
     cudaSetDevice(device);
     for (void* ptr : {(void*)d_rows, (void*)d_norm2, (void*)d_ids, (void*)d_level, (void*)d_vbase, (void*)d_edge_off, (void*)d_edge_nbr,
-                      (void*)d_edge_dist, (void*)d_stats})
+                      (void*)d_edge_dist, (void*)d_nbr0, (void*)d_stats})
       if (ptr) cudaFree(ptr);
     if (stream) cudaStreamDestroy(stream);
   }

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-(DATA=latent N=100000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:hnsw_search -s 2 -c 1 -o gpurun_out/k4_full -f python tools/probe_hnsw_1m.py > gpurun_out/ncu_k4.log 2>&1)
-(DATA=latent N=100000 NQ=1024 timeout 600 python tools/probe_hnsw_1m.py > gpurun_out/hnsw_100k_nq1024.log 2>&1)
-tail -n 3 gpurun_out/ncu_k4.log; cat gpurun_out/hnsw_100k_nq1024.log
+(timeout 600 python -m pytest tests/test_gpu_hnsw.py tests/test_gpu_hnsw_build.py -m gpu -q -x 2>&1 | tail -30) > gpurun_out/pytest_hb.log
+cat gpurun_out/pytest_hb.log
+(DATA=latent N=100000 NQ=256,1024 timeout 300 python tools/probe_hnsw_1m.py > gpurun_out/hnsw_100k_v2.log 2>&1); cat gpurun_out/hnsw_100k_v2.log
+(DATA=latent N=1000000 NQ=256,1024 timeout 600 python tools/probe_hnsw_1m.py > gpurun_out/hnsw_1m_v2.log 2>&1); cat gpurun_out/hnsw_1m_v2.log
