@@ -18,6 +18,7 @@
 // over the batch.  lowerBound is frozen per expansion in the reference (hnsw.go:357), which is
 // what makes the batch legal.  Throughput comes from many resident CTAs (queries) per SM.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -50,7 +51,9 @@ struct HnswParams {
   uint32_t* visited;                            // [nq][words] bitmap, zeroed by the caller
   uint32_t visited_words;
   Hit* out; int* out_counts; uint32_t out_stride;
-  unsigned long long* stats;                    // [0] distance evaluations, [1] expansions, [2] overflow flag
+  const uint32_t* q_map;                        // CTA -> query (re-runs of a subset), or null
+  uint2* qlog; uint32_t log_cap;                // [nq][log_cap] queue operations of the fast path (replayed after a tie)
+  unsigned long long* stats;                    // [0] distance evaluations, [1] expansions, [2] queue overflows, [3] ties
 };
 
 // Go container/heap (src/container/heap/heap.go: up / down), keyed on priority only —
@@ -100,17 +103,103 @@ struct SmemHeap {
   }
 };
 
-// One CTA per query.  Warp 0 drives the walk: lane 0 replays the reference's sequential logic (Go heaps, the
-// greedy scan) over the pass that was just scored and decides the next pass; the whole warp then fetches that
-// neighbour list, test-and-sets the visited bits, compacts the unvisited slots (ballot: list order is kept) and
-// issues one cp.async.bulk (UBLKCP) per row, so every row of an expansion is in flight at once.  All four warps
-// score the rows out of shared memory (4 lanes per row, 2 AVX-lane chains each: the exact avx.cpp arithmetic of
+// The result set of searchLevel as a sorted array spread over warp 0's registers (lane L owns entries
+// [L*R, L*R+R), ascending priority, +inf padding), used while every priority in it is distinct.  Then the
+// reference's two heaps reduce to ordered-set semantics: resultVertices = the ef smallest distances seen, and the
+// candidates that can still be expanded are exactly the unexpanded members of that set — a candidate evicted from
+// it has priority > lowerBound for the rest of the walk (lowerBound never grows once the set is full), so popping
+// it can only end the loop (hnsw.go:359-361), which "no unexpanded member left" does as well.  The first equal
+// pair of priorities (or a NaN) makes Go's heap layout matter: insert() reports it before changing anything, and
+// the walk continues on the literal heaps, rebuilt by replaying the log of queue operations made so far.
+template <int R>
+struct WarpSorted {
+  float p[R > 0 ? R : 1];
+  uint32_t s[R > 0 ? R : 1];                      // slot; bit 31 = already expanded
+  uint32_t n;
+  static constexpr uint32_t kExpanded = 0x80000000u;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int r = 0; r < R; r++) { p[r] = __int_as_float(0x7f800000); s[r] = kNoSlot; }
+    n = 0;
+  }
+  // true = a tie (or NaN): nothing was changed, the caller must leave the fast path
+  __device__ __forceinline__ bool insert(float d, uint32_t slot, uint32_t ef, uint32_t lane) {
+    uint32_t cnt = 0;
+    bool eq = d != d;
+#pragma unroll
+    for (int r = 0; r < R; r++) { cnt += p[r] < d ? 1u : 0u; eq |= p[r] == d; }
+    const float up_p = __shfl_up_sync(0xffffffffu, p[R - 1], 1);
+    const uint32_t up_s = __shfl_up_sync(0xffffffffu, s[R - 1], 1);
+    const uint32_t below = __ballot_sync(0xffffffffu, cnt == (uint32_t)R);   // lanes entirely below d: 0 .. full-1
+    if (__any_sync(0xffffffffu, eq)) return true;
+    const uint32_t full = __popc(below);
+    if (lane > full) {                            // everything moves up by one
+#pragma unroll
+      for (int r = R - 1; r >= 1; r--) { p[r] = p[r - 1]; s[r] = s[r - 1]; }
+      p[0] = up_p; s[0] = up_s;
+    } else if (lane == full) {                    // d lands at this lane's entry `cnt`
+#pragma unroll
+      for (int r = R - 1; r >= 1; r--) {
+        if ((uint32_t)r > cnt) { p[r] = p[r - 1]; s[r] = s[r - 1]; }
+        else if ((uint32_t)r == cnt) { p[r] = d; s[r] = slot; }
+      }
+      if (cnt == 0) { p[0] = d; s[0] = slot; }
+    }
+    n++;
+    if (n > ef) {                                  // resultVertices.Pop() of the largest (:379-381)
+      n = ef;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if (lane * R + r >= ef) { p[r] = __int_as_float(0x7f800000); s[r] = kNoSlot; }
+    }
+    return false;
+  }
+  // resultVertices.Peek(): the largest member = the last valid entry of lane (n-1)/R
+  __device__ __forceinline__ float top(uint32_t lane) const {
+    float v = p[0];
+#pragma unroll
+    for (int r = 1; r < R; r++) v = lane * R + r < n ? p[r] : v;
+    return __shfl_sync(0xffffffffu, v, ((n - 1) / R) & 31);
+  }
+  // smallest unexpanded member -> (priority, slot), marked expanded; false if there is none
+  __device__ __forceinline__ bool next(float& cp, uint32_t& cs, uint32_t lane) {
+    bool found = false, mark[R > 0 ? R : 1];
+    float vp = 0.0f;
+    uint32_t vs = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const bool c = !found && !(s[r] & kExpanded) && lane * R + r < n;
+      vp = c ? p[r] : vp;
+      vs = c ? s[r] : vs;
+      mark[r] = c;
+      found |= c;
+    }
+    const uint32_t have = __ballot_sync(0xffffffffu, found);
+    if (!have) return false;
+    const uint32_t src = __ffs(have) - 1;
+    cp = __shfl_sync(0xffffffffu, vp, src);
+    cs = __shfl_sync(0xffffffffu, vs, src);
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (mark[r] && lane == src) s[r] |= kExpanded;
+    return true;
+  }
+};
+
+// One CTA per query.  Warp 0 drives the walk: it folds the pass that was just scored into the reference's
+// sequential logic (the greedy scan; the result/candidate queues — WarpSorted while R > 0 and no tie was met,
+// else lane 0 replaying Go's heaps) and decides the next pass; then it fetches that neighbour list,
+// test-and-sets the visited bits, compacts the unvisited slots (ballot: list order is kept) and issues one
+// cp.async.bulk (UBLKCP) per row, so every row of an expansion is in flight at once.  All four warps score the
+// rows out of shared memory (4 lanes per row, 2 AVX-lane chains each: the exact avx.cpp arithmetic of
 // flat_scan.cu).  lowerBound is frozen per expansion in the reference (hnsw.go:357), which is what makes the
-// batch legal.  Two CTA barriers per pass; passes whose neighbours are all visited never leave warp 0.
+// batch legal.  Two CTA barriers per pass; passes whose neighbours are all visited never leave warp 0.  Warp 0's
+// control state is computed redundantly by all of its lanes (it depends only on shared and global memory).
 enum { CMD_STOP = 0, CMD_ONE = 1, CMD_LIST = 2, CMD_L0 = 3 };
 enum { ST_ENTRY = 0, ST_GREEDY = 1, ST_ENTRY2 = 2, ST_SEARCH = 3 };
+enum { STOP_DONE = 1, STOP_OVERFLOW = 2, STOP_TIE = 3 };
 
-template <int METRIC>
+template <int METRIC, int R>
 __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* rows_s = smem;                                                        // [chunk_rows][rs]
@@ -122,7 +211,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
   __shared__ uint32_t sh_cnt, sh_state;
   __shared__ __align__(8) uint64_t sh_bar;
 
-  const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t q = p.q_map ? p.q_map[blockIdx.x] : blockIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&sh_bar);
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); sh_state = 0; sh_cnt = 0; }
   for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
@@ -133,99 +223,170 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
   uint32_t* vis = p.visited + (size_t)q * p.visited_words;
   uint32_t phase = 0;
 
-  // lane-0 state of warp 0
+  // warp 0's walk state
   unsigned long long evals = 0, exps = 0;
-  SmemHeap cand{cand_e, 0, false}, res{res_e, 0, true};
+  SmemHeap cand{cand_e, 0, false}, res{res_e, 0, true};   // lane 0 only, once `literal`
+  WarpSorted<R> ws;
+  if constexpr (R > 0) ws.init();
+  bool literal = R == 0;
+  uint2* qlog = p.qlog + (size_t)q * p.log_cap;          // queue operations of the fast path, in order
+  uint32_t log_n = 0;
   int stage = ST_ENTRY, l = 0;
   uint32_t ep = p.entry, best = kNoSlot, c0 = 0, e1 = 0, prev_m = 0, cur = 0, chunk = 0;
   bool need_list = true, chunk_more = false, started = false;
   float min_d = 0.0f, lb = 0.0f;
 
+  // lane 0: one accepted neighbour through the reference's two heaps (hnsw.go:375-381); false = cand is full
+  auto heap_accept = [&](float d, uint32_t slot) -> bool {
+    if (cand.n >= p.cand_cap) return false;
+    cand.push(d, slot);
+    res.push(d, slot);
+    if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
+    return true;
+  };
+  // leave the fast path: lane 0 rebuilds Go's heaps by replaying the logged pushes / pops (next record prefetched)
+  auto go_literal = [&]() {
+    if (lane == 0 && log_n) {
+      uint2 e = qlog[0];
+      for (uint32_t i = 0; i < log_n; i++) {
+        const uint2 nx = i + 1 < log_n ? qlog[i + 1] : e;
+        if (e.y == kNoSlot) { float tp; uint32_t ts; cand.pop(tp, ts); }
+        else heap_accept(__uint_as_float(e.x), e.y);
+        e = nx;
+      }
+    }
+    __syncwarp();
+    literal = true;
+  };
+
   for (;;) {
     if (warp == 0) {
       uint32_t m = 0;
       for (;;) {
-        uint32_t kind = CMD_STOP, a = 0, b = 0;
-        if (lane == 0) {
-          uint32_t stop = 1;
-          // ---- fold the pass that was just scored (nb_slot / nb_dist [0, prev_m)) into the walk
-          if (!started) {
-            started = true;                                   // nothing scored yet: first pass = the entrypoint (hnsw.go:253)
-          } else if (stage == ST_ENTRY) {
-            min_d = nb_dist[0];
-            evals += 1;
-            l = p.level[ep];
-            stage = ST_GREEDY;
-          } else if (stage == ST_GREEDY) {                    // greedyClosestNeighbor, hnsw.go:320-343
-            for (uint32_t i = 0; i < prev_m; i++)
-              if (nb_dist[i] < min_d) { min_d = nb_dist[i]; best = nb_slot[i]; }
-            evals += prev_m;
-          } else if (stage == ST_ENTRY2) {                    // searchLevel(query, ep, ef, 0): hnsw.go:346-352
-            evals += 1;
-            cand.push(nb_dist[0], ep);
-            res.push(nb_dist[0], ep);
-            atomicOr(vis + (ep >> 5), 1u << (ep & 31));
-            __threadfence_block();
+        uint32_t kind = CMD_STOP, a = 0, b = 0, stop = STOP_DONE;
+        // ---- fold the pass that was just scored (nb_slot / nb_dist [0, prev_m)) into the walk
+        if (!started) {
+          started = true;                                     // nothing scored yet: first pass = the entrypoint (hnsw.go:253)
+        } else if (stage == ST_ENTRY) {
+          min_d = nb_dist[0];
+          evals += 1;
+          l = p.level[ep];
+          stage = ST_GREEDY;
+        } else if (stage == ST_GREEDY) {                      // greedyClosestNeighbor, hnsw.go:320-343
+          for (uint32_t i = 0; i < prev_m; i++) {
+            const float d = nb_dist[i];
+            if (d < min_d) { min_d = d; best = nb_slot[i]; }
+          }
+          evals += prev_m;
+        } else {                                              // ST_ENTRY2: hnsw.go:346-352; ST_SEARCH: hnsw.go:364-384
+          evals += prev_m;
+          const float dv = lane < prev_m ? nb_dist[lane] : 0.0f;
+          const uint32_t sv = lane < prev_m ? nb_slot[lane] : 0u;
+          uint32_t i0 = 0;                                    // first entry the literal heaps still have to see
+          if constexpr (R > 0) {
+            if (!literal) {
+              const uint32_t all = prev_m >= 32 ? 0xffffffffu : (1u << prev_m) - 1u;
+              const uint32_t lt = __ballot_sync(0xffffffffu, lane < prev_m && dv < lb) ;
+              const uint32_t nan = __ballot_sync(0xffffffffu, lane < prev_m && dv != dv);
+              // (:374) `distance < lowerBound || len < ef`, entries in list order; NaN goes the literal way
+              uint32_t todo = (stage == ST_ENTRY2 || ws.n < p.ef) ? all : lt;
+              i0 = prev_m;
+              while (todo) {
+                const uint32_t i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float d = __shfl_sync(0xffffffffu, dv, i);
+                const uint32_t sl = __shfl_sync(0xffffffffu, sv, i);
+                if (log_n >= p.log_cap) { stop = STOP_OVERFLOW; break; }
+                if (((nan >> i) & 1u) || ws.insert(d, sl, p.ef, lane)) { i0 = i; go_literal(); break; }
+                if (lane == 0) qlog[log_n] = make_uint2(__float_as_uint(d), sl);
+                log_n++;
+                if (ws.n >= p.ef) todo &= lt;
+              }
+            }
+          }
+          if (literal && stop == STOP_DONE) {
+            if (lane == 0) {
+              for (uint32_t i = i0; i < prev_m; i++) {
+                const float d = nb_dist[i];
+                if (stage == ST_ENTRY2 || d < lb || res.n < p.ef) {   // (:374)
+                  if (!heap_accept(d, nb_slot[i])) { stop = STOP_OVERFLOW; break; }
+                }
+              }
+            }
+            stop = __shfl_sync(0xffffffffu, stop, 0);
+          }
+          if (stage == ST_ENTRY2) {
+            if (lane == 0) { atomicOr(vis + (ep >> 5), 1u << (ep & 31)); __threadfence_block(); }
             stage = ST_SEARCH;
-          } else {                                            // hnsw.go:364-384
-            evals += prev_m;
-            for (uint32_t i = 0; i < prev_m; i++) {
-              const float d = nb_dist[i];
-              if (d < lb || res.n < p.ef) {                   // (:374)
-                if (cand.n >= p.cand_cap) { stop = 2; break; }
-                cand.push(d, nb_slot[i]);
-                res.push(d, nb_slot[i]);
-                if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
-              }
-            }
           }
-          prev_m = 0;
-          // ---- decide the next pass
-          if (stop == 2) {
-            kind = CMD_STOP;
-          } else if (stage == ST_ENTRY) {
-            kind = CMD_ONE; a = ep;
-          } else {
-            if (stage == ST_GREEDY) {
-              for (;;) {
-                if (need_list) {
-                  if (l <= 0) { stage = ST_ENTRY2; break; }
-                  const uint32_t vb = p.vbase[ep];
-                  c0 = p.edge_off[vb + l]; e1 = p.edge_off[vb + l + 1];
-                  need_list = false;
-                }
-                if (c0 < e1) {
-                  kind = CMD_LIST; a = c0; b = e1 - c0 < cw ? e1 : c0 + cw;
-                  c0 = b;
-                  break;
-                }
-                if (best == kNoSlot) l--;                     // no strictly closer neighbour: next level down (:338-340)
-                else { ep = best; best = kNoSlot; }           // move and scan again
-                need_list = true;
-              }
-            }
-            if (stage == ST_ENTRY2) {
-              kind = CMD_ONE; a = ep;                         // entrypointDistance is recomputed (:346)
-            } else if (stage == ST_SEARCH) {
-              if (!chunk_more) {
-                if (cand.n == 0) kind = CMD_STOP;             // (:354)
-                else {
-                  float cp; uint32_t cs;
-                  cand.pop(cp, cs);
-                  lb = res.top();                             // resultVertices.Peek() (:357)
-                  if (cp > lb) kind = CMD_STOP;               // (:359-361)
-                  else { cur = cs; chunk = 0; exps += 1; kind = CMD_L0; }
-                }
-              } else kind = CMD_L0;
-              a = cur; b = chunk;
-            }
-          }
-          if (kind == CMD_STOP) sh_state = stop;
         }
-        kind = __shfl_sync(0xffffffffu, kind, 0);
-        a = __shfl_sync(0xffffffffu, a, 0);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (kind == CMD_STOP) { m = 0; break; }
+        prev_m = 0;
+        // ---- decide the next pass
+        if (stop != STOP_DONE) {
+          kind = CMD_STOP;
+        } else if (stage == ST_ENTRY) {
+          kind = CMD_ONE; a = ep;
+        } else {
+          if (stage == ST_GREEDY) {
+            for (;;) {
+              if (need_list) {
+                if (l <= 0) { stage = ST_ENTRY2; break; }
+                const uint32_t vb = p.vbase[ep];
+                c0 = p.edge_off[vb + l]; e1 = p.edge_off[vb + l + 1];
+                need_list = false;
+              }
+              if (c0 < e1) {
+                kind = CMD_LIST; a = c0; b = e1 - c0 < cw ? e1 : c0 + cw;
+                c0 = b;
+                break;
+              }
+              if (best == kNoSlot) l--;                       // no strictly closer neighbour: next level down (:338-340)
+              else { ep = best; best = kNoSlot; }             // move and scan again
+              need_list = true;
+            }
+          }
+          if (stage == ST_ENTRY2) {
+            kind = CMD_ONE; a = ep;                           // entrypointDistance is recomputed (:346)
+          } else if (stage == ST_SEARCH) {
+            if (chunk_more) kind = CMD_L0;
+            else {
+              bool picked = false;
+              if constexpr (R > 0) {
+                if (!literal) {
+                  picked = true;
+                  float cp; uint32_t cs;
+                  if (log_n >= p.log_cap) { stop = STOP_OVERFLOW; }
+                  else if (ws.next(cp, cs, lane)) {           // candidateVertices.Pop() (:355); cp <= lowerBound by construction
+                    lb = ws.top(lane);                        // resultVertices.Peek() (:357)
+                    cur = cs & ~WarpSorted<R>::kExpanded; kind = CMD_L0;
+                    if (lane == 0) qlog[log_n] = make_uint2(0u, kNoSlot);
+                    log_n++;
+                  }
+                }
+              }
+              if (!picked) {
+                if (lane == 0) {
+                  if (cand.n != 0) {                          // (:354)
+                    float cp; uint32_t cs;
+                    cand.pop(cp, cs);
+                    lb = res.top();                           // resultVertices.Peek() (:357)
+                    if (!(cp > lb)) { cur = cs; kind = CMD_L0; }   // (:359-361)
+                  }
+                }
+                kind = __shfl_sync(0xffffffffu, kind, 0);
+                cur = __shfl_sync(0xffffffffu, cur, 0);
+                lb = __shfl_sync(0xffffffffu, lb, 0);
+              }
+              if (kind == CMD_L0) { chunk = 0; exps += 1; }
+            }
+            a = cur; b = chunk;
+          }
+        }
+        if (kind == CMD_STOP) {
+          if (lane == 0) sh_state = stop;
+          m = 0;
+          break;
+        }
         uint32_t s = kNoSlot;
         bool valid = false;
         if (kind == CMD_ONE) { s = a; valid = lane == 0; }
@@ -255,17 +416,20 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
         if (valid) bulk_g2s(smem_u32(rows_s + (size_t)pos * p.rs), p.rows + (size_t)s * p.row_stride, p.row_stride, bar);
         if (m) break;
       }
-      if (lane == 0) { sh_cnt = m; prev_m = m; }
+      if (lane == 0) sh_cnt = m;
+      prev_m = m;
     }
     __syncthreads();
     if (sh_state) break;
     const uint32_t m = sh_cnt;
     // ---- all warps: exact distances of the m gathered rows -> nb_dist[]
+    const uint32_t j = warp * 8 + (lane >> 2), h = lane & 3;
+    const bool valid = j < m;
+    float rn = 0.0f;
+    if (METRIC == COLTT_COSINE && valid && h == 0) rn = p.row_norm2[nb_slot[j]];   // in flight while the rows land
     mbar_wait(bar, phase);
     phase ^= 1;
     if (warp * 8 < m) {
-      const uint32_t j = warp * 8 + (lane >> 2), h = lane & 3;
-      const bool valid = j < m;
       const uint8_t* rowp = rows_s + (size_t)(valid ? j : 0) * p.rs;
       float a0 = 0.0f, a1 = 0.0f;                 // AVX lanes 2h and 2h+1
 #pragma unroll 8
@@ -279,7 +443,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
           a0 = add_rn(a0, mul_rn(d0, d0)); a1 = add_rn(a1, mul_rn(d1, d1));
         }
       }
-      // ((l0+l1)+(l2+l3)) + ((l4+l5)+(l6+l7)): the reduction tree of flat_scan.cu (avx.cpp:26-31,66-73)
+      // ((l0+l1)+(l2+l3)) + ((l4+l5)+(l6+l7)): the reduction tree of flat_scan.cu (avx.cpp:4-9)
       float t = add_rn(a0, a1);
       t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
       float tot = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
@@ -288,21 +452,42 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
         if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
         else { const float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
       }
-      if (valid && h == 0)
-        nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, p.row_norm2[nb_slot[j]]) : sqrt_via_f64(tot);
+      if (valid && h == 0) nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, rn) : sqrt_via_f64(tot);
     }
     __syncthreads();
   }
   // ---- selectNeighbors(k) (hnsw.go:391-397) and the back-to-front fill (:268-275)
-  if (tid == 0) {
-    if (sh_state == 2) {
-      p.out_counts[q] = 0;
-      atomicAdd(p.stats + 2, 1ull);
-    } else {
+  if (warp == 0) {
+    const uint32_t state = sh_state;
+    Hit* out = p.out + (size_t)q * p.out_stride;
+    if (state != STOP_DONE) {
+      if (lane == 0) {
+        p.out_counts[q] = state == STOP_TIE ? -1 : 0;
+        atomicAdd(p.stats + (state == STOP_TIE ? 3 : 2), 1ull);
+      }
+      return;                                      // the re-run counts this query's evaluations
+    }
+    bool done = false;
+    if constexpr (R > 0) {
+      if (!literal) {
+        done = true;
+        const uint32_t n_out = ws.n < p.k ? ws.n : p.k;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const uint32_t idx = lane * R + r;
+          if (idx < n_out) {
+            const uint32_t slot = ws.s[r] & ~WarpSorted<R>::kExpanded;
+            Hit h; h.id = p.ids[slot]; h.score = ws.p[r]; h.slot = slot;
+            out[idx] = h;
+          }
+        }
+        if (lane == 0) p.out_counts[q] = (int)n_out;
+      }
+    }
+    if (!done && lane == 0) {
       float tp; uint32_t ts;
       while (res.n > p.k) res.pop(tp, ts);
       const uint32_t n_out = res.n;
-      Hit* out = p.out + (size_t)q * p.out_stride;
       for (int i = (int)n_out - 1; i >= 0; i--) {
         res.pop(tp, ts);
         Hit h; h.id = p.ids[ts]; h.score = tp; h.slot = ts;
@@ -310,8 +495,11 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
       }
       p.out_counts[q] = (int)n_out;
     }
-    atomicAdd(p.stats + 0, evals);
-    atomicAdd(p.stats + 1, exps);
+    if (lane == 0) {
+      atomicAdd(p.stats + 0, evals);
+      atomicAdd(p.stats + 1, exps);
+      if (R > 0 && literal) atomicAdd(p.stats + 3, 1ull);
+    }
   }
 }
 
@@ -386,7 +574,7 @@ int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   COLTT_CUDA(cudaGetDeviceProperties(&pr, device));
   h->n_sms = pr.multiProcessorCount;
   COLTT_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 3 * sizeof(unsigned long long)));
+  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 4 * sizeof(unsigned long long)));
   std::vector<uint64_t> ids;
   std::vector<int32_t> levels;
   std::vector<uint8_t> rows;
@@ -461,6 +649,23 @@ int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   return COLTT_OK;
 }
 
+
+static int launch_hnsw_search(int metric, int R, const HnswParams& p, unsigned n_ctas, size_t smem, cudaStream_t st) {
+#define COLTT_HNSW_CASE(M, RR)                                                               \
+  if (metric == M && R == RR) {                                                              \
+    int arc = kernel_attrs(hnsw_search_kernel<M, RR>, smem);                                 \
+    if (arc) return arc;                                                                     \
+    hnsw_search_kernel<M, RR><<<n_ctas, kHnswThreads, smem, st>>>(p);                        \
+  } else
+  COLTT_HNSW_CASE(COLTT_COSINE, 0) COLTT_HNSW_CASE(COLTT_COSINE, 2) COLTT_HNSW_CASE(COLTT_COSINE, 4) COLTT_HNSW_CASE(COLTT_COSINE, 8)
+  COLTT_HNSW_CASE(COLTT_EUCLIDEAN, 0) COLTT_HNSW_CASE(COLTT_EUCLIDEAN, 2) COLTT_HNSW_CASE(COLTT_EUCLIDEAN, 4) COLTT_HNSW_CASE(COLTT_EUCLIDEAN, 8)
+  return fail(COLTT_ERR_UNSUPPORTED, "no HNSW kernel for this metric / result-set width");
+#undef COLTT_HNSW_CASE
+  count_launch();
+  COLTT_CUDA(cudaGetLastError());
+  return COLTT_OK;
+}
+
 static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_in, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
   if (nq == 0) return COLTT_OK;
   if (!queries || !out_ids || !out_scores || !out_counts) return fail(COLTT_ERR_INVALID, "null argument");
@@ -477,15 +682,19 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   // than SMs (the walk is latency bound: a second resident query hides the first one's serial heap work).
   const uint32_t rs = (h->row_stride + 127) / 128 * 128 + 32;
   const size_t sm_total = 227 * 1024;
-  uint32_t cand_cap = kCandCapMin;
-  while (cand_cap < 8 * ef && cand_cap < kCandCapMax) cand_cap *= 2;
+  // R > 0: result set in warp registers (ef <= 32*R); R == 0: literal Go-heap replay in shared memory (large ef, and
+  // the re-run of queries whose walk met equal priorities).
   static const int env_chunk = getenv("COLTT_HNSW_CHUNK") ? atoi(getenv("COLTT_HNSW_CHUNK")) : 0;
   static const int env_ctas = getenv("COLTT_HNSW_CTAS") ? atoi(getenv("COLTT_HNSW_CTAS")) : 0;
+  static const int env_literal = getenv("COLTT_HNSW_LITERAL") ? atoi(getenv("COLTT_HNSW_LITERAL")) : 0;
+  int R = env_literal ? 0 : ef <= 64 ? 2 : ef <= 128 ? 4 : ef <= 256 ? 8 : 0;
+  uint32_t cand_cap = kCandCapMin;
+  while (cand_cap < 8 * ef && cand_cap < kCandCapMax) cand_cap *= 2;
   uint32_t chunk_rows = 0;
   size_t smem = 0;
-  auto plan = [&](uint32_t cap) -> bool {
+  auto plan = [&](uint32_t cap, size_t n_ctas) -> bool {
     const size_t fixed = (size_t)q_stride * 4 + (size_t)cap * 8 + (size_t)(ef + 1) * 8 + kHnswChunkMax * 8;
-    int ctas = env_ctas > 0 ? env_ctas : (nq > (size_t)h->n_sms ? 2 : 1);
+    int ctas = env_ctas > 0 ? env_ctas : (n_ctas > (size_t)h->n_sms ? 2 : 1);
     for (; ctas >= 1; ctas--) {
       const size_t budget = sm_total / ctas - 1024 - 128;     // 1 KB reserved per CTA + the static shared variables
       if (budget <= fixed) continue;
@@ -499,7 +708,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
     }
     return false;
   };
-  if (!plan(cand_cap)) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
+  if (!plan(cand_cap, nq)) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
   const uint32_t words = (h->n + 31) / 32;
   cudaStream_t st = h->stream;
   int rc;
@@ -521,30 +730,52 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   p.ef = ef; p.visited = (uint32_t*)h->visited.p; p.visited_words = words; p.out = (Hit*)h->out.p; p.out_counts = (int*)h->counts.p;
   p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = rs;
   std::vector<Hit> hits(nq * (size_t)k);
-  unsigned long long stats[3];
+  unsigned long long stats[4], evals = 0, exps = 0, ties = 0;
+  std::vector<uint32_t> redo;                     // queries to run again (empty = the whole batch)
   for (;;) {
-    p.chunk_rows = chunk_rows; p.cand_cap = cand_cap;
-    COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
-    COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), st));
-    if (h->metric == COLTT_COSINE) {
-      { int arc = kernel_attrs(hnsw_search_kernel<COLTT_COSINE>, smem); if (arc) return arc; }
-      hnsw_search_kernel<COLTT_COSINE><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
-    } else {
-      { int arc = kernel_attrs(hnsw_search_kernel<COLTT_EUCLIDEAN>, smem); if (arc) return arc; }
-      hnsw_search_kernel<COLTT_EUCLIDEAN><<<(unsigned)nq, kHnswThreads, smem, st>>>(p);
+    const size_t n_ctas = redo.empty() ? nq : redo.size();
+    p.chunk_rows = chunk_rows; p.cand_cap = cand_cap; p.log_cap = 2 * cand_cap;
+    if ((rc = h->qlog.ensure(R > 0 ? nq * (size_t)p.log_cap * 8 : 8))) return rc;
+    p.qlog = (uint2*)h->qlog.p;
+    p.q_map = nullptr;
+    if (!redo.empty()) {
+      if ((rc = h->q_map.ensure(redo.size() * 4))) return rc;
+      COLTT_CUDA(cudaMemcpyAsync(h->q_map.p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+      p.q_map = (const uint32_t*)h->q_map.p;
     }
-    count_launch();
-    COLTT_CUDA(cudaGetLastError());
+    COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
+    COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), st));
+    if ((rc = launch_hnsw_search(h->metric, R, p, (unsigned)n_ctas, smem, st))) return rc;
     COLTT_CUDA(cudaMemcpyAsync(hits.data(), h->out.p, hits.size() * sizeof(Hit), cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaMemcpyAsync(out_counts, h->counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaMemcpyAsync(stats, h->d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaStreamSynchronize(st));
+    evals += stats[0];
+    exps += stats[1];
+    static const bool dbg = getenv("COLTT_HNSW_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[hnsw] pass: ctas=%zu R=%d chunk=%u smem=%zu cap=%u overflows=%llu ties=%llu\n", n_ctas, R, chunk_rows, smem, cand_cap, stats[2], stats[3]);
+    ties += stats[3];
     if (!stats[2]) break;
-    // a candidate queue outgrew its shared-memory heap: run the batch again with the largest one
-    if (cand_cap >= kCandCapMax || !plan(kCandCapMax))
+    // a candidate queue (or the fast path's operation log) outgrew its capacity: those queries run again on the
+    // literal heaps with the largest one
+    if ((R == 0 && cand_cap >= kCandCapMax) || !plan(kCandCapMax, stats[2]))
       return fail(COLTT_ERR_UNSUPPORTED, "HNSW candidate queue overflowed its shared-memory capacity (ef too large)");
+    R = 0;
     cand_cap = kCandCapMax;
+    std::vector<uint32_t> again;
+    if (redo.empty()) {
+      for (size_t q = 0; q < nq; q++)
+        if (out_counts[q] <= 0) again.push_back((uint32_t)q);
+    } else {
+      for (uint32_t q : redo)
+        if (out_counts[q] <= 0) again.push_back(q);
+    }
+    if (again.empty()) return fail(COLTT_ERR_UNSUPPORTED, "HNSW re-run bookkeeping lost its queries");
+    redo.swap(again);
   }
+  stats[0] = evals;
+  stats[1] = exps;
+  h->last_ties = ties;
   h->last_evals = stats[0];
   h->last_exp = stats[1];
   for (size_t q = 0; q < nq; q++)

@@ -24,8 +24,8 @@ struct Hnsw {
   unsigned long long* d_stats = nullptr;
   cudaStream_t stream = nullptr;
   std::mutex mu;
-  DeviceBuf q_in, q_deq, q_n2, visited, out, counts;
-  uint64_t last_evals = 0, last_exp = 0;
+  DeviceBuf q_in, q_deq, q_n2, visited, out, counts, q_map, qlog;
+  uint64_t last_evals = 0, last_exp = 0, last_ties = 0;   // last search: distance evaluations, expansions, queries that met a tie
   uint64_t build_fast_queries = 0, build_fast_fallbacks = 0;   // bulk build: searches served by the FAST path / re-run exactly
   double build_ms[4] = {0, 0, 0, 0};            // bulk build: ingest, kNN search, exact edge distances, host graph assembly
   ~Hnsw() {

@@ -31,7 +31,7 @@ def test_hnsw_search_matches_oracle(cb, oracle, metric, n, d):
     g = cb.Hnsw.Load(h.commit())
     assert g.Len() == len(h) == n
     qs = normal(12, d, QUERY_SEED + d)
-    for ef, k in [(0, 10), (64, 10), (128, 1), (40, 40)]:
+    for ef, k in [(0, 10), (64, 10), (128, 1), (40, 40), (200, 10), (300, 5)]:
         if ef:
             h.set_ef(ef)
         else:
