@@ -161,6 +161,20 @@ struct WarpSorted {
     for (int r = 1; r < R; r++) v = lane * R + r < n ? p[r] : v;
     return __shfl_sync(0xffffffffu, v, ((n - 1) / R) & 31);
   }
+  // slot of the smallest unexpanded member (not marked), or kNoSlot
+  __device__ __forceinline__ uint32_t peek(uint32_t lane) const {
+    bool found = false;
+    uint32_t vs = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const bool c = !found && !(s[r] & kExpanded) && lane * R + r < n;
+      vs = c ? s[r] : vs;
+      found |= c;
+    }
+    const uint32_t have = __ballot_sync(0xffffffffu, found);
+    if (!have) return kNoSlot;
+    return __shfl_sync(0xffffffffu, vs, __ffs(have) - 1);
+  }
   // smallest unexpanded member -> (priority, slot), marked expanded; false if there is none
   __device__ __forceinline__ bool next(float& cp, uint32_t& cs, uint32_t lane) {
     bool found = false, mark[R > 0 ? R : 1];
@@ -235,6 +249,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
   uint32_t ep = p.entry, best = kNoSlot, c0 = 0, e1 = 0, prev_m = 0, cur = 0, chunk = 0;
   bool need_list = true, chunk_more = false, started = false;
   float min_d = 0.0f, lb = 0.0f;
+  // speculation: neighbour list and visited words of the likeliest next candidate, fetched under the current pass
+  uint32_t spec_cur = kNoSlot, spec_s = kNoSlot, spec_w = 0;
 
   // lane 0: one accepted neighbour through the reference's two heaps (hnsw.go:375-381); false = cand is full
   auto heap_accept = [&](float d, uint32_t slot) -> bool {
@@ -298,7 +314,10 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
                 const uint32_t sl = __shfl_sync(0xffffffffu, sv, i);
                 if (log_n >= p.log_cap) { stop = STOP_OVERFLOW; break; }
                 if (((nan >> i) & 1u) || ws.insert(d, sl, p.ef, lane)) { i0 = i; go_literal(); break; }
-                if (lane == 0) qlog[log_n] = make_uint2(__float_as_uint(d), sl);
+                if (lane == 0) {
+                  qlog[log_n] = make_uint2(__float_as_uint(d), sl);
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(p.nbr0 + (size_t)sl * p.nbr0_stride));
+                }
                 log_n++;
                 if (ws.n >= p.ef) todo &= lt;
               }
@@ -396,15 +415,23 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
         } else {
           // visited test-and-set for the whole chunk (:368-371), in parallel; the ballot below keeps list order
           const uint32_t off = b * cw + lane;
-          if (lane < cw && off < p.nbr0_stride) s = p.nbr0[(size_t)a * p.nbr0_stride + off];
+          const bool hit = a == spec_cur && b == 0;           // list and visited words are already here
+          if (hit) s = spec_s;
+          else if (lane < cw && off < p.nbr0_stride) s = p.nbr0[(size_t)a * p.nbr0_stride + off];
           const bool listed = s != kNoSlot;
           const uint32_t lm = __ballot_sync(0xffffffffu, listed);
           if (listed) {
-            const uint32_t old = atomicOr(vis + (s >> 5), 1u << (s & 31));
-            valid = !((old >> (s & 31)) & 1u);
+            if (hit) {                                        // nothing touched this query's bitmap since spec_w was read
+              valid = !((spec_w >> (s & 31)) & 1u);
+              if (valid) atomicOr(vis + (s >> 5), 1u << (s & 31));
+            } else {
+              const uint32_t old = atomicOr(vis + (s >> 5), 1u << (s & 31));
+              valid = !((old >> (s & 31)) & 1u);
+            }
           }
           chunk_more = (uint32_t)__popc(lm) == cw && (b + 1) * cw < p.nbr0_stride;
           chunk = b + 1;
+          spec_cur = kNoSlot;                                 // the bitmap just changed: spec_w is stale from here on
         }
         // compact the valid slots into nb_slot[] and start their row copies
         const uint32_t mask = __ballot_sync(0xffffffffu, valid);
@@ -418,6 +445,14 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
       }
       if (lane == 0) sh_cnt = m;
       prev_m = m;
+      spec_cur = kNoSlot;
+      if constexpr (R > 0) {
+        if (m && !literal && stage == ST_SEARCH && !chunk_more && p.nbr0_stride <= cw) {
+          spec_cur = ws.peek(lane) & ~WarpSorted<R>::kExpanded;
+          if (spec_cur != (kNoSlot & ~WarpSorted<R>::kExpanded)) spec_s = lane < p.nbr0_stride ? p.nbr0[(size_t)spec_cur * p.nbr0_stride + lane] : kNoSlot;
+          else spec_cur = kNoSlot;
+        }
+      }
     }
     __syncthreads();
     if (sh_state) break;
@@ -454,6 +489,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
       }
       if (valid && h == 0) nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, rn) : sqrt_via_f64(tot);
     }
+    if (warp == 0 && spec_cur != kNoSlot) spec_w = spec_s != kNoSlot ? __ldcg(vis + (spec_s >> 5)) : 0u;
     __syncthreads();
   }
   // ---- selectNeighbors(k) (hnsw.go:391-397) and the back-to-front fill (:268-275)

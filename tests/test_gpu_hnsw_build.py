@@ -208,3 +208,29 @@ def test_bulk_build_caller_levels_and_small_cases(cb, oracle):
         cb.Hnsw.Build(np.array([5, 5], np.uint64), vecs[:2])
     for x in (g0, g1, g2):
         x.close()
+
+
+def test_large_graph_search_matches_oracle(cb, oracle):
+    """A graph large enough for long walks (expansions whose neighbours are all visited, distance ties between
+    distinct vertices, several CTAs per SM): bulk-built on the GPU, committed, and searched by the oracle's literal
+    restatement of hnsw.go from the same blob — ids, score bits and the evaluation / expansion counts must agree."""
+    n, d, lat = 150_000, 48, 6
+    g0 = np.random.Generator(np.random.Philox(77))
+    proj = g0.standard_normal((lat, d), dtype=np.float32)
+    vecs = (g0.standard_normal((n, lat), dtype=np.float32) @ proj + np.float32(0.05) * g0.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    ids = sparse_ids(n, 5)
+    g = cb.Hnsw.Build(ids, vecs, metric=0, m=16, seed=3)
+    blob = g.Commit()
+    h = oracle.Hnsw.load(blob)
+    qs = (g0.standard_normal((320, lat), dtype=np.float32) @ proj).astype(np.float32)
+    for ef, k in [(128, 10), (200, 10), (48, 5)]:
+        h.set_ef(ef)
+        h.stats(reset=True)
+        want = [h.search(q, k) for q in qs]
+        evals, exps = h.stats(reset=True)
+        gi, gs, gc = g.BatchSearch(qs, k, ef)
+        for j in range(len(qs)):
+            assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], want[j][0], want[j][1], f"large ef={ef} q{j}")
+        st = g.last_stats()
+        assert st["dist_evals"] == evals and st["expansions"] == exps, (ef, st, evals, exps)
+    g.close()
