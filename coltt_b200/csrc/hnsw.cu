@@ -53,7 +53,7 @@ struct HnswParams {
   Hit* out; int* out_counts; uint32_t out_stride;
   const uint32_t* q_map;                        // CTA -> query (re-runs of a subset), or null
   uint2* qlog; uint32_t log_cap;                // [nq][log_cap] queue operations of the fast path (replayed after a tie)
-  unsigned long long* stats;                    // [0] distance evaluations, [1] expansions, [2] queue overflows, [3] ties
+  unsigned long long* stats;                    // [0] distance evaluations, [1] expansions, [2] queue overflows, [3] queries finished on the literal heaps, [4..7] H1 / H2 / H3 / NaN events
 };
 
 // Go container/heap (src/container/heap/heap.go: up / down), keyed on priority only —
@@ -104,34 +104,54 @@ struct SmemHeap {
 };
 
 // The result set of searchLevel as a sorted array spread over warp 0's registers (lane L owns entries
-// [L*R, L*R+R), ascending priority, +inf padding), used while every priority in it is distinct.  Then the
-// reference's two heaps reduce to ordered-set semantics: resultVertices = the ef smallest distances seen, and the
-// candidates that can still be expanded are exactly the unexpanded members of that set — a candidate evicted from
-// it has priority > lowerBound for the rest of the walk (lowerBound never grows once the set is full), so popping
-// it can only end the loop (hnsw.go:359-361), which "no unexpanded member left" does as well.  The first equal
-// pair of priorities (or a NaN) makes Go's heap layout matter: insert() reports it before changing anything, and
-// the walk continues on the literal heaps, rebuilt by replaying the log of queue operations made so far.
+// [L*R, L*R+R), ascending priority, +inf padding).  While Go's heap layout cannot matter, the reference's two
+// heaps reduce to ordered-set semantics: resultVertices = the ef smallest distances seen, and the candidates
+// that can still be expanded are exactly the unexpanded members of that set — a candidate evicted from it has
+// priority > lowerBound for the rest of the walk (lowerBound never grows once the set is full), so popping it can
+// only end the loop (hnsw.go:359-361), which "no unexpanded member left" does as well.  The layout matters only
+// where equal priorities meet an operation that has to choose between them; every queue operation is logged, so
+// the literal heaps can be rebuilt at that point (see the kernel):
+//   H1  candidateVertices.Pop() with two unexpanded members at the minimum  -> the literal candidate heap decides
+//   H2  resultVertices.Pop() with the two largest members equal, or a NaN   -> the walk continues on the literal heaps
+//   H3  equal priorities among the first k+1 members at the end             -> the literal result heap orders them
 template <int R>
 struct WarpSorted {
   float p[R > 0 ? R : 1];
   uint32_t s[R > 0 ? R : 1];                      // slot; bit 31 = already expanded
   uint32_t n;
+  bool has_tie;                                   // an equal pair was inserted at some point (sticky)
   static constexpr uint32_t kExpanded = 0x80000000u;
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int r = 0; r < R; r++) { p[r] = __int_as_float(0x7f800000); s[r] = kNoSlot; }
     n = 0;
+    has_tie = false;
   }
-  // true = a tie (or NaN): nothing was changed, the caller must leave the fast path
-  __device__ __forceinline__ bool insert(float d, uint32_t slot, uint32_t ef, uint32_t lane) {
+  // entry n-1-back (back = 0: the largest member, resultVertices.Peek(); back = 1: the second largest)
+  __device__ __forceinline__ float from_top(uint32_t back, uint32_t lane) const {
+    const uint32_t lim = n - back;                // entries [0, lim) are candidates; the last of them is wanted
+    float v = p[0];
+#pragma unroll
+    for (int r = 1; r < R; r++) v = lane * R + r < lim ? p[r] : v;
+    return __shfl_sync(0xffffffffu, v, ((lim - 1) / R) & 31);
+  }
+  __device__ __forceinline__ float top(uint32_t lane) const { return from_top(0, lane); }
+  // false = H2 (or NaN): nothing was changed, the caller must continue on the literal heaps
+  __device__ __forceinline__ bool insert(float d, uint32_t slot, uint32_t ef, uint32_t lane, bool check = true) {
     uint32_t cnt = 0;
-    bool eq = d != d;
+    bool eq = false;
 #pragma unroll
     for (int r = 0; r < R; r++) { cnt += p[r] < d ? 1u : 0u; eq |= p[r] == d; }
     const float up_p = __shfl_up_sync(0xffffffffu, p[R - 1], 1);
     const uint32_t up_s = __shfl_up_sync(0xffffffffu, s[R - 1], 1);
     const uint32_t below = __ballot_sync(0xffffffffu, cnt == (uint32_t)R);   // lanes entirely below d: 0 .. full-1
-    if (__any_sync(0xffffffffu, eq)) return true;
+    if (d != d) return false;
+    if (__any_sync(0xffffffffu, eq)) has_tie = true;
+    if (check && has_tie && n >= ef) {            // this insert evicts: are the two largest afterwards equal?
+      const float m1 = top(lane);
+      if (d == m1) return false;
+      if (n >= 2 && from_top(1, lane) == m1) return false;
+    }
     const uint32_t full = __popc(below);
     if (lane > full) {                            // everything moves up by one
 #pragma unroll
@@ -152,32 +172,31 @@ struct WarpSorted {
       for (int r = 0; r < R; r++)
         if (lane * R + r >= ef) { p[r] = __int_as_float(0x7f800000); s[r] = kNoSlot; }
     }
-    return false;
+    return true;
   }
-  // resultVertices.Peek(): the largest member = the last valid entry of lane (n-1)/R
-  __device__ __forceinline__ float top(uint32_t lane) const {
-    float v = p[0];
+  // drop the member with this slot (the literal result heap evicted it)
+  __device__ __forceinline__ void remove(uint32_t slot, uint32_t lane) {
+    uint32_t hit = R;
 #pragma unroll
-    for (int r = 1; r < R; r++) v = lane * R + r < n ? p[r] : v;
-    return __shfl_sync(0xffffffffu, v, ((n - 1) / R) & 31);
-  }
-  // slot of the smallest unexpanded member (not marked), or kNoSlot
-  __device__ __forceinline__ uint32_t peek(uint32_t lane) const {
-    bool found = false;
-    uint32_t vs = 0;
+    for (int r = 0; r < R; r++)
+      if ((s[r] & ~kExpanded) == slot && lane * R + r < n) hit = r;
+    const uint32_t have = __ballot_sync(0xffffffffu, hit < (uint32_t)R);
+    float dn_p = __shfl_down_sync(0xffffffffu, p[0], 1);
+    uint32_t dn_s = __shfl_down_sync(0xffffffffu, s[0], 1);
+    if (!have) return;
+    if (lane == 31) { dn_p = __int_as_float(0x7f800000); dn_s = kNoSlot; }
+    const uint32_t at = __ffs(have) - 1;
+    if (lane >= at) {
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      const bool c = !found && !(s[r] & kExpanded) && lane * R + r < n;
-      vs = c ? s[r] : vs;
-      found |= c;
+      for (int r = 0; r < R - 1; r++)
+        if (lane > at || (uint32_t)r >= hit) { p[r] = p[r + 1]; s[r] = s[r + 1]; }
+      p[R - 1] = dn_p; s[R - 1] = dn_s;
     }
-    const uint32_t have = __ballot_sync(0xffffffffu, found);
-    if (!have) return kNoSlot;
-    return __shfl_sync(0xffffffffu, vs, __ffs(have) - 1);
+    n--;
   }
-  // smallest unexpanded member -> (priority, slot), marked expanded; false if there is none
-  __device__ __forceinline__ bool next(float& cp, uint32_t& cs, uint32_t lane) {
-    bool found = false, mark[R > 0 ? R : 1];
+  // smallest unexpanded member -> (priority, slot), not marked; false if there is none
+  __device__ __forceinline__ bool find(float& cp, uint32_t& cs, uint32_t lane) const {
+    bool found = false;
     float vp = 0.0f;
     uint32_t vs = 0;
 #pragma unroll
@@ -185,7 +204,6 @@ struct WarpSorted {
       const bool c = !found && !(s[r] & kExpanded) && lane * R + r < n;
       vp = c ? p[r] : vp;
       vs = c ? s[r] : vs;
-      mark[r] = c;
       found |= c;
     }
     const uint32_t have = __ballot_sync(0xffffffffu, found);
@@ -193,10 +211,32 @@ struct WarpSorted {
     const uint32_t src = __ffs(have) - 1;
     cp = __shfl_sync(0xffffffffu, vp, src);
     cs = __shfl_sync(0xffffffffu, vs, src);
+    return true;
+  }
+  // H1: more than one unexpanded member has priority cp
+  __device__ __forceinline__ bool several(float cp, uint32_t lane) const {
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) c += (!(s[r] & kExpanded) && lane * R + r < n && p[r] == cp) ? 1u : 0u;
+    const uint32_t some = __ballot_sync(0xffffffffu, c > 0);
+    return __popc(some) > 1 || __any_sync(0xffffffffu, c > 1);
+  }
+  __device__ __forceinline__ void mark(uint32_t slot, uint32_t lane) {
 #pragma unroll
     for (int r = 0; r < R; r++)
-      if (mark[r] && lane == src) s[r] |= kExpanded;
-    return true;
+      if (s[r] == slot && lane * R + r < n) s[r] |= kExpanded;
+  }
+  // H3: equal neighbours among the first min(k+1, n) members
+  __device__ __forceinline__ bool head_ties(uint32_t k, uint32_t lane) const {
+    const uint32_t lim = k + 1 < n ? k + 1 : n;
+    const float nxt0 = __shfl_down_sync(0xffffffffu, p[0], 1);
+    bool t = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const float nx = r + 1 < R ? p[r + 1 < R ? r + 1 : 0] : nxt0;
+      t |= lane * R + r + 1 < lim && p[r] == nx;
+    }
+    return __any_sync(0xffffffffu, t);
   }
 };
 
@@ -252,6 +292,13 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
   // speculation: neighbour list and visited words of the likeliest next candidate, fetched under the current pass
   uint32_t spec_cur = kNoSlot, spec_s = kNoSlot, spec_w = 0;
 
+  // lane 0: log records [0, cand_pos) / [0, res_pos) are in the literal candidate / result heap (brought up to date
+  // only when Go's layout has to decide something)
+  uint32_t cand_pos = 0, res_pos = 0;
+  // an H2 eviction leaves a candidate outside the result set whose priority equals the largest member's: while that
+  // holds it can still be popped and expanded (hnsw.go:359 tests `>`), so the literal candidate heap picks
+  bool haz_set = false;
+  float haz_x = 0.0f;
   // lane 0: one accepted neighbour through the reference's two heaps (hnsw.go:375-381); false = cand is full
   auto heap_accept = [&](float d, uint32_t slot) -> bool {
     if (cand.n >= p.cand_cap) return false;
@@ -260,19 +307,40 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
     if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
     return true;
   };
-  // leave the fast path: lane 0 rebuilds Go's heaps by replaying the logged pushes / pops (next record prefetched)
-  auto go_literal = [&]() {
-    if (lane == 0 && log_n) {
-      uint2 e = qlog[0];
-      for (uint32_t i = 0; i < log_n; i++) {
-        const uint2 nx = i + 1 < log_n ? qlog[i + 1] : e;
-        if (e.y == kNoSlot) { float tp; uint32_t ts; cand.pop(tp, ts); }
-        else heap_accept(__uint_as_float(e.x), e.y);
-        e = nx;
+  // lane 0: replay log records [from, log_n) into Go's heaps (next record prefetched); false = cand is full
+  auto replay = [&](uint32_t from, bool do_cand, bool do_res) -> bool {
+    if (from >= log_n) return true;
+    uint2 e = qlog[from];
+    for (uint32_t i = from; i < log_n; i++) {
+      const uint2 nx = i + 1 < log_n ? qlog[i + 1] : e;
+      if (e.y == kNoSlot) {
+        if (do_cand) { float tp; uint32_t ts; cand.pop(tp, ts); }
+      } else {
+        const float d = __uint_as_float(e.x);
+        if (do_cand) {
+          if (cand.n >= p.cand_cap) return false;
+          cand.push(d, e.y);
+        }
+        if (do_res) {
+          res.push(d, e.y);
+          if (res.n > p.ef) { float tp; uint32_t ts; res.pop(tp, ts); }
+        }
       }
+      e = nx;
     }
-    __syncwarp();
+    return true;
+  };
+  // leave the fast path for good: both literal heaps brought up to date; false = cand is full
+  auto go_literal = [&]() -> bool {
+    uint32_t ok = 1;
+    if (lane == 0) {
+      replay(res_pos, false, true);
+      ok = replay(cand_pos, true, false) ? 1u : 0u;
+      cand_pos = res_pos = log_n;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
     literal = true;
+    return ok != 0;
   };
 
   for (;;) {
@@ -303,8 +371,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
             if (!literal) {
               const uint32_t all = prev_m >= 32 ? 0xffffffffu : (1u << prev_m) - 1u;
               const uint32_t lt = __ballot_sync(0xffffffffu, lane < prev_m && dv < lb) ;
-              const uint32_t nan = __ballot_sync(0xffffffffu, lane < prev_m && dv != dv);
-              // (:374) `distance < lowerBound || len < ef`, entries in list order; NaN goes the literal way
+              // (:374) `distance < lowerBound || len < ef`, entries in list order
               uint32_t todo = (stage == ST_ENTRY2 || ws.n < p.ef) ? all : lt;
               i0 = prev_m;
               while (todo) {
@@ -313,7 +380,30 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
                 const float d = __shfl_sync(0xffffffffu, dv, i);
                 const uint32_t sl = __shfl_sync(0xffffffffu, sv, i);
                 if (log_n >= p.log_cap) { stop = STOP_OVERFLOW; break; }
-                if (((nan >> i) & 1u) || ws.insert(d, sl, p.ef, lane)) { i0 = i; go_literal(); break; }
+                if (!ws.insert(d, sl, p.ef, lane)) {
+                  if (lane == 0) atomicAdd(p.stats + (d != d ? 7 : 5), 1ull);
+                  if (d != d) {                               // NaN: this and the remaining entries go the literal way
+                    i0 = i;
+                    if (!go_literal()) stop = STOP_OVERFLOW;
+                    break;
+                  }
+                  // H2: the literal result heap, brought up to date, takes the push and decides the eviction
+                  uint32_t ts = 0;
+                  if (lane == 0) {
+                    replay(res_pos, false, true);
+                    res.push(d, sl);
+                    float tp;
+                    res.pop(tp, ts);
+                    res_pos = log_n + 1;                      // ... including the push logged below
+                  }
+                  ts = __shfl_sync(0xffffffffu, ts, 0);
+                  haz_x = ws.top(lane) > d ? ws.top(lane) : d;   // priority of the evicted member == the largest one left
+                  haz_set = true;
+                  if (ts != sl) {
+                    ws.remove(ts, lane);
+                    ws.insert(d, sl, p.ef, lane, false);
+                  }
+                }
                 if (lane == 0) {
                   qlog[log_n] = make_uint2(__float_as_uint(d), sl);
                   asm volatile("prefetch.global.L2 [%0];" ::"l"(p.nbr0 + (size_t)sl * p.nbr0_stride));
@@ -375,11 +465,33 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
                   picked = true;
                   float cp; uint32_t cs;
                   if (log_n >= p.log_cap) { stop = STOP_OVERFLOW; }
-                  else if (ws.next(cp, cs, lane)) {           // candidateVertices.Pop() (:355); cp <= lowerBound by construction
-                    lb = ws.top(lane);                        // resultVertices.Peek() (:357)
-                    cur = cs & ~WarpSorted<R>::kExpanded; kind = CMD_L0;
-                    if (lane == 0) qlog[log_n] = make_uint2(0u, kNoSlot);
-                    log_n++;
+                  else {
+                    // candidateVertices.Pop() (:355): the smallest unexpanded member — unless Go's layout has a say
+                    bool found = ws.find(cp, cs, lane);
+                    if (haz_set && ws.n && ws.top(lane) < haz_x) haz_set = false;
+                    const bool consult = found ? (ws.has_tie && (ws.several(cp, lane) || (haz_set && cp == haz_x))) : haz_set;
+                    if (consult) {                            // H1: the literal candidate heap, brought up to date, pops
+                      uint32_t ok = 1, any = 0;
+                      if (lane == 0) {
+                        atomicAdd(p.stats + 4, 1ull);
+                        ok = replay(cand_pos, true, false) ? 1u : 0u;
+                        if (ok && cand.n) { cand.pop(cp, cs); any = 1; }
+                        cand_pos = log_n + 1;                 // ... including the pop logged below
+                      }
+                      ok = __shfl_sync(0xffffffffu, ok, 0);
+                      any = __shfl_sync(0xffffffffu, any, 0);
+                      cp = __shfl_sync(0xffffffffu, cp, 0);
+                      cs = __shfl_sync(0xffffffffu, cs, 0);
+                      if (!ok) stop = STOP_OVERFLOW;
+                      found = any && !(cp > ws.top(lane));    // (:354), (:359-361)
+                    }
+                    if (found && stop == STOP_DONE) {
+                      ws.mark(cs, lane);
+                      lb = ws.top(lane);                      // resultVertices.Peek() (:357)
+                      cur = cs; kind = CMD_L0;
+                      if (lane == 0) qlog[log_n] = make_uint2(0u, kNoSlot);
+                      log_n++;
+                    }
                   }
                 }
               }
@@ -448,8 +560,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
       spec_cur = kNoSlot;
       if constexpr (R > 0) {
         if (m && !literal && stage == ST_SEARCH && !chunk_more && p.nbr0_stride <= cw) {
-          spec_cur = ws.peek(lane) & ~WarpSorted<R>::kExpanded;
-          if (spec_cur != (kNoSlot & ~WarpSorted<R>::kExpanded)) spec_s = lane < p.nbr0_stride ? p.nbr0[(size_t)spec_cur * p.nbr0_stride + lane] : kNoSlot;
+          float xp;
+          if (ws.find(xp, spec_cur, lane)) spec_s = lane < p.nbr0_stride ? p.nbr0[(size_t)spec_cur * p.nbr0_stride + lane] : kNoSlot;
           else spec_cur = kNoSlot;
         }
       }
@@ -505,6 +617,10 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
     }
     bool done = false;
     if constexpr (R > 0) {
+      if (!literal && ws.has_tie && ws.head_ties(p.k, lane)) {   // H3
+        if (lane == 0) { atomicAdd(p.stats + 6, 1ull); replay(res_pos, false, true); }   // the result heap alone is needed
+        literal = true;
+      }
       if (!literal) {
         done = true;
         const uint32_t n_out = ws.n < p.k ? ws.n : p.k;
@@ -610,7 +726,7 @@ int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
   COLTT_CUDA(cudaGetDeviceProperties(&pr, device));
   h->n_sms = pr.multiProcessorCount;
   COLTT_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 4 * sizeof(unsigned long long)));
+  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 8 * sizeof(unsigned long long)));
   std::vector<uint64_t> ids;
   std::vector<int32_t> levels;
   std::vector<uint8_t> rows;
@@ -766,7 +882,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   p.ef = ef; p.visited = (uint32_t*)h->visited.p; p.visited_words = words; p.out = (Hit*)h->out.p; p.out_counts = (int*)h->counts.p;
   p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = rs;
   std::vector<Hit> hits(nq * (size_t)k);
-  unsigned long long stats[4], evals = 0, exps = 0, ties = 0;
+  unsigned long long stats[8], evals = 0, exps = 0, ties = 0;
   std::vector<uint32_t> redo;                     // queries to run again (empty = the whole batch)
   for (;;) {
     const size_t n_ctas = redo.empty() ? nq : redo.size();
@@ -780,7 +896,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
       p.q_map = (const uint32_t*)h->q_map.p;
     }
     COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
-    COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), st));
+    COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), st));
     if ((rc = launch_hnsw_search(h->metric, R, p, (unsigned)n_ctas, smem, st))) return rc;
     COLTT_CUDA(cudaMemcpyAsync(hits.data(), h->out.p, hits.size() * sizeof(Hit), cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaMemcpyAsync(out_counts, h->counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
@@ -789,7 +905,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
     evals += stats[0];
     exps += stats[1];
     static const bool dbg = getenv("COLTT_HNSW_DEBUG") != nullptr;
-    if (dbg) fprintf(stderr, "[hnsw] pass: ctas=%zu R=%d chunk=%u smem=%zu cap=%u overflows=%llu ties=%llu\n", n_ctas, R, chunk_rows, smem, cand_cap, stats[2], stats[3]);
+    if (dbg) fprintf(stderr, "[hnsw] pass: ctas=%zu R=%d chunk=%u smem=%zu cap=%u overflows=%llu literal=%llu H1=%llu H2=%llu H3=%llu NaN=%llu\n", n_ctas, R, chunk_rows, smem, cand_cap, stats[2], stats[3], stats[4], stats[5], stats[6], stats[7]);
     ties += stats[3];
     if (!stats[2]) break;
     // a candidate queue (or the fast path's operation log) outgrew its capacity: those queries run again on the

@@ -248,7 +248,7 @@ static int hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids_in, c
   COLTT_CUDA(cudaGetDeviceProperties(&pr, cfg->device));
   h->n_sms = pr.multiProcessorCount;
   COLTT_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 4 * sizeof(unsigned long long)));
+  COLTT_CUDA(cudaMalloc((void**)&h->d_stats, 8 * sizeof(unsigned long long)));
   h->n = n;
   cudaStream_t st = h->stream;
   const double t0 = now_ms();

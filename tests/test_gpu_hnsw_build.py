@@ -218,11 +218,13 @@ def test_large_graph_search_matches_oracle(cb, oracle):
     g0 = np.random.Generator(np.random.Philox(77))
     proj = g0.standard_normal((lat, d), dtype=np.float32)
     vecs = (g0.standard_normal((n, lat), dtype=np.float32) @ proj + np.float32(0.05) * g0.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    vecs[100_000:104_000] = vecs[:4000]            # exact duplicates: equal priorities that meet pops and evictions
     ids = sparse_ids(n, 5)
     g = cb.Hnsw.Build(ids, vecs, metric=0, m=16, seed=3)
     blob = g.Commit()
     h = oracle.Hnsw.load(blob)
     qs = (g0.standard_normal((320, lat), dtype=np.float32) @ proj).astype(np.float32)
+    qs[:40] = vecs[:40]                            # queries next to duplicated vertices
     for ef, k in [(128, 10), (200, 10), (48, 5)]:
         h.set_ef(ef)
         h.stats(reset=True)
