@@ -14,3 +14,4 @@ from .edge import (  # noqa: F401
     SELECT_COMPAT, SELECT_NEAREST, MATH_EXACT, MATH_FAST, score_helper,
 )
 from .vectorindex import Hnsw  # noqa: F401,E402
+from .experimental import MultiVectorVertex, MultiVectorIndex, NearestNeighbor  # noqa: F401,E402

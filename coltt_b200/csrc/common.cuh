@@ -64,6 +64,14 @@ __device__ __forceinline__ float cosine_epilogue(float dot, float na, float nb) 
   return fabsf(sub_rn(1.0f, q));
 }
 
+// experimental/experimental_helper.go:134-139 scoreHelper (== edge/edge_helper.go:143-148): cosine ((2 - s) / 2) * 100 in
+// float32; euclidean float32(math.Max(0, float64(100 - s))) — NaN stays NaN, -0 becomes +0.
+__device__ __forceinline__ float score_helper(float s, int metric) {
+  if (metric == COLTT_COSINE) return mul_rn(__fdiv_rn(sub_rn(2.0f, s), 2.0f), 100.0f);
+  const float x = sub_rn(100.0f, s);
+  return x != x ? x : (x > 0.0f ? x : 0.0f);
+}
+
 // ---- codecs ----------------------------------------------------------------------------
 // pkg/compresshelper/float8.go:270-313 f32bitsToF8bits, literal.
 __host__ __device__ __forceinline__ uint8_t f8_compat_encode(uint32_t u32) {

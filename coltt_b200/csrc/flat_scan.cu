@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   for (uint32_t t = 0; t < S && t < n_work; t++) issue(t);
 
   uint32_t gi = 0, c = 0;
-  float nb_pref = 0.0f;
+  float nb_pref = 0.0f, macc_pref = 0.0f;
   uint32_t slot_pref = 0;
   for (uint32_t t = 0; t < n_work; t++) {
     if (c == 0) {
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
       if (item_p < p.n_items) {
         slot_pref = p.subset ? p.subset[item_p] : item_p;
         if (METRIC == COLTT_COSINE) nb_pref = p.row_norm2[slot_pref];
+        if (p.multi_acc && !p.multi_first) macc_pref = p.multi_acc[slot_pref];
       }
     }
     const uint32_t s = t % S;
@@ -181,7 +182,15 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
           if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
           else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
         }
-        const float score = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn_s[qi], nb) : sqrt_via_f64(tot);
+        float score = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn_s[qi], nb) : sqrt_via_f64(tot);
+        if (p.multi_acc) {
+          // score += scoreHelper(sim) * (float32(ratio) / 100), unfused, in request order (multi_vector_vertex.go:110-115)
+          score = add_rn(p.multi_first ? 0.0f : macc_pref, mul_rn(score_helper(score, METRIC), p.multi_w));
+          if (!p.multi_last) {
+            if (valid && g == 0) p.multi_acc[slot] = score;
+            continue;
+          }
+        }
         {   // another warp of this CTA may already hold K rows better than ours: adopt its bound
           const uint32_t shared_bits = cta_kth_s[qi];
           if (p.nearest ? shared_bits != 0xffffffffu : shared_bits != 0u) {

@@ -54,6 +54,11 @@ struct ScanParams {
   const uint32_t* n_active; // nullable: number of queries, on the device (overrides nq)
   uint32_t chunk_bytes;     // bytes of one row copied per pipeline stage (multiple of 128)
   uint32_t n_stages;        // stages per warp
+  // CFLAT multi-vector scoring (experimental/multi_vector_vertex.go:108-116): one launch per included field adds
+  // scoreHelper(distance) * weight to a per-slot running score; the launch of the last field selects on the sum.
+  float* multi_acc;         // nullable: [slot] running score (nq must be 1)
+  float multi_w;            // float32(ratio) / 100
+  int multi_first, multi_last;
 };
 struct ScanPlan {
   int grid_x, grid_y, warps, qt;

@@ -51,7 +51,7 @@ struct SearchCtx {
   cudaStream_t last_stream = nullptr;
   bool used = false, have_times = false, timed_last = false;
   float ms[4] = {0, 0, 0, 0};
-  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf;
+  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf, multi_acc;
   PinnedBuf h_q, h_out;
   GemmMapCache maps;                // TMA descriptors of the last FAST launch on this scratch
   ~SearchCtx();

@@ -162,6 +162,18 @@ COLTT_API int coltt_b200_store_import(coltt_store* s, const void* buf, size_t le
  * dim elements of 4/2/1 bytes.  For tests and for Hnsw-style Get(). */
 COLTT_API int coltt_b200_store_get_row(coltt_store* s, uint64_t id, void* out, size_t out_bytes);
 
+/* ---- experimental CFLAT multi-vector search ------------------------------------------------
+ * multiVectorVertex.MultiVertexSearch (experimental/multi_vector_vertex.go:85-137).  A CFLAT collection keeps one
+ * fp32 vector per named field and vertex; here every field is a coltt_store (quant NONE, same dim / metric / device)
+ * and the host applies each ChangedVertex / RemoveVertex to all of them in the same order, so they share the slot
+ * layout.  The caller passes the INCLUDED query fields in request order: fields[j] the store of that field,
+ * queries[j] its un-normalized fp32 query (dim floats, host), ratios[j] its Ratio (the Go side has already checked
+ * that they sum to 100, experimental_analyzer.go:143-154).  score = sum_j scoreHelper(distance_j) * (float32(ratio_j)
+ * / 100) in float32, unfused, in that order; the k largest scores come back in descending order (ties: id descending).
+ * out_ids / out_scores hold k entries, *out_count = min(k, vertices). */
+COLTT_API int coltt_b200_multi_search(coltt_store* const* fields, const float* const* queries, const int32_t* ratios,
+                                      int n_fields, int k, uint64_t* out_ids, float* out_scores, int32_t* out_count);
+
 /* ---- core/vectorindex HNSW ------------------------------------------------------------
  * Hnsw.Load (core/vectorindex/hnsw_commit.go:164-278): parses a Commit(header=true) blob
  * into a device-resident CSR graph + row matrix. */

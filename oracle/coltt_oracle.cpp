@@ -299,6 +299,60 @@ ORC_API float orc_score_helper(float score, int metric) {
   return (float)std::max(0.0, (double)(100 - score));
 }
 
+// experimental/multi_vector_vertex.go:60-67,85-137 MultiVertexSearch (CFLAT), restated over dense arrays:
+// fields[f] is the [n][dim] matrix of field f as handed to ChangedVertex (normalized here for cosine, :64-66);
+// q_field[j] / queries[j] / ratios[j] describe the INCLUDED query vectors in request order.  Per vertex
+//   score = 0; score += scoreHelper(Distance(vertex[field_j], Normalize(query_j))) * (float32(ratio_j) / 100)
+// (:108-116, float32, unfused), then the topK largest scores, descending (multi_priority_queue.go:47-75).  Among equal
+// scores the reference's order depends on Go's heap and map iteration; this checker uses score descending, NaN first,
+// then id descending (the reverse of the total order T used for FLAT).
+ORC_API int orc_multi_search(uint32_t dim, int metric, size_t n, const uint64_t* ids, int n_fields, const float* const* fields,
+                             int n_inc, const int* q_field, const float* const* queries, const int* ratios, int k,
+                             uint64_t* out_ids, float* out_scores) {
+  if (n_inc <= 0 || k <= 0) return 0;
+  std::vector<AlignedBuf> stored(n_fields);
+  std::vector<float*> sp(n_fields);
+  const size_t dpad = ((size_t)dim + 7) / 8 * 8;
+  for (int f = 0; f < n_fields; f++) {
+    sp[f] = stored[f].get(std::max<size_t>(n, 1) * dpad);
+    for (size_t r = 0; r < n; r++) {
+      float* dst = sp[f] + r * dpad;
+      if (metric == 0 /* cosine */) orc_normalize(fields[f] + r * (size_t)dim, dim, dst);
+      else std::memcpy(dst, fields[f] + r * (size_t)dim, 4 * (size_t)dim);
+    }
+  }
+  std::vector<AlignedBuf> qb(n_inc);
+  std::vector<float*> qp(n_inc);
+  for (int j = 0; j < n_inc; j++) {
+    qp[j] = qb[j].get(dpad);
+    if (metric == 0 /* cosine */) orc_normalize(queries[j], dim, qp[j]);          // :97-101
+    else std::memcpy(qp[j], queries[j], 4 * (size_t)dim);
+  }
+  struct MScore { float priority; uint64_t id; };
+  std::vector<MScore> all(n);
+  for (size_t r = 0; r < n; r++) {
+    float score = 0.0f;
+    for (int j = 0; j < n_inc; j++) {
+      const float* v = sp[q_field[j]] + r * dpad;
+      const float sim = metric == 0 /* cosine */ ? cosine_distance_impl(dim, v, qp[j], true) : euclid_distance_impl(dim, v, qp[j], true);
+      const float w = (float)(uint32_t)ratios[j] / 100;
+      const float term = orc_score_helper(sim, metric) * w;
+      score = score + term;
+    }
+    all[r] = MScore{score, ids[r]};
+  }
+  auto before = [](const MScore& a, const MScore& b) {                      // reverse of T
+    const bool an = a.priority != a.priority, bn = b.priority != b.priority;
+    if (an != bn) return an;
+    if (!an && a.priority != b.priority) return a.priority > b.priority;
+    return a.id > b.id;
+  };
+  const size_t kk = std::min<size_t>((size_t)k, n);
+  std::partial_sort(all.begin(), all.begin() + kk, all.end(), before);
+  for (size_t i = 0; i < kk; i++) { out_ids[i] = all[i].id; out_scores[i] = all[i].priority; }
+  return (int)kk;
+}
+
 // pkg/sharding/shard.go:34-41 ShardVertex: FNV-1a 64 over the LE bytes of id, mod c.
 ORC_API uint64_t orc_shard_vertex(uint64_t x, uint64_t c) {
   uint64_t h = 14695981039346656037ull;

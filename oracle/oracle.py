@@ -365,6 +365,29 @@ class Hnsw:
         return Hnsw(_handle=h)
 
 
+def multi_search(dim, metric, ids, fields, included, k):
+    """experimental MultiVertexSearch (CFLAT): `fields` = {name: [n, dim] fp32 as handed to ChangedVertex}, `included` =
+    [(name, query, ratio)] in request order -> (ids, scores), the k largest scores, descending."""
+    names = list(fields)
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    n = ids.size
+    mats = [np.ascontiguousarray(fields[f], dtype=np.float32).reshape(n, dim) for f in names]
+    fptr = (f32p * len(names))(*[m.ctypes.data_as(f32p) for m in mats])
+    qs = [np.ascontiguousarray(q, dtype=np.float32) for _, q, _ in included]
+    qptr = (f32p * len(qs))(*[q.ctypes.data_as(f32p) for q in qs])
+    qf = (C.c_int * len(qs))(*[names.index(f) for f, _, _ in included])
+    ratios = (C.c_int * len(qs))(*[int(r) for _, _, r in included])
+    out_ids = np.zeros(max(k, 1), dtype=np.uint64)
+    out_sc = np.zeros(max(k, 1), dtype=np.float32)
+    L = lib()
+    L.orc_multi_search.restype = C.c_int
+    L.orc_multi_search.argtypes = [C.c_uint32, C.c_int, C.c_size_t, u64p, C.c_int, C.POINTER(f32p), C.c_int, C.POINTER(C.c_int),
+                                   C.POINTER(f32p), C.POINTER(C.c_int), C.c_int, u64p, f32p]
+    cnt = L.orc_multi_search(dim, metric, n, ids.ctypes.data_as(u64p), len(names), fptr, len(qs), qf, qptr, ratios, k,
+                             out_ids.ctypes.data_as(u64p), out_sc.ctypes.data_as(f32p))
+    return out_ids[:cnt], out_sc[:cnt]
+
+
 def compute_recall(base_ids, ids, at):
     b, bp = _u64(base_ids)
     i, ip = _u64(ids)

@@ -286,3 +286,35 @@ def test_fp16_products_are_exact_in_fp32(oracle):
     # that store keeps the two-rounding path
     dec = np.asarray(oracle.f8_to_f32(np.arange(256, dtype=np.uint8)), np.float32)
     assert not np.array_equal(dec.astype(np.float16).astype(np.float32), dec)
+
+
+def test_cflat_multi_search_is_the_sequential_f32_weighted_sum(oracle):
+    """experimental MultiVertexSearch (multi_vector_vertex.go:85-137): score = sum over included fields, in request
+    order, of scoreHelper(Distance) * (float32(ratio)/100) in float32; topK largest, descending — against a numpy
+    float32 emulation of the Go expression, both metrics, an excluded field, and k > n."""
+    r = np.random.default_rng(1)
+    n, d = 400, 24
+    ids = np.arange(1, n + 1, dtype=np.uint64) * 7
+    F = {"title": r.standard_normal((n, d)).astype(np.float32), "body": r.standard_normal((n, d)).astype(np.float32),
+         "tags": r.standard_normal((n, d)).astype(np.float32)}
+    q = {f: r.standard_normal(d).astype(np.float32) for f in F}
+    f32 = np.float32
+    for metric in (0, 1):
+        for inc, k in (([("title", 30), ("body", 70)], 5), ([("tags", 100)], 7), ([("body", 20), ("tags", 45), ("title", 35)], n + 3)):
+            gi, gs = oracle.multi_search(d, metric, ids, F, [(f, q[f], ra) for f, ra in inc], k)
+            sc = []
+            for row in range(n):
+                s = f32(0)
+                for f, ra in inc:
+                    if metric == 0:
+                        dist = oracle.cosine_distance(oracle.normalize(F[f][row]), oracle.normalize(q[f]))
+                        h = f32(f32(f32(f32(2) - f32(dist)) / f32(2)) * f32(100))
+                    else:
+                        dist = oracle.euclidean_distance(F[f][row], q[f])
+                        h = f32(max(0.0, float(f32(f32(100) - f32(dist)))))
+                    s = f32(s + f32(h * f32(f32(ra) / f32(100))))
+                sc.append(s)
+            sc = np.array(sc, np.float32)
+            o = np.lexsort((-ids.astype(np.int64), -sc))[:k]
+            assert np.array_equal(gi, ids[o]) and gs.tobytes() == sc[o].tobytes(), (metric, inc)
+            assert np.all(np.diff(gs) <= 0)
