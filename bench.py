@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw"],
+                    help="flat = BASELINE configs[1] (the headline, default); hnsw = configs[2] (core/vectorindex HNSW, one GPU)")
+    ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--batch", type=int, default=256)
@@ -177,11 +180,108 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------- config 3 (HNSW) arm
+def latent_rows(n, d, seed, lat=32, chunk=100_000):
+    """Vectors with structure a graph index can use: a 32-d Gaussian latent through a fixed random projection + 10 % noise
+    (on isotropic N(0,1)^768 data M=16 HNSW itself reaches recall@10 ~ 0.1: the reference's walk, not a bug of either side)."""
+    A = np.random.Generator(np.random.Philox(0xA)).standard_normal((lat, d), dtype=np.float32)
+    g = np.random.Generator(np.random.Philox(seed))
+    out = np.empty((n, d), np.float32)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        out[i:i + m] = g.standard_normal((m, lat), dtype=np.float32) @ A + np.float32(0.1) * g.standard_normal((m, d), dtype=np.float32)
+    return out
+
+
+def run_hnsw_arm(args):
+    """BASELINE configs[2]: core/vectorindex HNSW fp32 dim=768 N=1M efSearch=128 top-10 on one B200.  A step = one batch
+    through coltt_b200_hnsw_search (host buffers in and out: this path has no device-resident entry point, so `value`
+    and `e2e` are the same measurement); the roofline is the random row gather of the walk."""
+    import torch
+    import coltt_b200 as cb
+    from coltt_b200 import _lib
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    L = _lib.lib()
+    assert L.coltt_b200_device_count() >= 1, "no sm_100 GPU: coltt_b200 has no CPU fallback"
+    torch.cuda.set_device(0)
+    n, d, k, ef = args.rows, args.dim, args.k, args.ef
+    nq = args.batch if args.batch != 256 else 1024
+    steps, warmup = min(args.steps, 50), max(3, min(args.warmup, 5))
+    rows = latent_rows(n, d, BASE_SEED)
+    ids = np.arange(n, dtype=np.uint64) + 1
+    t0 = time.perf_counter()
+    h = cb.Hnsw.Build(ids, rows, metric=cb.Distance_Cosine, m=16, ef=ef)
+    t_build = time.perf_counter() - t0
+    qsets = [latent_rows(nq, d, QUERY_SEED + i) for i in range(4)]
+    for i in range(warmup):
+        h.BatchSearch(qsets[i % 4], k, ef)
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = L.coltt_b200_kernel_launches()
+    kern, evals, exps = [], 0, 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        h.BatchSearch(qsets[i % 4], k, ef)
+        st = h.last_stats()
+        kern.append(st["kernel_ms"]); evals += st["dist_evals"]; exps += st["expansions"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = L.coltt_b200_kernel_launches() - launches0
+    clocks = sampler.stop()
+    kern_ms = float(np.mean(kern))
+    qps = nq * steps / wall
+    peaks = measured_peaks()
+    alg = (evals * (d * 4 + 8) + exps * 32 * 4) / steps                 # SURVEY 8(d): E*(D*4+8) + X*mMax0*4 per batch
+    roof = {"bound": "hbm", "achieved": alg / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": ncu_traffic("hnsw_search_kernel"),
+            "traffic_note": "captured at N=100K, batch 256 (profiles/r1_hnsw_search_summary.md)", "kernel": "hnsw_search_kernel",
+            "algorithmic_bytes": alg, "kernel_ms": kern_ms, "peak_source": peaks["src"],
+            "note": "random 3 KB row gathers; dist_evals and expansions are the oracle's counts"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {"metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * wall / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "core/vectorindex HNSW fp32 cosine dim=768 N=1M M=16 efSearch=128 top-10 (BASELINE configs[2])", "rows": n, "dim": d,
+                       "batch": nq, "k": k, "ef": ef, "data_model": "32-d latent + 10% noise", "build_s": round(t_build, 2),
+                       "l2": "row table 3.07 GB > 126 MB L2 (inputs larger than L2)", "dist_evals_per_query": evals / (steps * nq),
+                       "expansions_per_query": exps / (steps * nq)},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 16 + nq * 4 + 64,
+                    "note": "value is already end to end (host buffers through the C-ABI)"},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks}
+    if not args.no_cpu:
+        from oracle import oracle as orc
+        # recall@10 against exact search (FLAT fp32 store on the GPU, bit-identical to the oracle's arithmetic)
+        rq = min(64, nq)
+        sp = cb.VectorSpace("gt", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_None), capacity_hint=n, select_mode=cb.SELECT_NEAREST)
+        sp.ChangedVertices(ids, rows)
+        wi, _, _ = sp.BatchVertexSearch(qsets[0][:rq], k, math_mode=cb.MATH_EXACT)
+        sp.close()
+        gi, _, _ = h.BatchSearch(qsets[0], k, ef)
+        line["recall_at_10"] = float(np.mean([orc.compute_recall(wi[j, :k], gi[j, :k], k) for j in range(rq)]))
+        # CPU baseline: the oracle's literal hnsw.go walk, one thread (Hnsw.Search is single-threaded per query), on a bounded
+        # sample graph of 100 K vertices built here and loaded from its Commit blob (a 1 M-vertex blob is 3.5 GB of Python bytes)
+        ns = min(n, 100_000)
+        hs = cb.Hnsw.Build(ids[:ns], rows[:ns], metric=cb.Distance_Cosine, m=16, ef=ef)
+        oh = orc.Hnsw.load(hs.Commit())
+        hs.close()
+        oh.set_ef(ef)
+        cq = 32
+        t0 = time.perf_counter()
+        for j in range(cq):
+            oh.search(qsets[0][j], k)
+        line["cpu_baseline"] = {"value": cq / (time.perf_counter() - t0), "unit": "queries/s", "cores": 1, "kind": "port",
+                                "sample": f"{cq} queries on a {ns}-vertex graph (of {n}); the walk grows ~log N, so this over-states the CPU at 1 M"}
+    print(json.dumps(line), flush=True)
+    h.close()
+
+
 # ------------------------------------------------------------------------------------ our arm
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "hnsw":
+        return run_hnsw_arm(args)
 
     import torch
     import coltt_b200 as cb

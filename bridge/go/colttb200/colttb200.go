@@ -202,3 +202,68 @@ func (g *Hnsw) Search(query []float32, k int, ef int) ([]Hit, error) {
 	}
 	return out, nil
 }
+
+// BuildHnsw: bulk construction on the GPU in place of n x Hnsw.Insert (core/vectorindex/hnsw.go:104-167);
+// levels may be nil (drawn like RandomLevel, hnsw.go:280-282).
+func BuildHnsw(dim uint32, distance int32, m, ef, efConstruction int32, device int32, seed uint64, ids []uint64, vectors []float32, levels []int32) (*Hnsw, error) {
+	cfg := C.coltt_hnsw_build_cfg{dim: C.uint32_t(dim), metric: C.int32_t(distance), m: C.int32_t(m), ef: C.int32_t(ef),
+		ef_construction: C.int32_t(efConstruction), device: C.int32_t(device), seed: C.uint64_t(seed)}
+	var lv *C.int32_t
+	if len(levels) > 0 {
+		lv = (*C.int32_t)(unsafe.Pointer(&levels[0]))
+	}
+	var h *C.coltt_hnsw
+	rc := C.coltt_b200_hnsw_build(&cfg, (*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&vectors[0])), lv, C.size_t(len(ids)), &h)
+	if err := lastErr(rc); err != nil {
+		return nil, err
+	}
+	g := &Hnsw{h: h}
+	runtime.SetFinalizer(g, func(g *Hnsw) { g.Close() })
+	return g, nil
+}
+
+// Commit: Hnsw.Commit(w, true) (core/vectorindex/hnsw_commit.go:69-162).
+func (g *Hnsw) Commit() ([]byte, error) {
+	var n C.size_t
+	if err := lastErr(C.coltt_b200_hnsw_commit(g.h, nil, &n)); err != nil {
+		return nil, err
+	}
+	buf := make([]byte, int(n)+1)
+	if err := lastErr(C.coltt_b200_hnsw_commit(g.h, unsafe.Pointer(&buf[0]), &n)); err != nil {
+		return nil, err
+	}
+	return buf[:int(n)], nil
+}
+
+// MultiVertexSearch: experimental/multi_vector_vertex.go:85-137 over one Store per included vector field
+// (request order); hits come back with descending Score like multi_priority_queue.go ToSlice().
+func MultiVertexSearch(fields []*Store, queries [][]float32, ratios []int32, topK int) ([]Hit, error) {
+	nf := len(fields)
+	// C arrays of handles / query pointers live in C memory: cgo forbids passing Go memory that holds Go pointers
+	hs := (*[1 << 20]*C.coltt_store)(C.malloc(C.size_t(nf) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	qs := (*[1 << 20]*C.float)(C.malloc(C.size_t(nf) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(hs))
+	defer C.free(unsafe.Pointer(qs))
+	dim := len(queries[0])
+	flat := (*C.float)(C.malloc(C.size_t(nf*dim) * 4))
+	defer C.free(unsafe.Pointer(flat))
+	fl := unsafe.Slice((*float32)(unsafe.Pointer(flat)), nf*dim)
+	for j := 0; j < nf; j++ {
+		hs[j] = fields[j].h
+		copy(fl[j*dim:(j+1)*dim], queries[j])
+		qs[j] = (*C.float)(unsafe.Pointer(&fl[j*dim]))
+	}
+	ids := make([]uint64, topK)
+	scores := make([]float32, topK)
+	var count C.int32_t
+	rc := C.coltt_b200_multi_search(&hs[0], &qs[0], (*C.int32_t)(unsafe.Pointer(&ratios[0])), C.int(nf), C.int(topK),
+		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	if err := lastErr(rc); err != nil {
+		return nil, err
+	}
+	out := make([]Hit, int(count))
+	for i := range out {
+		out[i] = Hit{ids[i], scores[i]}
+	}
+	return out, nil
+}

@@ -15,3 +15,4 @@ from .edge import (  # noqa: F401
 )
 from .vectorindex import Hnsw  # noqa: F401,E402
 from .experimental import MultiVectorVertex, MultiVectorIndex, NearestNeighbor  # noqa: F401,E402
+from .batcher import MicroBatcher  # noqa: F401,E402

@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "coltt_b200_store_export", "coltt_b200_store_import", "coltt_b200_store_get_row",
     "coltt_b200_hnsw_load", "coltt_b200_hnsw_destroy", "coltt_b200_hnsw_len", "coltt_b200_hnsw_search",
     "coltt_b200_hnsw_last_stats", "coltt_b200_hnsw_build", "coltt_b200_hnsw_commit", "coltt_b200_hnsw_build_stats", "coltt_b200_hnsw_build_fast_stats",
-    "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_multi_search",
+    "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_multi_search", "coltt_b200_hnsw_last_timing",
 ]
 
 
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.coltt_b200_hnsw_len.argtypes = [vp, u64p]
     L.coltt_b200_hnsw_search.argtypes = [vp, f32p, C.c_size_t, C.c_int, C.c_int, u64p, f32p, i32p]
     L.coltt_b200_hnsw_last_stats.argtypes = [vp, u64p, u64p]
+    L.coltt_b200_hnsw_last_timing.argtypes = [vp, f32p]
     L.coltt_b200_hnsw_build.argtypes = [C.POINTER(HnswBuildCfg), u64p, f32p, i32p, C.c_size_t, C.POINTER(vp)]
     L.coltt_b200_hnsw_commit.argtypes = [vp, vp, C.POINTER(C.c_size_t)]
     L.coltt_b200_hnsw_build_stats.argtypes = [vp, C.POINTER(C.c_double), u64p, i32p]

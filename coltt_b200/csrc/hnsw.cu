@@ -883,6 +883,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = rs;
   std::vector<Hit> hits(nq * (size_t)k);
   unsigned long long stats[8], evals = 0, exps = 0, ties = 0;
+  float kernel_ms = 0.0f;
   std::vector<uint32_t> redo;                     // queries to run again (empty = the whole batch)
   for (;;) {
     const size_t n_ctas = redo.empty() ? nq : redo.size();
@@ -897,13 +898,17 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
     }
     COLTT_CUDA(cudaMemsetAsync(h->visited.p, 0, nq * (size_t)words * 4, st));
     COLTT_CUDA(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(unsigned long long), st));
+    if (!h->ev0) { COLTT_CUDA(cudaEventCreate(&h->ev0)); COLTT_CUDA(cudaEventCreate(&h->ev1)); }
+    COLTT_CUDA(cudaEventRecord(h->ev0, st));
     if ((rc = launch_hnsw_search(h->metric, R, p, (unsigned)n_ctas, smem, st))) return rc;
+    COLTT_CUDA(cudaEventRecord(h->ev1, st));
     COLTT_CUDA(cudaMemcpyAsync(hits.data(), h->out.p, hits.size() * sizeof(Hit), cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaMemcpyAsync(out_counts, h->counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaMemcpyAsync(stats, h->d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
     COLTT_CUDA(cudaStreamSynchronize(st));
     evals += stats[0];
     exps += stats[1];
+    { float ms = 0.0f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); kernel_ms += ms; }
     static const bool dbg = getenv("COLTT_HNSW_DEBUG") != nullptr;
     if (dbg) fprintf(stderr, "[hnsw] pass: ctas=%zu R=%d chunk=%u smem=%zu cap=%u overflows=%llu literal=%llu H1=%llu H2=%llu H3=%llu NaN=%llu\n", n_ctas, R, chunk_rows, smem, cand_cap, stats[2], stats[3], stats[4], stats[5], stats[6], stats[7]);
     ties += stats[3];
@@ -928,6 +933,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   stats[0] = evals;
   stats[1] = exps;
   h->last_ties = ties;
+  h->last_kernel_ms = kernel_ms;
   h->last_evals = stats[0];
   h->last_exp = stats[1];
   for (size_t q = 0; q < nq; q++)
@@ -961,6 +967,11 @@ COLTT_API int coltt_b200_hnsw_search(coltt_hnsw* h, const float* queries, size_t
                                      int32_t* out_counts) {
   if (!h) return fail(COLTT_ERR_INVALID, "null index");
   return coltt::hnsw_search(reinterpret_cast<Hnsw*>(h), queries, nq, k, ef, out_ids, out_scores, out_counts);
+}
+COLTT_API int coltt_b200_hnsw_last_timing(coltt_hnsw* h, float* kernel_ms) {
+  if (!h || !kernel_ms) return fail(COLTT_ERR_INVALID, "null argument");
+  *kernel_ms = reinterpret_cast<Hnsw*>(h)->last_kernel_ms;
+  return COLTT_OK;
 }
 COLTT_API int coltt_b200_hnsw_last_stats(coltt_hnsw* h, uint64_t* dist_evals, uint64_t* expansions) {
   if (!h || !dist_evals || !expansions) return fail(COLTT_ERR_INVALID, "null argument");

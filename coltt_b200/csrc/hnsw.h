@@ -23,6 +23,8 @@ struct Hnsw {
   uint32_t nbr0_stride = 32;
   unsigned long long* d_stats = nullptr;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // around the search kernel(s) of the last call
+  float last_kernel_ms = 0.0f;
   std::mutex mu;
   DeviceBuf q_in, q_deq, q_n2, visited, out, counts, q_map, qlog;
   uint64_t last_evals = 0, last_exp = 0, last_ties = 0;   // last search: distance evaluations, expansions, queries that met a tie
@@ -33,6 +35,8 @@ struct Hnsw {
     for (void* ptr : {(void*)d_rows, (void*)d_norm2, (void*)d_ids, (void*)d_level, (void*)d_vbase, (void*)d_edge_off, (void*)d_edge_nbr,
                       (void*)d_edge_dist, (void*)d_nbr0, (void*)d_stats})
       if (ptr) cudaFree(ptr);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
   }
 };

@@ -116,4 +116,6 @@ class Hnsw:
     def last_stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         _lib.check(_lib.lib().coltt_b200_hnsw_last_stats(self._h, C.byref(a), C.byref(b)))
-        return {"dist_evals": int(a.value), "expansions": int(b.value)}
+        ms = C.c_float(0.0)
+        _lib.check(_lib.lib().coltt_b200_hnsw_last_timing(self._h, C.byref(ms)))
+        return {"dist_evals": int(a.value), "expansions": int(b.value), "kernel_ms": float(ms.value)}

@@ -188,6 +188,9 @@ COLTT_API int coltt_b200_hnsw_search(coltt_hnsw* h, const float* queries, size_t
 /* Counters of the last search call: distance evaluations and expansions (for the roofline). */
 COLTT_API int coltt_b200_hnsw_last_stats(coltt_hnsw* h, uint64_t* dist_evals, uint64_t* expansions);
 
+/* Device time in milliseconds of the search kernel(s) of the last coltt_b200_hnsw_search call (CUDA events on its stream). */
+COLTT_API int coltt_b200_hnsw_last_timing(coltt_hnsw* h, float* kernel_ms);
+
 /* Bulk construction (replaces n x Hnsw.Insert, core/vectorindex/hnsw.go:104-167, for an initial load): per level,
  * the m nearest neighbours of every member by brute force on the tensor cores, exact fp32 edge distances, back
  * edges and pruneNeighbors (hnsw.go:449-474) — see csrc/hnsw_build.cu.  `levels` may be NULL (drawn as

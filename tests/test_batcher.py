@@ -1,0 +1,61 @@
+"""Micro-batcher: concurrent single-query callers are coalesced into batched searches and each gets
+exactly its own row back.  Host logic only — the batched search here is a numpy stand-in."""
+import threading
+
+import numpy as np
+import pytest
+
+from coltt_b200.batcher import MicroBatcher
+
+
+def _brute(rows):
+    calls = []
+
+    def search(qs, k):
+        calls.append(len(qs))
+        d = ((qs[:, None, :] - rows[None, :, :]) ** 2).sum(-1)
+        idx = np.argsort(d, axis=1, kind="stable")[:, :k]
+        return idx.astype(np.uint64), np.take_along_axis(d, idx, 1).astype(np.float32), np.full(len(qs), min(k, len(rows)), np.int32)
+    return search, calls
+
+
+def test_concurrent_callers_are_coalesced_and_get_their_own_rows():
+    rng = np.random.default_rng(0)
+    rows = rng.standard_normal((500, 16)).astype(np.float32)
+    search, calls = _brute(rows)
+    mb = MicroBatcher(search, 16, max_batch=32, max_wait_ms=20.0)
+    qs = rng.standard_normal((200, 16)).astype(np.float32)
+    out = [None] * len(qs)
+
+    def worker(lo, hi):
+        for i in range(lo, hi):
+            out[i] = mb.VertexSearch(qs[i], 5)
+    ths = [threading.Thread(target=worker, args=(i * 25, (i + 1) * 25)) for i in range(8)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    mb.close()
+    want_ids, want_sc, _ = search(qs, 5)
+    for i in range(len(qs)):
+        assert np.array_equal(out[i][0], want_ids[i]) and out[i][1].tobytes() == want_sc[i].tobytes()
+    assert mb.served == 200 and mb.batches < 200 and max(calls[:-1]) <= 32 and max(calls[:-1]) > 1
+
+
+def test_mixed_topk_flush_on_timeout_errors_and_close():
+    rows = np.eye(8, dtype=np.float32)
+    search, calls = _brute(rows)
+    mb = MicroBatcher(search, 8, max_batch=256, max_wait_ms=1.0)
+    f1, f2, f3 = mb.submit(rows[1], 3), mb.submit(rows[2], 1), mb.submit(rows[3], 3)
+    assert f1.result(5)[0][0] == 1 and f2.result(5)[0].tolist() == [2] and f3.result(5)[0][0] == 3
+    assert calls[:2] == [2, 1]                       # equal-topK requests ride together, the odd one alone
+    with pytest.raises(ValueError, match="Dim Length"):
+        mb.submit(np.zeros(5, np.float32), 3)
+    mb.close()
+    with pytest.raises(RuntimeError):
+        mb.submit(rows[0], 1)
+
+    def boom(qs, k):
+        raise RuntimeError("device lost")
+    mb2 = MicroBatcher(boom, 8, max_wait_ms=0.1)
+    with pytest.raises(RuntimeError, match="device lost"):
+        mb2.VertexSearch(rows[0], 2)
+    mb2.close()

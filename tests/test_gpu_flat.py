@@ -240,3 +240,29 @@ def test_nan_scores_rank_last(cb, oracle):
         assert [h.Id for h in hits] == wi.tolist()
         assert np.isnan([h.Score for h in hits][-2:]).all()
     sp.close()
+
+
+def test_micro_batcher_rows_equal_single_query_calls(cb, oracle):
+    """f-4: 8 threads of single-query callers coalesced by coltt_b200.batcher.MicroBatcher into batched searches —
+    every caller gets exactly what its own VertexSearch call returns (= the oracle's answer)."""
+    import threading
+    from coltt_b200.batcher import MicroBatcher
+    n, d, k = 6000, 96, 7
+    ids, vecs = sparse_ids(n, 21), normal(n, d, 21)
+    sp, st = _pair(cb, oracle, d, 0, 1, ids, vecs)
+    qs = normal(96, d, QUERY_SEED + 5)
+    mb = MicroBatcher(lambda q, kk: sp.BatchVertexSearch(q, kk, select_mode=cb.SELECT_NEAREST), d, max_batch=32, max_wait_ms=5.0)
+    out = [None] * len(qs)
+
+    def worker(lo, hi):
+        for i in range(lo, hi):
+            out[i] = mb.VertexSearch(qs[i], k)
+    ths = [threading.Thread(target=worker, args=(i * 12, (i + 1) * 12)) for i in range(8)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    mb.close()
+    assert mb.served == len(qs) and mb.batches < len(qs)
+    for i in range(len(qs)):
+        wi, ws = st.search_total_order(qs[i], k, select_mode=1)
+        assert_same_hits(out[i][0], out[i][1], wi, ws, f"batcher q{i}")
+    sp.close()
