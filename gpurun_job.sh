@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-(DATA=latent N=100000 NQ=256 timeout 300 ncu --set full --clock-control none --import-source on -k regex:hnsw_search -s 2 -c 1 -o gpurun_out/k4v5_full -f python tools/probe_hnsw_1m.py > gpurun_out/ncu_k4v5.log 2>&1); grep -E "Profiling" gpurun_out/ncu_k4v5.log | head -2
-(COLTT_HNSW_DEBUG=1 COLTT_HNSW_CTAS=3 COLTT_HNSW_CHUNK=20 DATA=latent N=1000000 NQ=1024,4096 timeout 200 python tools/probe_hnsw_1m.py > gpurun_out/hnsw_1m_c3.log 2>gpurun_out/hnsw_1m_c3.err); cut -c1-120,440- gpurun_out/hnsw_1m_c3.log; sort gpurun_out/hnsw_1m_c3.err | uniq -c | head -4
-(COLTT_HNSW_DEBUG=1 COLTT_HNSW_CTAS=4 COLTT_HNSW_CHUNK=14 DATA=latent N=1000000 NQ=1024,4096 timeout 200 python tools/probe_hnsw_1m.py > gpurun_out/hnsw_1m_c4.log 2>gpurun_out/hnsw_1m_c4.err); cut -c1-120,440- gpurun_out/hnsw_1m_c4.log; sort gpurun_out/hnsw_1m_c4.err | uniq -c | head -4
+(timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gemm_filter|rerank|flat_scan|merge_topk|prep_rows' -s 7 -c 30 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_launch_final.log 2>&1); tail -n 2 gpurun_out/ncu_launch_final.log | cut -c1-300; wc -l gpurun_out/launches_final.csv
