@@ -266,3 +266,30 @@ def test_micro_batcher_rows_equal_single_query_calls(cb, oracle):
         wi, ws = st.search_total_order(qs[i], k, select_mode=1)
         assert_same_hits(out[i][0], out[i][1], wi, ws, f"batcher q{i}")
     sp.close()
+
+
+def test_config4_shape_f8_dim1536_top100_batched_and_sharded(cb, oracle):
+    """BASELINE config 4 shape at an oracle-sized N: edge FLAT f8 (the reference's literal codec: 8 decodable values,
+    massive ties -> total order T), cosine, dim 1536, top-100, a query batch, and the rows split into two shards by
+    ShardVertex (pkg/sharding/shard.go:34-41) whose per-shard top-100 lists merge into the single-store answer."""
+    n, d, k = 12_000, 1536, 100
+    ids, vecs = sparse_ids(n, 44), normal(n, d, 44)
+    qs = normal(12, d, QUERY_SEED + 44)
+    sp, st = _pair(cb, oracle, d, 0, 2, ids, vecs)
+    shard = np.array([oracle.shard_vertex(int(i), 16) % 2 for i in ids])
+    parts = [_pair(cb, oracle, d, 0, 2, ids[shard == r], vecs[shard == r])[0] for r in (0, 1)]
+    for mode in (cb.SELECT_COMPAT, cb.SELECT_NEAREST):
+        gi, gs, gc = sp.BatchVertexSearch(qs, k, select_mode=mode)
+        per = [p.BatchVertexSearch(qs, k, select_mode=mode) for p in parts]
+        for j in range(len(qs)):
+            wi, ws = st.search_total_order(qs[j], k, select_mode=mode)
+            assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], wi, ws, f"c4 mode={mode} q{j}")
+            # merge of the two shards' lists under T == the unsharded answer (what dist.py's K5 merge computes on the GPU)
+            mi = np.concatenate([p[0][j, :p[2][j]] for p in per])
+            ms = np.concatenate([p[1][j, :p[2][j]] for p in per])
+            key = np.where(np.isnan(ms), np.inf, ms)
+            order = np.lexsort((mi, np.isnan(ms), key))
+            order = order[:k] if mode == cb.SELECT_NEAREST else order[-k:]
+            assert_same_hits(mi[order], ms[order], wi, ws, f"c4 sharded mode={mode} q{j}")
+    for p in parts + [sp]:
+        p.close()
