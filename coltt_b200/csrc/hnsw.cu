@@ -150,7 +150,7 @@ struct WarpSorted {
     if (check && has_tie && n >= ef) {            // this insert evicts: are the two largest afterwards equal?
       const float m1 = top(lane);
       if (d == m1) return false;
-      if (n >= 2 && from_top(1, lane) == m1) return false;
+      if (d < m1 && n >= 2 && from_top(1, lane) == m1) return false;   // d > m1: d itself is the unique largest and goes
     }
     const uint32_t full = __popc(below);
     if (lane > full) {                            // everything moves up by one
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
                     res_pos = log_n + 1;                      // ... including the push logged below
                   }
                   ts = __shfl_sync(0xffffffffu, ts, 0);
-                  haz_x = ws.top(lane) > d ? ws.top(lane) : d;   // priority of the evicted member == the largest one left
+                  haz_x = ws.top(lane);                       // priority of the evicted member == the largest one left
                   haz_set = true;
                   if (ts != sl) {
                     ws.remove(ts, lane);
