@@ -104,6 +104,8 @@ def model_search(nbrs, dist, ep, ef, k, stats):
 
     def insert(d, s, check=True):
         nonlocal has_tie
+        if d != d:
+            return False                              # NaN: the walk continues on the literal heaps for good
         if any(e[0] == d for e in ws):
             has_tie = True
         if check and has_tie and len(ws) >= ef:
@@ -116,9 +118,47 @@ def model_search(nbrs, dist, ep, ef, k, stats):
             ws.pop()
         return True
 
+    def finish_literal(out_of, lb, rest):
+        """go_literal(): both heaps brought up to date, then the reference's loop — first the rest of the expansion
+        that met the NaN (same frozen lowerBound), then the remaining walk."""
+        nonlocal evals, exps
+        replay("res")
+        replay("cand")
+        first = True
+        while True:
+            if not first:
+                if not len(cand):
+                    break
+                cp, out_of = cand.pop()
+                lb = res.a[0][0]
+                if cp > lb:
+                    break
+                exps += 1
+                rest = []
+                for s in nbrs[out_of]:
+                    if s not in visited:
+                        visited.add(s)
+                        evals += 1
+                        rest.append(s)
+            first = False
+            for s in rest:
+                d = dist[s]
+                if out_of is None or d < lb or len(res) < ef:
+                    cand.push(d, s)
+                    res.push(d, s)
+                    if len(res) > ef:
+                        res.pop()
+        while len(res) > k:
+            res.pop()
+        out = [None] * len(res)
+        for i in range(len(res) - 1, -1, -1):
+            out[i] = res.pop()
+        return out, evals, exps
+
     visited = {ep}
     evals, exps = 1, 0
-    insert(dist[ep], ep)
+    if not insert(dist[ep], ep):
+        return finish_literal(None, 0.0, [ep])          # ST_ENTRY2 with a NaN entrypoint distance
     log.append((dist[ep], ep))
     while True:
         # ---- pick
@@ -146,14 +186,15 @@ def model_search(nbrs, dist, ep, ef, k, stats):
         lb = ws[-1][0]
         log.append(None)
         exps += 1
-        # ---- expand + fold
-        for s in nbrs[cs]:
-            if s in visited:
-                continue
-            visited.add(s)
+        # ---- expand + fold (the kernel test-and-sets the visited bits of the whole list, then folds in list order)
+        fresh = [s for s in nbrs[cs] if s not in visited]
+        visited.update(fresh)
+        evals += len(fresh)
+        for i, s in enumerate(fresh):
             d = dist[s]
-            evals += 1
             if d < lb or len(ws) < ef:
+                if d != d:
+                    return finish_literal(cs, lb, fresh[i:])
                 if not insert(d, s):
                     stats["H2"] += 1
                     replay("res")
@@ -179,13 +220,18 @@ def model_search(nbrs, dist, ep, ef, k, stats):
     return [(e[0], e[1]) for e in ws[:k]], evals, exps
 
 
-def _graph(rng, n, deg, levels):
+def _canon(r):
+    return [("nan" if p != p else p, s) for p, s in r[0]], r[1], r[2]
+
+
+def _graph(rng, n, deg, levels, nan_frac=0.0):
     nbrs = []
     for v in range(n):
         m = int(rng.integers(1, deg + 1))
         c = set(int(x) for x in rng.integers(0, n, size=m)) - {v}
         nbrs.append(sorted(c))                    # ascending neighbour id, the deterministic iteration order
     dist = rng.integers(0, levels, size=n).astype(np.float32)
+    dist[rng.random(n) < nan_frac] = np.nan                  # zero-norm rows: 0/0 in the reference too
     return nbrs, [float(x) for x in dist]
 
 
@@ -195,12 +241,12 @@ def test_register_result_set_with_lazy_literal_heaps_walks_like_go(levels):
     stats = {"H1": 0, "H2": 0, "H3": 0}
     for trial in range(1500):
         n = int(rng.integers(2, 120))
-        nbrs, dist = _graph(rng, n, int(rng.integers(1, 12)), levels)
+        nbrs, dist = _graph(rng, n, int(rng.integers(1, 12)), levels, nan_frac=0.03 if trial % 3 == 0 else 0.0)
         ep = int(rng.integers(0, n))
         ef = int(rng.integers(1, 24))
         k = int(rng.integers(1, ef + 1))
         want = literal_search(nbrs, dist, ep, ef, k)
         got = model_search(nbrs, dist, ep, ef, k, stats)
-        assert got == want, (levels, trial, n, ef, k)
+        assert _canon(got) == _canon(want), (levels, trial, n, ef, k)
     if levels <= 40:
         assert stats["H1"] and stats["H2"] and stats["H3"], stats     # every hazard path was exercised
