@@ -43,7 +43,7 @@ def test_concurrent_callers_are_coalesced_and_get_their_own_rows():
 def test_mixed_topk_flush_on_timeout_errors_and_close():
     rows = np.eye(8, dtype=np.float32)
     search, calls = _brute(rows)
-    mb = MicroBatcher(search, 8, max_batch=256, max_wait_ms=1.0)
+    mb = MicroBatcher(search, 8, max_batch=256, max_wait_ms=250.0)   # long enough for the three submits below to be queued together
     f1, f2, f3 = mb.submit(rows[1], 3), mb.submit(rows[2], 1), mb.submit(rows[3], 3)
     assert f1.result(5)[0][0] == 1 and f2.result(5)[0].tolist() == [2] and f3.result(5)[0][0] == 3
     assert calls[:2] == [2, 1]                       # equal-topK requests ride together, the odd one alone
