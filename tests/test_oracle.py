@@ -318,3 +318,24 @@ def test_cflat_multi_search_is_the_sequential_f32_weighted_sum(oracle):
             o = np.lexsort((-ids.astype(np.int64), -sc))[:k]
             assert np.array_equal(gi, ids[o]) and gs.tobytes() == sc[o].tobytes(), (metric, inc)
             assert np.all(np.diff(gs) <= 0)
+
+
+def test_lane_emulation_reproduces_the_committed_reference_outputs(oracle):
+    """tests/golden/avx_golden.json holds what the reference's own compiled AVX kernels returned for seeded inputs
+    (generated by tests/golden/make_avx_golden.py where /root/reference exists); the oracle's scalar lane-order
+    restatement must reproduce those bits with the reference hook OFF — this pins it where oracle/_ref is absent too."""
+    import ctypes as C
+    import json
+    import os
+    from tests.golden.make_avx_golden import bits, inputs
+    oracle.use_reference_kernels(False)
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "avx_golden.json")))
+    L = oracle.lib()
+    assert len(gold["cases"]) >= 40
+    for c in gold["cases"]:
+        a, b = inputs(c["dim"], c["trial"])
+        ap, bp = a.ctypes.data_as(oracle.f32p), b.ctypes.data_as(oracle.f32p)
+        dot, n2, l2 = C.c_float(), C.c_float(), C.c_float()
+        L.orc_cosine_dot_norm(c["dim"], ap, bp, C.byref(dot), C.byref(n2))
+        L.orc_l2sq(c["dim"], ap, bp, C.byref(l2))
+        assert (bits(dot.value), bits(n2.value), bits(l2.value)) == (c["dot"], c["norm2"], c["l2sq"]), c
