@@ -133,6 +133,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf": 1590.0, "src": "fallback"}
 
 
+def roofline_fast(alg_bytes, flops, kern_ms, peaks, traffic, kname):
+    """Roofline of the tcgen05 filter kernel.  Both floors are computed from the MEASURED peaks; the larger one binds:
+    at 256 queries x fp16 rows the intensity is 256 flop/B, above the measured ridge (bf16 TFLOP/s / HBM GB/s ~ 210),
+    so the tensor pipe is the bound and HBM the secondary figure (both are reported)."""
+    sec = kern_ms / 1e3
+    gbs, tfs = alg_bytes / sec / 1e9, flops / sec / 1e12
+    t_hbm, t_tensor = alg_bytes / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tf"] * 1e12)
+    roof = {"kernel": kname, "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops, "traffic": traffic,
+            "hbm_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": gbs / peaks["hbm_gbs"],
+            "tensor_tflops": tfs, "tensor_peak_tflops": peaks["tf"], "tensor_frac": tfs / peaks["tf"],
+            "floor_ms": {"hbm": t_hbm * 1e3, "tensor": t_tensor * 1e3}}
+    if t_tensor >= t_hbm:
+        roof.update({"bound": "tensor", "achieved": tfs, "peak": peaks["tf"], "unit": "TFLOP/s"})
+    else:
+        roof.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s"})
+    return roof
+
+
 # ------------------------------------------------------------------------------- reference arm
 def cpu_arm(args, rows, ids, queries, n_threads):
     """The reference's CPU path (port of VertexSearch control flow driving the reference's own
@@ -443,10 +461,7 @@ def main():
                                          f"{flops / (kern_ms / 1e3) / 1e12:.1f} TFLOP/s fp32 unfused"}
     else:
         kname = "gemm_filter_pair_kernel" if nq > 128 else "gemm_filter_kernel"
-        roof = {"bound": "hbm", "achieved": alg_bytes / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "traffic": ncu_traffic(kname), "kernel": kname, "algorithmic_bytes": alg_bytes,
-                "tensor_tflops": flops / (kern_ms / 1e3) / 1e12, "tensor_peak_tflops": peaks["tf"],
-                "tensor_frac": flops / (kern_ms / 1e3) / 1e12 / peaks["tf"]}
+        roof = roofline_fast(alg_bytes, flops, kern_ms, peaks, ncu_traffic(kname), kname)
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["peak_source"] = peaks["src"]
     roof["kernel_ms"] = kern_ms

@@ -59,3 +59,22 @@ def test_mixed_topk_flush_on_timeout_errors_and_close():
     with pytest.raises(RuntimeError, match="device lost"):
         mb2.VertexSearch(rows[0], 2)
     mb2.close()
+
+
+def test_bench_roofline_picks_the_binding_floor():
+    """bench.py's roofline: both floors from the measured peaks, the larger one binds (config 2 sits above the ridge)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    peaks = {"hbm_gbs": 6541.1, "tf": 1364.4, "src": "measured"}
+    n, d, nq, k = 1_000_000, 768, 256, 10
+    alg = n * d * 2 + n * 4 + nq * d * 4 + nq * k * 16
+    r = bench.roofline_fast(alg, 2.0 * nq * n * d, 0.3614, peaks, 1597533448, "gemm_filter_pair_kernel")
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["achieved"] / r["peak"] - 0.797) < 0.01
+    assert abs(r["hbm_frac"] - 0.652) < 0.01 and r["floor_ms"]["tensor"] > r["floor_ms"]["hbm"]
+    r1 = bench.roofline_fast(alg, 2.0 * 8 * n * d, 0.3, peaks, None, "gemm_filter_kernel")     # 8 queries: HBM-bound
+    assert r1["bound"] == "hbm" and r1["unit"] == "GB/s" and r1["peak"] == 6541.1
+    for key in ("bound", "achieved", "peak", "unit", "traffic"):
+        assert key in r and key in r1
