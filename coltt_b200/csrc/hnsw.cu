@@ -36,6 +36,7 @@ static constexpr uint32_t kHnswChunkMax = 32;    // neighbour rows gathered and 
 static constexpr uint32_t kCandCapMin = 1024;    // candidate min-heap capacity (shared memory): first attempt
 static constexpr uint32_t kCandCapMax = 8192;    //   ... and the re-run after an overflow
 static constexpr uint32_t kNoSlot = 0xffffffffu;
+static constexpr uint32_t kRingMaxStages = 4;
 
 struct HnswParams {
   const uint8_t* rows; uint32_t row_stride; uint32_t dim; uint32_t q_stride;
@@ -54,6 +55,10 @@ struct HnswParams {
   const uint32_t* q_map;                        // CTA -> query (re-runs of a subset), or null
   uint2* qlog; uint32_t log_cap;                // [nq][log_cap] queue operations of the fast path (replayed after a tie)
   unsigned long long* stats;                    // [0] distance evaluations, [1] expansions, [2] queue overflows, [3] queries finished on the literal heaps, [4..7] H1 / H2 / H3 / NaN events
+  // RING variant only (experimental, COLTT_HNSW_RING): rows are staged through per-warp rings of dim-chunks
+  uint32_t ring_cb;                             // bytes of a row per ring stage (multiple of 32)
+  uint32_t ring_cs;                             // shared-memory stride of one staged chunk (== 32 mod 128)
+  uint32_t ring_stages;                         // stages per warp (<= kRingMaxStages)
 };
 
 // Go container/heap (src/container/heap/heap.go: up / down), keyed on priority only —
@@ -253,7 +258,10 @@ enum { CMD_STOP = 0, CMD_ONE = 1, CMD_LIST = 2, CMD_L0 = 3 };
 enum { ST_ENTRY = 0, ST_GREEDY = 1, ST_ENTRY2 = 2, ST_SEARCH = 3 };
 enum { STOP_DONE = 1, STOP_OVERFLOW = 2, STOP_TIE = 3 };
 
-template <int METRIC, int R>
+// RING (experimental, off by default): instead of landing whole rows (32 x 3 KB per CTA at dim 768), every warp streams
+// its own 8 rows through a small ring of dim-chunks, K1-style — accumulators stay in registers across chunks, so the
+// arithmetic order is unchanged — which cuts the staging memory ~4x and lets four queries share an SM.
+template <int METRIC, int R, bool RING = false>
 __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* rows_s = smem;                                                        // [chunk_rows][rs]
@@ -269,6 +277,15 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&sh_bar);
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); sh_state = 0; sh_cnt = 0; }
+  uint32_t ring_bar0 = 0, ring_phase = 0;          // RING: this warp's first stage barrier; one phase bit per stage
+  if constexpr (RING) {
+    __shared__ __align__(8) uint64_t sh_ring_bar[kHnswThreads / 32][kRingMaxStages];
+    ring_bar0 = smem_u32(&sh_ring_bar[warp][0]);
+    if (lane == 0) {
+      for (uint32_t st = 0; st < kRingMaxStages; st++) mbar_init(ring_bar0 + 8 * st, 1);
+      fence_mbar_init();
+    }
+  }
   for (uint32_t d = tid; d < p.q_stride; d += blockDim.x) q_s[d] = p.queries[(size_t)q * p.q_stride + d];
   __syncthreads();
   const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
@@ -550,9 +567,11 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
         const uint32_t pos = __popc(mask & ((1u << lane) - 1u));
         m = __popc(mask);
         if (valid) nb_slot[pos] = s;
-        if (lane == 0 && m) mbar_arrive_expect_tx(bar, m * p.row_stride);
-        __syncwarp();
-        if (valid) bulk_g2s(smem_u32(rows_s + (size_t)pos * p.rs), p.rows + (size_t)s * p.row_stride, p.row_stride, bar);
+        if constexpr (!RING) {
+          if (lane == 0 && m) mbar_arrive_expect_tx(bar, m * p.row_stride);
+          __syncwarp();
+          if (valid) bulk_g2s(smem_u32(rows_s + (size_t)pos * p.rs), p.rows + (size_t)s * p.row_stride, p.row_stride, bar);
+        }
         if (m) break;
       }
       if (lane == 0) sh_cnt = m;
@@ -574,6 +593,57 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
     const bool valid = j < m;
     float rn = 0.0f;
     if (METRIC == COLTT_COSINE && valid && h == 0) rn = p.row_norm2[nb_slot[j]];   // in flight while the rows land
+    if constexpr (RING) {
+      if (warp * 8 < m) {
+        // this warp's rows [warp*8, warp*8 + nrows) stream through its own ring: stage = 8 rows x ring_cb bytes
+        const uint32_t nrows = m - warp * 8 < 8u ? m - warp * 8 : 8u;
+        const uint32_t CB = p.ring_cb, CS = p.ring_cs, S = p.ring_stages, CBE = CB / 4;
+        const uint32_t n_chunks = (p.row_stride + CB - 1) / CB;
+        uint8_t* ring = rows_s + (size_t)warp * S * 8 * CS;
+        const uint8_t* src = p.rows + (size_t)(valid ? nb_slot[j] : 0u) * p.row_stride;
+        auto issue_chunk = [&](uint32_t c) {
+          const uint32_t st = c % S, off = c * CB;
+          const uint32_t bytes = p.row_stride - off < CB ? p.row_stride - off : CB;
+          if (lane == 0) mbar_arrive_expect_tx(ring_bar0 + 8 * st, bytes * nrows);
+          __syncwarp();
+          if (valid && h == 0) bulk_g2s(smem_u32(ring + ((size_t)st * 8 + (lane >> 2)) * CS), src + off, bytes, ring_bar0 + 8 * st);
+        };
+        for (uint32_t c = 0; c < S && c < n_chunks; c++) issue_chunk(c);
+        float a0 = 0.0f, a1 = 0.0f, tot = 0.0f;     // AVX lanes 2h and 2h+1
+        for (uint32_t c = 0; c < n_chunks; c++) {
+          const uint32_t st = c % S;
+          mbar_wait(ring_bar0 + 8 * st, (ring_phase >> st) & 1u);
+          ring_phase ^= 1u << st;
+          const uint8_t* rowp = ring + ((size_t)st * 8 + (valid ? (lane >> 2) : 0u)) * CS;
+          const uint32_t e0 = c * CBE, e1 = e0 + CBE < full8 ? e0 + CBE : full8;
+#pragma unroll 8
+          for (uint32_t e = e0; e < e1; e += 8) {
+            const float2 rv = *reinterpret_cast<const float2*>(rowp + (size_t)(e - e0 + 2 * h) * 4);
+            const float2 qv = *reinterpret_cast<const float2*>(q_s + e + 2 * h);
+            if (METRIC == COLTT_COSINE) {
+              a0 = add_rn(a0, mul_rn(qv.x, rv.x)); a1 = add_rn(a1, mul_rn(qv.y, rv.y));
+            } else {
+              const float d0 = sub_rn(qv.x, rv.x), d1 = sub_rn(qv.y, rv.y);
+              a0 = add_rn(a0, mul_rn(d0, d0)); a1 = add_rn(a1, mul_rn(d1, d1));
+            }
+          }
+          if (c == n_chunks - 1) {                  // the scalar tail (dim % 8 elements) lives in the last chunk
+            float t = add_rn(a0, a1);
+            t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+            tot = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+            for (uint32_t d = full8; d < p.dim; d++) {
+              const float rv = reinterpret_cast<const float*>(rowp)[d - e0], qv = q_s[d];
+              if (METRIC == COLTT_COSINE) tot = add_rn(tot, mul_rn(qv, rv));
+              else { const float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
+            }
+          }
+          __syncwarp();
+          fence_proxy_async();                       // our reads of stage st precede its refill by the async proxy
+          if (c + S < n_chunks) issue_chunk(c + S);
+        }
+        if (valid && h == 0) nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, rn) : sqrt_via_f64(tot);
+      }
+    } else {
     mbar_wait(bar, phase);
     phase ^= 1;
     if (warp * 8 < m) {
@@ -600,6 +670,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(HnswParams p)
         else { const float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
       }
       if (valid && h == 0) nb_dist[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, rn) : sqrt_via_f64(tot);
+    }
     }
     if (warp == 0 && spec_cur != kNoSlot) spec_w = spec_s != kNoSlot ? __ldcg(vis + (spec_s >> 5)) : 0u;
     __syncthreads();
@@ -803,6 +874,20 @@ int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
 
 
 static int launch_hnsw_search(int metric, int R, const HnswParams& p, unsigned n_ctas, size_t smem, cudaStream_t st) {
+  if (p.ring_cb) {   // experimental dim-chunk ring (COLTT_HNSW_RING), register result set only
+#define COLTT_HNSW_RING_CASE(M, RR)                                                          \
+  if (metric == M && R == RR) {                                                              \
+    int arc = kernel_attrs(hnsw_search_kernel<M, RR, true>, smem);                           \
+    if (arc) return arc;                                                                     \
+    hnsw_search_kernel<M, RR, true><<<n_ctas, kHnswThreads, smem, st>>>(p);                  \
+  } else
+    COLTT_HNSW_RING_CASE(COLTT_COSINE, 4) COLTT_HNSW_RING_CASE(COLTT_EUCLIDEAN, 4)
+    return fail(COLTT_ERR_UNSUPPORTED, "COLTT_HNSW_RING serves 64 < ef <= 128 only");
+#undef COLTT_HNSW_RING_CASE
+    count_launch();
+    COLTT_CUDA(cudaGetLastError());
+    return COLTT_OK;
+  }
 #define COLTT_HNSW_CASE(M, RR)                                                               \
   if (metric == M && R == RR) {                                                              \
     int arc = kernel_attrs(hnsw_search_kernel<M, RR>, smem);                                 \
@@ -839,6 +924,8 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   static const int env_chunk = getenv("COLTT_HNSW_CHUNK") ? atoi(getenv("COLTT_HNSW_CHUNK")) : 0;
   static const int env_ctas = getenv("COLTT_HNSW_CTAS") ? atoi(getenv("COLTT_HNSW_CTAS")) : 0;
   static const int env_literal = getenv("COLTT_HNSW_LITERAL") ? atoi(getenv("COLTT_HNSW_LITERAL")) : 0;
+  // experimental: COLTT_HNSW_RING="<chunk bytes>,<stages>" (e.g. "512,2") stages rows through per-warp dim-chunk rings
+  static const char* env_ring = getenv("COLTT_HNSW_RING");
   int R = env_literal ? 0 : ef <= 64 ? 2 : ef <= 128 ? 4 : ef <= 256 ? 8 : 0;
   uint32_t cand_cap = kCandCapMin;
   while (cand_cap < 8 * ef && cand_cap < kCandCapMax) cand_cap *= 2;
@@ -861,6 +948,19 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
     return false;
   };
   if (!plan(cand_cap, nq)) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
+  uint32_t ring_cb = 0, ring_cs = 0, ring_stages = 0;
+  if (env_ring && R == 4) {
+    unsigned cb = 0, stg = 0;
+    if (sscanf(env_ring, "%u,%u", &cb, &stg) == 2 && cb >= 32 && cb % 32 == 0 && stg >= 2 && stg <= kRingMaxStages) {
+      ring_cb = std::min<uint32_t>(cb, (h->row_stride + 31) / 32 * 32);
+      ring_cs = (ring_cb + 127) / 128 * 128 + 32;
+      ring_stages = stg;
+      const size_t fixed = (size_t)q_stride * 4 + (size_t)cand_cap * 8 + (size_t)(ef + 1) * 8 + kHnswChunkMax * 8;
+      chunk_rows = kHnswChunkMax;                 // the rows region is chunk_rows * rs bytes: 32 rows x stages x ring_cs
+      smem = fixed + (size_t)kHnswChunkMax * ring_stages * ring_cs;
+      if (smem > 200 * 1024) ring_cb = 0;
+    }
+  }
   const uint32_t words = (h->n + 31) / 32;
   cudaStream_t st = h->stream;
   int rc;
@@ -880,7 +980,8 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   p.nbr0 = h->d_nbr0; p.nbr0_stride = h->nbr0_stride;
   p.metric = h->metric; p.queries = (const float*)h->q_deq.p; p.q_norm2 = (const float*)h->q_n2.p; p.nq = (uint32_t)nq; p.k = (uint32_t)k;
   p.ef = ef; p.visited = (uint32_t*)h->visited.p; p.visited_words = words; p.out = (Hit*)h->out.p; p.out_counts = (int*)h->counts.p;
-  p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = rs;
+  p.out_stride = (uint32_t)k; p.stats = h->d_stats; p.rs = ring_cb ? ring_stages * ring_cs : rs;
+  p.ring_cb = ring_cb; p.ring_cs = ring_cs; p.ring_stages = ring_stages;
   std::vector<Hit> hits(nq * (size_t)k);
   unsigned long long stats[8], evals = 0, exps = 0, ties = 0;
   float kernel_ms = 0.0f;
@@ -919,6 +1020,7 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
       return fail(COLTT_ERR_UNSUPPORTED, "HNSW candidate queue overflowed its shared-memory capacity (ef too large)");
     R = 0;
     cand_cap = kCandCapMax;
+    p.ring_cb = 0; p.rs = rs;                      // the literal re-run uses the whole-row staging
     std::vector<uint32_t> again;
     if (redo.empty()) {
       for (size_t q = 0; q < nq; q++)
