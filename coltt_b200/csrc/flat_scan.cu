@@ -23,6 +23,8 @@
 //
 // Algorithmic bytes per launch:  n_items*dim*elem + n_items*4 (norms)
 //   + nq*dim*4 (queries) + grid*nq*k*16 (lists) — one HBM pass over the shard per QT queries.
+#include <cstdlib>
+
 #include "exact_math.cuh"
 #include "kernels.cuh"
 #include "store.h"
@@ -263,11 +265,17 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
   if (nq == 0) return fail(COLTT_ERR_INVALID, "no queries");
   const uint32_t q_stride = (dim + 7) / 8 * 8;
   int qt = nq == 1 ? 1 : (nq <= 4 ? 4 : 8);
-  const size_t budget = 227 * 1024 - 256;  // static smem (lut, counts) is small; keep a margin
+  // experimental (COLTT_SCAN_CTAS=2, default 1): two resident CTAs per SM with half-depth rings — the fp16 scan is
+  // issue-bound at 2 warps per scheduler (profiles/r1_flat_scan_rerank_summary.md); not validated on a GPU yet
+  static const int env_ctas = [] { const char* e = getenv("COLTT_SCAN_CTAS"); const int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
   auto q_bytes = [&](int q) { return (size_t)q * q_stride * 4 + 32; };
   while (qt > 1 && q_bytes(qt) > 96 * 1024) qt = qt == 8 ? 4 : 1;
   if (q_bytes(qt) > 160 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "dim too large for the scan kernel");
   const size_t fixed = q_bytes(qt) + (size_t)kScanWarps * 8 * 8 + 128;
+  const size_t half = (227 * 1024) / 2 - 1024 - 256;
+  const size_t merge_need = ((size_t)kScanWarps * k + k) * sizeof(Hit) + kScanWarps * sizeof(int);
+  const int ctas_per_sm = (env_ctas == 2 && fixed + 32 * 1024 <= half && merge_need <= half) ? 2 : 1;
+  const size_t budget = ctas_per_sm == 2 ? half : 227 * 1024 - 256;  // static smem (lut, counts) is small; keep a margin
   const size_t per_warp = (budget - fixed) / kScanWarps;
   const uint32_t row_up = (row_stride + 127) / 128 * 128;
   uint32_t cb = 0, stages = 0;
@@ -287,7 +295,7 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
   if (smem > 227 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "shared memory budget exceeded");
   const uint32_t n_groups = (n_items + kRowsPerWarp - 1) / kRowsPerWarp;
   uint32_t gx = (n_groups + kScanWarps - 1) / kScanWarps;
-  if (gx > (uint32_t)n_sms) gx = (uint32_t)n_sms;
+  if (gx > (uint32_t)(n_sms * ctas_per_sm)) gx = (uint32_t)(n_sms * ctas_per_sm);
   if (gx == 0) gx = 1;
   plan->grid_x = (int)gx;
   plan->grid_y = (int)((nq + qt - 1) / qt);
