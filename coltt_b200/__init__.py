@@ -10,7 +10,7 @@ from ._lib import ColttError, lib, build_library, LIB_PATH  # noqa: F401
 from .edge import (  # noqa: F401
     Vectorstore, VectorSpace, SearchResultItem, Metadata,
     Distance_Cosine, Distance_Euclidean,
-    Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16,
+    Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16, Quantization_F8_E4M3,
     SELECT_COMPAT, SELECT_NEAREST, MATH_EXACT, MATH_FAST, score_helper,
 )
 from .vectorindex import Hnsw  # noqa: F401,E402

@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "coltt_b200_hnsw_load", "coltt_b200_hnsw_destroy", "coltt_b200_hnsw_len", "coltt_b200_hnsw_search",
     "coltt_b200_hnsw_last_stats", "coltt_b200_hnsw_build", "coltt_b200_hnsw_commit", "coltt_b200_hnsw_build_stats", "coltt_b200_hnsw_build_fast_stats",
     "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_multi_search", "coltt_b200_hnsw_last_timing",
+    "coltt_b200_store_append_dev", "coltt_b200_store_fast_stats", "coltt_b200_fast_eps_rel",
 ]
 
 
@@ -96,6 +97,10 @@ def lib() -> C.CDLL:
     L.coltt_b200_store_last_timing.argtypes = [vp, f32p, C.c_int]
     L.coltt_b200_store_set_timing.argtypes = [vp, C.c_int]
     L.coltt_b200_kernel_launches.restype = C.c_uint64
+    L.coltt_b200_store_append_dev.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint64]
+    L.coltt_b200_store_fast_stats.argtypes = [vp, u64p]
+    L.coltt_b200_fast_eps_rel.argtypes = [C.c_uint32]
+    L.coltt_b200_fast_eps_rel.restype = C.c_float
     L.coltt_b200_multi_search.argtypes = [C.POINTER(vp), C.POINTER(f32p), i32p, C.c_int, C.c_int, u64p, f32p, i32p]
     for name in ABI_SYMBOLS:
         f = getattr(L, name)

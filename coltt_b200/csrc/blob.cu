@@ -56,6 +56,8 @@ static inline void put_be(uint8_t*& p, uint64_t v, int nb) {
 
 int Store::export_blob(void* buf, size_t* len) {
   std::shared_lock<std::shared_mutex> lk(mu);
+  if (elem == ELEM_F8E) return fail(COLTT_ERR_UNSUPPORTED, "SaveVertex has no layout for the F8_E4M3 extension (per-row scales)");
+  if (anonymous) return fail(COLTT_ERR_UNSUPPORTED, "store was filled from device memory: no host id map to export");
   const uint32_t es = elem_size(elem);
   const size_t per = 8 + 4 + (size_t)dim * es + 4;
   const size_t need = 16 * 8 + n_rows * per;
@@ -97,7 +99,9 @@ struct BlobReader {
 
 int Store::import_blob(const void* buf, size_t len) {
   std::unique_lock<std::shared_mutex> lk(mu);
+  if (elem == ELEM_F8E) return fail(COLTT_ERR_UNSUPPORTED, "LoadVertex has no layout for the F8_E4M3 extension (per-row scales)");
   COLTT_CUDA(cudaSetDevice(device));
+  { int wrc = wait_for_searches(); if (wrc) return wrc; }
   const uint32_t es = elem_size(elem);
   BlobReader r{(const uint8_t*)buf, len};
   std::vector<uint64_t> ids;

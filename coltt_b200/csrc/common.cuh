@@ -1,6 +1,7 @@
 // common.cuh — shared device/host helpers for libcoltt_b200 (sm_100a only).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,6 +112,29 @@ __host__ __device__ __forceinline__ uint32_t f8_compat_decode_bits(uint8_t in) {
   }
   coef &= 0x007fffffu;
   return sign | ((exp + (0x7f - 0xf)) << 23) | coef;
+}
+
+// F8_E4M3 store (builder-defined extension, no reference arithmetic — SURVEY F3; include/coltt_b200.h states the
+// format): OCP E4M3 "fn" codes, RNE, saturating, with one power-of-two scale per vector:
+//   s = 2^clamp(floor(log2(max|v|)) - 7, -40, 40)  (1 when max|v| is 0 or not finite),  c_i = e4m3(v_i / s),  x_i = s * dec(c_i).
+__device__ __forceinline__ float e4m3_scale_from_maxabs(float mx) {
+  if (!(mx <= 3.402823466e+38f) || mx == 0.0f) return 1.0f;
+  int e = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;          // floor(log2(mx)) for normal mx
+  if (((__float_as_uint(mx) >> 23) & 0xff) == 0) e = -127;          // subnormal: clamps below anyway
+  int es = e - 7;
+  es = es < -40 ? -40 : (es > 40 ? 40 : es);
+  return __uint_as_float((uint32_t)(es + 127) << 23);
+}
+__device__ __forceinline__ uint8_t e4m3_encode(float x) {   // cvt.rn.satfinite.e4m3x2.f32
+  return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float2 e4m3x2_decode(uint16_t c2) {   // cvt.rn.f16x2.e4m3x2: exact
+  const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)c2, __NV_E4M3);
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ float e4m3_decode(uint8_t c) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)c, __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
 }
 
 // ---- order-preserving float <-> uint32 (atomicMin/Max on bounds that may be negative) -------------

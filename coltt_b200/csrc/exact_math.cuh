@@ -16,6 +16,12 @@ __device__ __forceinline__ void load4(const uint8_t* p, const float* lut, float 
     float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
     float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else if (ELEM == ELEM_F8E) {
+    // E4M3 codes -> the UNSCALED decoded values (cvt.rn.f16x2.e4m3x2, exact); the caller applies the row's
+    // power-of-two scale (per element for L2, once per row for the dot product — same bits, see flat_scan.cu)
+    uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
+    const float2 a = e4m3x2_decode((uint16_t)(raw & 0xffffu)), b = e4m3x2_decode((uint16_t)(raw >> 16));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
   } else {
     uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
     v[0] = lut[raw & 0xff]; v[1] = lut[(raw >> 8) & 0xff]; v[2] = lut[(raw >> 16) & 0xff]; v[3] = lut[raw >> 24];
@@ -25,6 +31,7 @@ template <int ELEM>
 __device__ __forceinline__ float load1(const uint8_t* row, uint32_t idx, const float* lut) {
   if (ELEM == ELEM_F32) return reinterpret_cast<const float*>(row)[idx];
   if (ELEM == ELEM_F16) return __half2float(reinterpret_cast<const __half*>(row)[idx]);
+  if (ELEM == ELEM_F8E) return e4m3_decode(row[idx]);
   return lut[row[idx]];
 }
 
@@ -37,9 +44,11 @@ __device__ __forceinline__ float load1(const uint8_t* row, uint32_t idx, const f
 // fp32 rows keep the two roundings, and so does the f8-compat store: its decoder leaves a stray mantissa bit and
 // fp32-subnormal values for codes >= 0x80 (float8.go:233-266), whose products underflow.
 // (L2's (q-r)^2 has no such property: q-r may need > 24 bits.)
+// The E4M3 store has the same property with room to spare: both operands are (power of two) x (4 significant bits),
+// scales are clamped to 2^+-40, so every product has <= 8 significant bits and is exact.
 template <int ELEM>
 __device__ __forceinline__ float dot_step(float acc, float q, float r) {
-  if (ELEM == ELEM_F16) return __fmaf_rn(q, r, acc);
+  if (ELEM == ELEM_F16 || ELEM == ELEM_F8E) return __fmaf_rn(q, r, acc);
   return add_rn(acc, mul_rn(q, r));
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   __shared__ int warp_cnt_s[kScanWarps][QT];
   __shared__ uint32_t cta_kth_s[QT];   // best K-th bound any warp of this CTA has reached, order-encoded
 
-  constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
+  constexpr uint32_t ES = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);   // F8C and F8E: one byte
   const uint32_t W = kScanWarps, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t S = p.n_stages, CB = p.chunk_bytes, RS = CB + kRowPad;
   const uint32_t stage_bytes = kRowsPerWarp * RS;
@@ -61,17 +61,23 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   // Query groups of QT: grid.y groups run side by side, each CTA loops over the rest.  With `n_active`
   // the number of queries lives on the device (the FAST path's exact re-run of uncertified queries is
   // enqueued unconditionally and costs one empty wave when there is nothing to do); `q_map` then says
-  // which prepared query each compact index stands for.
-  const uint32_t nq_eff = p.n_active ? *p.n_active : p.nq;
+  // which prepared query each compact index stands for;
+  // `q_base` windows the compact list, so scratch lists stay bounded)
+  uint32_t nq_eff = p.nq;
+  if (p.n_active) {
+    const uint32_t na = *p.n_active;
+    nq_eff = na > p.q_base ? na - p.q_base : 0u;
+    if (nq_eff > p.nq) nq_eff = p.nq;
+  }
   for (uint32_t q0 = blockIdx.y * QT; q0 < nq_eff; q0 += gridDim.y * QT) {
   const uint32_t nqt = nq_eff - q0 < (uint32_t)QT ? nq_eff - q0 : (uint32_t)QT;
   for (uint32_t i = threadIdx.x; i < QT * p.q_stride; i += blockDim.x) {
     uint32_t qi = i / p.q_stride, d = i - qi * p.q_stride;
-    const uint32_t qsrc = qi < nqt ? (p.q_map ? p.q_map[q0 + qi] : q0 + qi) : 0u;
+    const uint32_t qsrc = qi < nqt ? (p.q_map ? p.q_map[p.q_base + q0 + qi] : q0 + qi) : 0u;
     q_s[i] = qi < nqt ? p.queries[(size_t)qsrc * p.q_stride + d] : 0.0f;
   }
   if (threadIdx.x < 8) {
-    const uint32_t qsrc = threadIdx.x < nqt ? (p.q_map ? p.q_map[q0 + threadIdx.x] : q0 + threadIdx.x) : 0u;
+    const uint32_t qsrc = threadIdx.x < nqt ? (p.q_map ? p.q_map[p.q_base + q0 + threadIdx.x] : q0 + threadIdx.x) : 0u;
     qn_s[threadIdx.x] = (threadIdx.x < nqt && METRIC == COLTT_COSINE) ? p.q_norm2[qsrc] : 0.0f;
   }
   if (lane == 0)
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   for (uint32_t t = 0; t < S && t < n_work; t++) issue(t);
 
   uint32_t gi = 0, c = 0;
-  float nb_pref = 0.0f, macc_pref = 0.0f;
+  float nb_pref = 0.0f, macc_pref = 0.0f, sc_pref = 1.0f;   // sc_pref: the row's E4M3 scale
   uint32_t slot_pref = 0;
   for (uint32_t t = 0; t < n_work; t++) {
     if (c == 0) {
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
       if (item_p < p.n_items) {
         slot_pref = p.subset ? p.subset[item_p] : item_p;
         if (METRIC == COLTT_COSINE) nb_pref = p.row_norm2[slot_pref];
+        if (ELEM == ELEM_F8E) sc_pref = p.row_scale[slot_pref];
         if (p.multi_acc && !p.multi_first) macc_pref = p.multi_acc[slot_pref];
       }
     }
@@ -149,6 +156,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
     for (uint32_t i8 = 0; i8 < n8; i8++) {
       float rv[4];
       load4<ELEM>(rb + i8 * 8 * ES, lut_s, rv);
+      if (ELEM == ELEM_F8E && METRIC != COLTT_COSINE) {   // (q - s*d)^2 needs the dequantized value itself
+        rv[0] = mul_rn(rv[0], sc_pref); rv[1] = mul_rn(rv[1], sc_pref); rv[2] = mul_rn(rv[2], sc_pref); rv[3] = mul_rn(rv[3], sc_pref);
+      }
 #pragma unroll
       for (int qi = 0; qi < QT; qi++) {
         const float4 qv = *reinterpret_cast<const float4*>(qb + (size_t)qi * p.q_stride + i8 * 8);
@@ -180,10 +190,15 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
         float tot = g == 0 ? add_rn(h, o) : add_rn(o, h);
         for (uint32_t d = full8; d < p.dim; d++) {  // scalar tail, avx.cpp:27-31 / :68-72
           float rv = load1<ELEM>(rowp, d - e0, lut_s);
+          if (ELEM == ELEM_F8E && METRIC != COLTT_COSINE) rv = mul_rn(rv, sc_pref);
           float qv = q_s[(size_t)qi * p.q_stride + d];
           if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
           else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
         }
+        // E4M3 rows: the dot product ran over the unscaled decoded values; the row's power-of-two scale multiplies every
+        // product and every partial sum exactly (no over/underflow: scales are clamped to 2^+-40), so applying it once
+        // here yields the bits of sum(q_i * (s*d_i)) in the reference order
+        if (ELEM == ELEM_F8E && METRIC == COLTT_COSINE) tot = mul_rn(tot, sc_pref);
         float score = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn_s[qi], nb) : sqrt_via_f64(tot);
         if (p.multi_acc) {
           // score += scoreHelper(sim) * (float32(ratio) / 100), unfused, in request order (multi_vector_vertex.go:110-115)
@@ -335,6 +350,7 @@ int launch_flat_scan(const ScanParams& p_in, const ScanPlan& plan, int elem, cud
   const bool cosine = p.metric == COLTT_COSINE;
   if (elem == ELEM_F32) return cosine ? launch_qt<ELEM_F32, COLTT_COSINE>(p, plan, stream) : launch_qt<ELEM_F32, COLTT_EUCLIDEAN>(p, plan, stream);
   if (elem == ELEM_F16) return cosine ? launch_qt<ELEM_F16, COLTT_COSINE>(p, plan, stream) : launch_qt<ELEM_F16, COLTT_EUCLIDEAN>(p, plan, stream);
+  if (elem == ELEM_F8E) return cosine ? launch_qt<ELEM_F8E, COLTT_COSINE>(p, plan, stream) : launch_qt<ELEM_F8E, COLTT_EUCLIDEAN>(p, plan, stream);
   return cosine ? launch_qt<ELEM_F8C, COLTT_COSINE>(p, plan, stream) : launch_qt<ELEM_F8C, COLTT_EUCLIDEAN>(p, plan, stream);
 }
 

@@ -11,8 +11,10 @@ static constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 
 static constexpr int kEpiThreads = 256;
 static constexpr int kEpiSets = 2;         // each set owns half of every tile's columns and its own per-query state
 static constexpr int kBN = 256;            // shard rows per tile (MMA N): one 128-cycle tcgen05.mma per K step
-static constexpr int kBK = 64;             // fp16 elements per K block of the resident query tile (128-byte swizzle rows)
-static constexpr int kBKB = 32;            // fp16 elements per shard-tile stage (64-byte swizzle rows)
+// Operand geometry is in BYTES, so the same kernels serve fp16 rows (kind::f16, 16 elements per MMA) and E4M3 rows
+// (kind::f8f6f4, 32 elements per MMA): one tcgen05.mma consumes 32 bytes of K from each operand row.
+static constexpr int kBK = 128;            // bytes per K block of the resident query tile (128-byte swizzle rows)
+static constexpr int kBKB = 64;            // bytes per row of a shard-tile stage (64-byte swizzle rows) = 2 MMAs
 
 // Role timers (clock64 around every wait) are compiled in only with -DCOLTT_K2_PROF=1: the reads sit on the
 // single-thread MMA issue path, where they cost more than the work they measure.
@@ -51,6 +53,32 @@ __device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t a_des
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// kind::f8f6f4 with both operands E4M3 (instruction-descriptor formats 0/0, the same bits as F16/F16 under kind::f16);
+// SASS: UTCQMMA
+__device__ __forceinline__ void umma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool FP8>
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (FP8) umma_f8_ss(d, a, b, idesc, acc); else umma_f16_ss(d, a, b, idesc, acc);
+}
+template <bool FP8>
+__device__ __forceinline__ void umma_ss_pair(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (FP8) umma_f8_ss_pair(d, a, b, idesc, acc); else umma_f16_ss_pair(d, a, b, idesc, acc);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -127,13 +155,26 @@ __device__ __forceinline__ float pick32(const float (&k)[32], uint32_t c) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// Epilogue of the filter GEMM (warps 2-5, thread = query).  For every 256-row tile: tcgen05.ld the
+// Epilogue of the filter GEMM (warps 2-9, thread = query).  For every 256-row tile: tcgen05.ld the
 // 128x256 fp32 accumulator 32 columns at a time, one FFMA turns each score into a "larger is better" key
-// (cosine: +-dot/||row||; L2: +-(2 dot - ||row||^2)), a max tree and ONE warp vote per 32 scores decide
-// whether anything beats the running K'-th bound held in a register; the rare survivors are appended to an
-// L2-resident per-(column,query) buffer.  top[] = this column's KP best keys (registers, sorted).
-// thr = max(top[KP-1], G), G = min over KP groups of columns of the best key any column of the group has
-// published: KP different columns each hold a row at least that good, so G bounds the shard-wide K'-th key.
+// (cosine: +-dot * s_row/||row||; L2: +-(2 dot - ||row||^2)), a max tree and ONE warp vote per 32 scores decide
+// whether anything beats the running bound held in a register; the rare survivors are appended to an
+// L2-resident per-(column,query) buffer.  A "column" is one epilogue set of one CTA: the columns partition
+// the shard's rows.
+//
+// The bound `thr` must never exceed the K'-th best key of the whole shard (K' = p.kprime >= K): a row is
+// dropped only when key <= thr.  Two sound sources, generalised from one scheme — every column keeps its own
+// KP best keys in registers (top[], sorted) and PUBLISHES one order statistic of them; with the columns
+// split into `groups` classes (column c is in class c % groups),
+//     G = min over classes of (max over the class's columns of the published value)
+// has at least `groups` distinct columns holding a published value >= G:
+//   * p.pub_kth == 0 (K' = KP: top-10 / top-24): a column publishes its BEST key, groups = KP  => KP rows >= G;
+//     its own KP-th best, top[KP-1], is a second bound (KP local rows >= it);
+//   * p.pub_kth == 1 (K' = groups * KP: top-100): a column publishes its KP-th best key, so each of the `groups`
+//     columns vouches for KP rows >= G  => groups * KP = K' rows >= G.  top[KP-1] alone vouches for only KP < K'
+//     rows, so here thr comes from G only.
+// (A wrong bound could never return a wrong answer — rerank.cu certifies the result against the bound the
+// survivors were cut at and sends uncertified queries to the exact kernel — but it would cost that re-run.)
 //   col / n_cols: this CTA's index among the CTAs that see this query, and how many there are
 //   tile0 / tile_stride: the tiles this CTA processes
 //   arrive_tempty(buf): releases accumulator `buf` to the MMA issuer (local or leader-CTA barrier)
@@ -150,17 +191,19 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
   const uint32_t q = q_tile0 + ql;
   const uint32_t et = threadIdx.x - 64;                // 0..255 among the epilogue threads
   constexpr uint32_t CHUNKS = kBN / 32 / kEpiSets;     // 32-column chunks per set per tile
-  col = col * kEpiSets + set;                          // every set is its own "column" of candidates / published maxima
+  col = col * kEpiSets + set;                          // every set is its own "column" of candidates / published values
   n_cols *= kEpiSets;
   buf_slot = buf_slot * kEpiSets + set;
   const bool q_valid = q < p.nq;
+  const bool pub_kth = p.pub_kth != 0;
+  const uint32_t groups = p.groups;
   const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
   float top[KP];
 #pragma unroll
   for (int i = 0; i < KP; i++) top[i] = NEG_INF;
   float my_best = NEG_INF;
   uint32_t next_sweep = 1;
-  const bool sweeping = q_valid && n_cols >= (uint32_t)KP;
+  const bool sweeping = q_valid && n_cols >= groups;
   float thr = q_valid ? NEG_INF : POS_INF;
   bool overflowed = false;
   uint32_t cnt = 0;
@@ -169,11 +212,11 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
   uint32_t ti = 0;
   long long w_tfull = 0, t_start_e = K2_NOW(), c_bar = 0, c_hot = 0, c_slow = 0, c_sweep = 0, n_slow = 0;
 
-  auto coef_store = [&](uint32_t idx, uint32_t row, float n2) {
+  auto coef_store = [&](uint32_t idx, uint32_t row, float n2, float sc) {
     float a = 0.0f, b = NEG_INF;
     if (row < p.n_rows) {
       if (p.metric == COLTT_COSINE) {
-        if (n2 > 0.0f) { a = p.nearest ? rsqrtf(n2) : -rsqrtf(n2); b = 0.0f; }
+        if (n2 > 0.0f) { a = (p.nearest ? rsqrtf(n2) : -rsqrtf(n2)) * sc; b = 0.0f; }
         else b = p.nearest ? NEG_INF : POS_INF;       // zero row: NaN distance, last in T order
       } else {
         a = p.nearest ? 2.0f : -2.0f;
@@ -183,29 +226,51 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     coef_a[idx] = a;
     coef_b[idx] = b;
   };
-  // ||row||^2 of the next tile is fetched while the current one is processed (one row per epilogue thread)
-  float n2_a = 0.0f;
+  // cross-column bound (see the header comment); reads n_cols published values of this query
+  auto sweep = [&]() {
+    float gmax[KP];
+#pragma unroll
+    for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
+    for (uint32_t c0 = 0; c0 < n_cols; c0 += groups) {
+#pragma unroll
+      for (int i = 0; i < KP; i++) {
+        if ((uint32_t)i < groups) {
+          const float pv = c0 + i < n_cols ? __ldcg(p.pub + (size_t)(c0 + i) * p.nq + q) : NEG_INF;
+          gmax[i] = fmaxf(gmax[i], pv);   // fmaxf ignores the NaN "nothing published yet" marker
+        }
+      }
+    }
+    float G = gmax[0];
+#pragma unroll
+    for (int i = 1; i < KP; i++) if ((uint32_t)i < groups) G = fminf(G, gmax[i]);
+    thr = fmaxf(thr, G);
+  };
+  // ||row||^2 (and the E4M3 row scale) of the next tile are fetched while the current one is processed (one row per epilogue thread)
+  float n2_a = 0.0f, sc_a = 1.0f;
   {
     const uint32_t ra = tile0 * kBN + et;
-    if (tile0 < n_tiles && ra < p.n_rows) n2_a = p.row_norm2[ra];
+    if (tile0 < n_tiles && ra < p.n_rows) { n2_a = p.row_norm2[ra]; if (p.row_scale) sc_a = p.row_scale[ra]; }
   }
   for (uint32_t t = tile0; t < n_tiles; t += tile_stride, ti++) {
     const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
     const uint32_t row0 = t * kBN;
     const long long cb0 = K2_NOW();
-    coef_store(et, row0 + et, n2_a);
+    coef_store(et, row0 + et, n2_a, sc_a);
     named_bar_sync(1, kEpiThreads);                      // coefficients of this tile visible
     c_bar += K2_NOW() - cb0;
     {
       const uint32_t ra = (t + tile_stride) * kBN + et;
       n2_a = ra < p.n_rows ? p.row_norm2[ra] : 0.0f;
+      sc_a = (p.row_scale && ra < p.n_rows) ? p.row_scale[ra] : 1.0f;
     }
     const long long ce0 = K2_NOW();
     mbar_wait(smem_u32(tfull_bar + buf), bph);
     w_tfull += K2_NOW() - ce0;
     tc_fence_after();
     const uint32_t tbase = tmem_base + ((quarter * 32) << 16) + buf * kBN + set * CHUNKS * 32;
+#if COLTT_K2_PROF
     const bool drain_only = (p.dbg_flags & 1u) != 0;     // pipeline-speed probe
+#endif
     uint32_t v[32];
     tmem_ld32(tbase, v);
 #pragma unroll 1
@@ -213,7 +278,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
       const uint32_t half = set * CHUNKS + hc;
       const long long cl0 = K2_NOW();
       tmem_wait_ld();
-      if (p.dbg_acc && q_valid) {
+      if (p.dbg_acc && q_valid) {                        // test hook: raw accumulators
 #pragma unroll
         for (int c = 0; c < 32; c++) {
           const uint32_t row = row0 + half * 32 + c;
@@ -240,7 +305,9 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
         __syncwarp();
         if (lane == 0) arrive_tempty(buf);               // this warp is done with the accumulator of tile ti
       }
+#if COLTT_K2_PROF
       if (drain_only) continue;
+#endif
       float kmax = NEG_INF;
 #pragma unroll
       for (int c4 = 0; c4 < 8; c4++)
@@ -273,14 +340,16 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
                   top[i - 1] = hi;
                   top[i] = lo;
                 }
-                thr = fmaxf(thr, top[KP - 1]);
+                if (!pub_kth) thr = fmaxf(thr, top[KP - 1]);                  // KP = K' local rows are at least this good
+                else if (top[KP - 1] > NEG_INF) __stcg(my_pub, top[KP - 1]);  // this column vouches for KP rows >= it
               }
-              if (kk > my_best) { my_best = kk; __stcg(my_pub, kk); }
+              if (!pub_kth && kk > my_best) { my_best = kk; __stcg(my_pub, kk); }
             }
           }
-          // the buffer must keep room for the next 32 columns: drop what fell below the bound
-          // (rare: the buffer is sized so that a typical scan never fills it); loads go out 8 at a time
+          // the buffer must keep room for the next 32 columns: refresh the cross-column bound, then drop what fell
+          // below it (rare: the buffer is sized so that a typical scan never fills it); loads go out 8 at a time
           if (cnt + 32 > C) {
+            if (sweeping) sweep();
             uint32_t w2 = 0;
             for (uint32_t s0 = 0; s0 < cnt; s0 += 8) {
               GemmCand e8[8];
@@ -291,7 +360,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
                 if (s0 + u < cnt && e8[u].key >= thr) { my_buf[(size_t)w2 * 128] = e8[u]; w2++; }
             }
             cnt = w2;
-            if (cnt + 32 > C) {   // more than C-32 rows tie at the bound: give this query to the exact path
+            if (cnt + 32 > C) {   // more than C-32 rows at or above the bound: give this query to the exact path
               overflowed = true;
               cnt = 0;
               thr = POS_INF;
@@ -308,23 +377,11 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     if (sweeping && !overflowed && ti == next_sweep) {
       const long long cw0 = K2_NOW();
       next_sweep = ti * 2;
-      float gmax[KP];
-#pragma unroll
-      for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
-      for (uint32_t c0 = 0; c0 < n_cols; c0 += KP) {
-#pragma unroll
-        for (int i = 0; i < KP; i++) {
-          const float pv = c0 + i < n_cols ? __ldcg(p.pub + (size_t)(c0 + i) * p.nq + q) : NEG_INF;
-          gmax[i] = fmaxf(gmax[i], pv);   // fmaxf ignores the NaN "nothing published yet" marker
-        }
-      }
-      float G = gmax[0];
-#pragma unroll
-      for (int i = 1; i < KP; i++) G = fminf(G, gmax[i]);
-      thr = fmaxf(thr, G);
+      sweep();
       c_sweep += K2_NOW() - cw0;
     }
   }
+#if COLTT_K2_PROF
   if (p.dbg_prof && et == 0) {   // set 0, quarter 2's first lane
     p.dbg_prof[(size_t)prof_slot * 8 + 5] = (unsigned long long)w_tfull;
     p.dbg_prof[(size_t)prof_slot * 8 + 6] = (unsigned long long)(K2_NOW() - t_start_e);
@@ -336,7 +393,11 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     p.dbg_prof2[(size_t)prof_slot * 8 + 4] = (unsigned long long)cnt;
     p.dbg_prof2[(size_t)prof_slot * 8 + 5] = (unsigned long long)c_slow;
   }
+#else
+  (void)w_tfull; (void)t_start_e; (void)c_bar; (void)c_hot; (void)c_slow; (void)c_sweep; (void)n_slow; (void)prof_slot;
+#endif
   // ---- hand the survivors to rerank.cu: [query][column][slot]; publish the bound they were cut at
+  if (sweeping && !overflowed) sweep();   // the other columns have published more since the last scheduled sweep
   if (q_valid) {
     const uint32_t CO = p.cand_out_cap;
     GemmCand* out = p.cand_out + ((size_t)q * n_cols + col) * CO;

@@ -1,5 +1,6 @@
 // gemm_filter.cu — K2: batched query x shard distance as a tcgen05 GEMM with a fused
-// threshold top-K' epilogue (COLTT_MATH_FAST), for fp16 rows ("bf16"/f16 stores).
+// threshold top-K' epilogue (COLTT_MATH_FAST), for fp16 rows ("bf16"/f16 stores, tcgen05 kind::f16) and
+// E4M3 rows (the builder-defined F8_E4M3 store, kind::f8f6f4 — same byte geometry, twice the elements per MMA).
 //
 // What it replaces: the same VertexSearch hot loop as flat_scan.cu
 // (edge/bf16_vectorstore.go:131-186 -> bf16_quantization.go:33-43 -> pkg/distance), for a
@@ -35,15 +36,15 @@
 
 namespace coltt {
 
-template <int KP>
+template <int KP, bool FP8>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_pf, GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // no static __shared__ in this kernel: the window base is 1024-aligned
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t NS = p.n_stages, KB = p.kblocks;
-  constexpr uint32_t STAGE_BYTES = kBN * kBKB * 2;  // 256 rows x 64 B = 16 KB
-  constexpr uint32_t ABLK_BYTES = 128 * kBK * 2;    // 128 queries x 128 B = 16 KB per K block
+  constexpr uint32_t STAGE_BYTES = kBN * kBKB;      // 256 rows x 64 B = 16 KB
+  constexpr uint32_t ABLK_BYTES = 128 * kBK;        // 128 queries x 128 B = 16 KB per K block
   const uint32_t NSTEP = KB * (kBK / kBKB);         // shard-tile stages per tile (2 per query K block)
 
   uint8_t* a_smem = smem;                                   // [KB][128 rows][128 B], 128B-swizzled, resident
@@ -93,7 +94,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
     __syncwarp();
     uint32_t s = 0, ph = 0;
+#if COLTT_K2_PROF
     const bool do_pf = (p.dbg_flags & 2u) == 0;
+#else
+    constexpr bool do_pf = true;
+#endif
     const uint32_t pf_mask = p.pf_inner / kBKB - 1;          // pf_inner / kBKB is a power of two
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
     if (do_pf && blockIdx.x < n_tiles && elect_one())
@@ -141,8 +146,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         tc_fence_after();
         const uint64_t b_desc = b_desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
         if (elect_one()) {
-          umma_f16_ss(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
-          umma_f16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);     // +32 B: the next 16 K elements
+          umma_ss<FP8>(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
+          umma_ss<FP8>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);     // +32 B: the next MMA's K slice
           umma_commit(empty0 + s * 8);                    // frees the smem stage when these MMAs retire
         }
         __syncwarp();
@@ -152,11 +157,15 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (elect_one()) umma_commit(smem_u32(tfull_bar + buf));   // accumulator complete
       __syncwarp();
     }
+#if COLTT_K2_PROF
     if (p.dbg_prof && lane == 0) {
       p.dbg_prof[(size_t)cta_lin * 8 + 2] = (unsigned long long)w_tempty;
       p.dbg_prof[(size_t)cta_lin * 8 + 3] = (unsigned long long)w_full;
       p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(K2_NOW() - t_start);
     }
+#else
+    (void)w_tempty; (void)w_full; (void)t_start;
+#endif
   } else {
     auto arrive = [&](uint32_t buf) { mbar_arrive(smem_u32(tempty_bar + buf)); };
     filter_epilogue<KP>(p, tmem_base, coef_a, coef_b, tfull_bar, arrive, blockIdx.x, gridDim.x, n_tiles, q_tile0, blockIdx.x, gridDim.x, cta_lin, cta_lin);
@@ -186,30 +195,47 @@ static EncodeTiledFn encode_tiled_fn() {
 int launch_gemm_filter_pair(const CUtensorMap& tm, const CUtensorMap& tmq, const CUtensorMap& tmpf, const GemmParams& p, const GemmPlan& plan,
                             cudaStream_t stream);
 
-int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan) {
-  const uint32_t kblocks = (dim + kBK - 1) / kBK;
-  if (k > 24) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 24 is served by the exact path");
-  const uint32_t kprime = k <= 10 ? 16 : 32;         // K' (register-resident per query); margin for the certificate
-  const uint32_t cap = 256;                          // working slots per (CTA set, query) in L2-resident global memory
-  const uint32_t out_cap = 2 * kprime + 16;          // survivors handed to rerank.cu per (CTA set, query)
+// Chooses the bound scheme (gemm_common.cuh) and the launch shape for a shard of `row_bytes`-wide rows.
+//   top-k <= 10: K' = 16, KP = 16 registers, columns publish their best key;   top-k <= 24: K' = 32, KP = 32;
+//   top-k <= 200: KP = 16, columns publish their 16th best key, groups = ceil(1.25 k / 16), K' = 16 groups
+//   (top-100: groups 8, K' = 128).  Larger k, or fewer columns than groups, is served by the exact path.
+int plan_gemm_filter(uint32_t row_bytes, bool fp8, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan) {
+  const uint32_t kblocks = (row_bytes + kBK - 1) / kBK;
+  uint32_t kp, kprime, pub_kth, groups, cap, out_cap;
+  if (k <= 10) { kp = 16; kprime = 16; pub_kth = 0; groups = 16; cap = 256; out_cap = 48; }
+  else if (k <= 24) { kp = 32; kprime = 32; pub_kth = 0; groups = 32; cap = 256; out_cap = 80; }
+  else {
+    kp = 16; pub_kth = 1;
+    groups = (k + k / 4 + 15) / 16;
+    if (groups > 16) return fail(COLTT_ERR_UNSUPPORTED, "FAST: top-k above 200 is served by the exact path");
+    kprime = groups * 16;
+    cap = 512;       // two tiles of rows arrive before the first cross-column bound
+    out_cap = 64;    // survivors per column at the end: K' * (a small factor) / n_cols, far below this
+  }
   static const char* pair_env = getenv("COLTT_FAST_PAIR");
   const bool pair = nq > 128 && !(pair_env && atoi(pair_env) == 0);   // CTA pairs (cta_group::2) once there are two query tiles
-  const size_t a_bytes = (size_t)kblocks * 128 * kBK * 2;
-  const size_t stage = (size_t)(pair ? kBN / 2 : kBN) * kBKB * 2;
+  // stage width of the CTA-pair kernel: COLTT_FAST_SB=64|128 (experiment knob; the default is the measured better one)
+  static const uint32_t env_sb = [] { const char* e = getenv("COLTT_FAST_SB"); const int v = e ? atoi(e) : 64; return v == 128 ? 128u : 64u; }();
+  const uint32_t sb = pair ? env_sb : (uint32_t)kBKB;
+  const size_t a_bytes = (size_t)kblocks * 128 * kBK;
+  const size_t stage = (size_t)(pair ? kBN / 2 : kBN) * sb;
   const size_t misc = 2 * kBN * 4 + 256;
   const size_t total = 227 * 1024;
   if (a_bytes + misc + 2 * stage > total)
-    return fail(COLTT_ERR_UNSUPPORTED, "FAST: query tile does not fit shared memory (dim > 768 fp16)");
+    return fail(COLTT_ERR_UNSUPPORTED, "FAST: query tile does not fit shared memory (rows wider than 1536 bytes)");
   uint32_t ns = (uint32_t)((total - a_bytes - misc) / stage);
   if (ns > 8) ns = 8;
-  static const char* ns_env = getenv("COLTT_FAST_NS");     // debug: shrink the stage ring
-  if (ns_env && atoi(ns_env) >= 2 && (uint32_t)atoi(ns_env) < ns) ns = (uint32_t)atoi(ns_env);
   plan->kblocks = kblocks;
   plan->kprime = kprime;
+  plan->kp = kp;
+  plan->pub_kth = pub_kth;
+  plan->groups = groups;
   plan->cand_cap = cap;
   plan->cand_out_cap = out_cap;
   plan->n_stages = ns;
   plan->pair = pair ? 1 : 0;
+  plan->fp8 = fp8 ? 1 : 0;
+  plan->sb = sb;
   if (pair) {
     plan->grid_y = (nq + 255) / 256;
     uint32_t pairs = (uint32_t)(n_sms / 2) / plan->grid_y;
@@ -228,22 +254,23 @@ int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan*
   return COLTT_OK;
 }
 
-static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner,
+// All maps describe BYTES (dtype UINT8): the swizzle patterns and box shapes are byte geometry, identical for fp16 and E4M3.
+static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner,
                       uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(COLTT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t gdim[2] = {inner, rows};
+  const cuuint64_t gdim[2] = {inner_bytes, rows};
   const cuuint64_t gstride[1] = {row_stride_bytes};
   const cuuint32_t box[2] = {box_inner, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(COLTT_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return COLTT_OK;
 }
 
-// number of CTAs that will see one query for this plan and shard size (the [query][column] stride of
-// cand_out / cand_cnt / pub)
+// number of columns (epilogue sets of the CTAs that see one query) for this plan and shard size: the [query][column]
+// stride of cand_out / cand_cnt / pub
 uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows) {
   const uint32_t n_tiles = (n_rows + kBN - 1) / kBN;
   return (plan.n_cols < n_tiles ? plan.n_cols : n_tiles) * kEpiSets;
@@ -258,52 +285,50 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   CUtensorMap& tmq = *reinterpret_cast<CUtensorMap*>(mc.maps[1]);
   CUtensorMap& tmpf = *reinterpret_cast<CUtensorMap*>(mc.maps[2]);
   GemmPlan plan = plan_in;
-  const uint32_t n_tiles = (p_in.n_rows + kBN - 1) / kBN;
   const uint32_t cols = gemm_filter_cols(plan, p_in.n_rows) / kEpiSets;   // CTAs (or pairs) along x
-  static const char* pfi_env = getenv("COLTT_PF_INNER");
-  static const char* pfd_env = getenv("COLTT_PF_DIST");
-  uint32_t pf_inner = pfi_env ? (uint32_t)atoi(pfi_env) : 128u, pf_dist = pfd_env ? (uint32_t)atoi(pfd_env) : 1u;
-  if (pf_inner != 32 && pf_inner != 64 && pf_inner != 128 && pf_inner != 256) pf_inner = 64;
-  if (pf_dist < 1 || pf_dist > 4096) pf_dist = 16;
+  if (cols * kEpiSets < plan.groups) return fail(COLTT_ERR_UNSUPPORTED, "FAST: fewer columns than bound classes");
+  const uint32_t row_bytes = p_in.dim * (plan.fp8 ? 1u : 2u);
+  const uint32_t pf_inner = 256;                                           // bytes per L2-prefetch request row
   const uint32_t box_rows = plan.pair ? kBN / 2 : kBN;
   int rc;
-  if (mc.rows != d_rows || mc.n_rows != p_in.n_rows || mc.dim != p_in.dim || mc.row_stride != row_stride || mc.box_rows != box_rows ||
-      mc.pf_inner != pf_inner) {
+  if (mc.rows != d_rows || mc.n_rows != p_in.n_rows || mc.row_bytes != row_bytes || mc.row_stride != row_stride || mc.box_rows != box_rows ||
+      mc.pf_inner != pf_inner || mc.sb != plan.sb) {
     mc.rows = nullptr;
-    // shard tile stages: 256 (or 128 per CTA of a pair) rows x 32 fp16 (64 B), 64B swizzle
-    rc = encode_map(&tm, d_rows, p_in.dim, p_in.n_rows, row_stride, kBKB, box_rows, CU_TENSOR_MAP_SWIZZLE_64B);
+    // shard tile stages: 256 (or 128 per CTA of a pair) rows x 64 B, 64B swizzle
+    rc = encode_map(&tm, d_rows, row_bytes, p_in.n_rows, row_stride, plan.sb, box_rows, plan.sb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     // L2 prefetch view of the shard: whole 128-byte lines, 128 rows per request
-    rc = encode_map(&tmpf, d_rows, p_in.dim, p_in.n_rows, row_stride, pf_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = encode_map(&tmpf, d_rows, row_bytes, p_in.n_rows, row_stride, pf_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    mc.rows = d_rows; mc.n_rows = p_in.n_rows; mc.dim = p_in.dim; mc.row_stride = row_stride; mc.box_rows = box_rows; mc.pf_inner = pf_inner;
+    mc.rows = d_rows; mc.n_rows = p_in.n_rows; mc.row_bytes = row_bytes; mc.row_stride = row_stride; mc.box_rows = box_rows; mc.pf_inner = pf_inner; mc.sb = plan.sb;
   }
-  if (mc.q != p_in.q_f16 || mc.nq != p_in.nq || mc.q_stride != p_in.q_stride) {
+  if (mc.q != p_in.q_lowered || mc.nq != p_in.nq || mc.q_stride != p_in.q_stride) {
     mc.q = nullptr;
-    // queries: [nq][q_stride] fp16, zero padded to kblocks*64 columns; box = 64 x 128 rows, 128B swizzle
-    rc = encode_map(&tmq, p_in.q_f16, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride * 2, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    // queries: [nq][q_stride bytes], zero padded to kblocks*128 bytes; box = 128 B x 128 rows, 128B swizzle
+    rc = encode_map(&tmq, p_in.q_lowered, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    mc.q = p_in.q_f16; mc.nq = p_in.nq; mc.q_stride = p_in.q_stride;
+    mc.q = p_in.q_lowered; mc.nq = p_in.nq; mc.q_stride = p_in.q_stride;
   }
   GemmParams p = p_in;
   p.rows = static_cast<const uint8_t*>(d_rows);
   p.row_stride = row_stride;
   p.pf_inner = pf_inner;
-  p.pf_dist = pf_dist;
   p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.cand_out_cap = plan.cand_out_cap; p.n_stages = plan.n_stages;
+  p.pub_kth = plan.pub_kth; p.groups = plan.groups;
   if (plan.pair) {
     plan.grid_x = 2 * cols;
     return launch_gemm_filter_pair(tm, tmq, tmpf, p, plan, stream);
   }
-  (void)n_tiles;
   dim3 grid(cols, plan.grid_y);
-  if (plan.kprime == 16) {
-    { int arc = kernel_attrs(gemm_filter_kernel<16>, plan.smem_bytes); if (arc) return arc; }
-    gemm_filter_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
-  } else {
-    { int arc = kernel_attrs(gemm_filter_kernel<32>, plan.smem_bytes); if (arc) return arc; }
-    gemm_filter_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
+#define COLTT_K2(KPV, F8V)                                                                          \
+  {                                                                                                 \
+    auto kfn = gemm_filter_kernel<KPV, F8V>;                                                        \
+    { int arc = kernel_attrs(kfn, plan.smem_bytes); if (arc) return arc; }                          \
+    kfn<<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);                         \
   }
+  if (plan.kp == 16) { if (plan.fp8) COLTT_K2(16, true) else COLTT_K2(16, false) }
+  else { if (plan.fp8) COLTT_K2(32, true) else COLTT_K2(32, false) }
+#undef COLTT_K2
   count_launch();
   COLTT_CUDA(cudaGetLastError());
   return COLTT_OK;

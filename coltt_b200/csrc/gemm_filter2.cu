@@ -16,7 +16,9 @@
 
 namespace coltt {
 
-template <int KP>
+// SB = bytes per row of a shard-tile stage: 64 (64B swizzle, 2 MMAs per stage) or 128 (128B swizzle, 4 MMAs per stage
+// and half as many barrier round trips per byte; chosen by the plan)
+template <int KP, bool FP8, int SB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_q,
                         const __grid_constant__ CUtensorMap tmap_pf, GemmParams p) {
@@ -24,9 +26,10 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t NS = p.n_stages, KB = p.kblocks;
   constexpr uint32_t HALF_ROWS = kBN / 2;                   // shard rows each CTA of the pair loads
-  constexpr uint32_t STAGE_BYTES = HALF_ROWS * kBKB * 2;    // 128 rows x 64 B = 8 KB per CTA per stage
-  constexpr uint32_t ABLK_BYTES = 128 * kBK * 2;
-  const uint32_t NSTEP = KB * (kBK / kBKB);
+  constexpr uint32_t STAGE_BYTES = HALF_ROWS * SB;          // 128 rows x 64 B = 8 KB (or x 128 B = 16 KB) per CTA per stage
+  constexpr uint32_t ABLK_BYTES = 128 * kBK;
+  constexpr uint32_t MPS = SB / 32;                         // tcgen05.mma per stage
+  const uint32_t NSTEP = KB * (kBK / SB);
 
   uint8_t* a_smem = smem;
   uint8_t* b_stages = a_smem + (size_t)KB * ABLK_BYTES;     // [NS][128 rows][64 B], 64B-swizzled
@@ -80,11 +83,15 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     // the L2 prefetch of the next tile (same K slice, one tile ahead) after it.
     uint32_t s = 0, ph = 0;
     const int row_off = (int)(rank * HALF_ROWS);
+#if COLTT_K2_PROF
     const bool do_pf = (p.dbg_flags & 2u) == 0;
-    const uint32_t pf_mask = p.pf_inner / kBKB - 1;          // pf_inner / kBKB is a power of two
+#else
+    constexpr bool do_pf = true;
+#endif
+    const uint32_t pf_mask = p.pf_inner / SB - 1;            // pf_inner / SB is a power of two
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
     if (do_pf && pair < n_tiles && elect_one())
-      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), (int)(pair * kBN) + row_off);
+      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * SB), (int)(pair * kBN) + row_off);
     __syncwarp();
     for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
       const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
@@ -94,8 +101,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (elect_one()) {
           // the leader's barrier collects both halves: it expects 2 x STAGE_BYTES, each CTA's load signals it
           if (rank == 0) mbar_arrive_expect_tx(full0 + s * 8, 2 * STAGE_BYTES);
-          tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
-          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), row_pf);
+          tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)(st * SB), row, full0 + s * 8);
+          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * SB), row_pf);
         }
         __syncwarp();
         if (++s == NS) { s = 0; ph ^= 1; }
@@ -112,7 +119,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
       uint32_t s = 0, ph = 0, ti = 0;
       long long w_tempty = 0, w_full = 0, t_start = K2_NOW();
       const uint64_t a_desc0 = make_desc_sw128(smem_u32(a_smem));
-      const uint64_t b_desc0 = make_desc_sw64(smem_u32(b_stages));
+      const uint64_t b_desc0 = SB == 128 ? make_desc_sw128(smem_u32(b_stages)) : make_desc_sw64(smem_u32(b_stages));
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       for (uint32_t t = pair; t < n_tiles; t += n_pairs, ti++) {
         const uint32_t buf = ti & 1, bph = (ti >> 1) & 1;
@@ -129,22 +136,28 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
           tc_fence_after();
           const uint64_t b_desc = b_desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
           if (elect_one()) {
-            umma_f16_ss_pair(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
-            umma_f16_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);       // +32 B: the next 16 K elements
+            umma_ss_pair<FP8>(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
+#pragma unroll
+            for (uint32_t m = 1; m < MPS; m++) umma_ss_pair<FP8>(d_tmem, a_desc + 2 * m, b_desc + 2 * m, idesc, 1u);   // +32 B of K each
             umma_commit_pair(empty0 + s * 8, 3);             // stage free in both CTAs
           }
           __syncwarp();
-          a_desc += (st & 1) ? (uint64_t)((ABLK_BYTES - 64) >> 4) : 4ull;    // +64 B inside a K block, then the next block
+          if (SB == 128) a_desc += (uint64_t)(ABLK_BYTES >> 4);              // one whole K block per stage
+          else a_desc += (st & 1) ? (uint64_t)((ABLK_BYTES - 64) >> 4) : 4ull;    // +64 B inside a K block, then the next block
           if (++s == NS) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit_pair(smem_u32(tfull_bar + buf), 3);   // accumulator ready in both CTAs
         __syncwarp();
       }
+#if COLTT_K2_PROF
       if (p.dbg_prof && lane == 0) {
         p.dbg_prof[(size_t)cta_lin * 8 + 2] = (unsigned long long)w_tempty;
         p.dbg_prof[(size_t)cta_lin * 8 + 3] = (unsigned long long)w_full;
         p.dbg_prof[(size_t)cta_lin * 8 + 4] = (unsigned long long)(K2_NOW() - t_start);
       }
+#else
+      (void)w_tempty; (void)w_full; (void)t_start;
+#endif
     }
   } else {
     auto arrive = [&](uint32_t buf) { mbar_arrive_cluster(smem_u32(tempty_bar + buf), 0); };   // on the leader's barrier
@@ -160,13 +173,17 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 int launch_gemm_filter_pair(const CUtensorMap& tm, const CUtensorMap& tmq, const CUtensorMap& tmpf, const GemmParams& p, const GemmPlan& plan,
                             cudaStream_t stream) {
   dim3 grid(plan.grid_x, plan.grid_y);
-  if (plan.kprime == 16) {
-    { int arc = kernel_attrs(gemm_filter_pair_kernel<16>, plan.smem_bytes); if (arc) return arc; }
-    gemm_filter_pair_kernel<16><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
-  } else {
-    { int arc = kernel_attrs(gemm_filter_pair_kernel<32>, plan.smem_bytes); if (arc) return arc; }
-    gemm_filter_pair_kernel<32><<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);
+#define COLTT_K2P(KPV, F8V, SBV)                                                                    \
+  {                                                                                                 \
+    auto kfn = gemm_filter_pair_kernel<KPV, F8V, SBV>;                                              \
+    { int arc = kernel_attrs(kfn, plan.smem_bytes); if (arc) return arc; }                          \
+    kfn<<<grid, kGemmThreads, plan.smem_bytes, stream>>>(tm, tmq, tmpf, p);                         \
   }
+#define COLTT_K2P_SB(KPV, F8V) { if (plan.sb == 128) COLTT_K2P(KPV, F8V, 128) else COLTT_K2P(KPV, F8V, 64) }
+  if (plan.kp == 16) { if (plan.fp8) COLTT_K2P_SB(16, true) else COLTT_K2P_SB(16, false) }
+  else { if (plan.fp8) COLTT_K2P_SB(32, true) else COLTT_K2P_SB(32, false) }
+#undef COLTT_K2P_SB
+#undef COLTT_K2P
   count_launch();
   COLTT_CUDA(cudaGetLastError());
   return COLTT_OK;

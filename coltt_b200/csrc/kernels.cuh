@@ -4,7 +4,9 @@
 
 namespace coltt {
 
-enum { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_F8C = 2 };
+// ELEM_F8C: the reference's literal (broken) 8-bit code; ELEM_F8E: builder-defined OCP E4M3 codes + one power-of-two
+// scale per row (common.cuh)
+enum { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_F8C = 2, ELEM_F8E = 3 };
 __host__ __device__ inline uint32_t elem_size(int e) { return e == ELEM_F32 ? 4u : (e == ELEM_F16 ? 2u : 1u); }
 
 // ---- prep.cu ---------------------------------------------------------------------------
@@ -25,6 +27,9 @@ struct PrepParams {
   uint32_t deq_stride;
   __half* f16_out;        // nullable: fp16 copy [n][f16_stride], zero padded
   uint32_t f16_stride;
+  float* scale_out;       // ELEM_F8E: per-vector scale, indexed like norm2_out
+  uint8_t* code_out;      // nullable (ELEM_F8E queries): the lowered codes [n][code_stride], zero padded
+  uint32_t code_stride;
   uint32_t* fill_ptr[3];  // nullable: 32-bit words to initialise in the same launch (search scratch)
   size_t fill_words[3];
   uint32_t fill_value[3];
@@ -39,6 +44,7 @@ struct ScanParams {
   uint32_t n_items;         // rows scanned: n_rows, or n_subset with `subset`
   const uint32_t* subset;   // nullable: slots to gather
   const float* row_norm2;   // [slot]
+  const float* row_scale;   // [slot] ELEM_F8E only
   const uint64_t* ids;      // [slot]
   const float* queries;     // [nq][q_stride] dequantized fp32, zero padded to q_stride
   const float* q_norm2;     // [nq]
@@ -52,6 +58,7 @@ struct ScanParams {
   int* cta_counts;          // out     [gridDim.x][nq]
   const uint32_t* q_map;    // nullable: compact query index -> prepared query row
   const uint32_t* n_active; // nullable: number of queries, on the device (overrides nq)
+  uint32_t q_base;          // with n_active: this launch serves compact indices [q_base, q_base + nq)
   uint32_t chunk_bytes;     // bytes of one row copied per pipeline stage (multiple of 128)
   uint32_t n_stages;        // stages per warp
   // CFLAT multi-vector scoring (experimental/multi_vector_vertex.go:108-116): one launch per included field adds
@@ -78,27 +85,29 @@ struct GemmCand {
 };
 struct GemmParams {
   uint32_t n_rows, dim, nq;
-  const __half* q_f16;       // [nq][q_stride] lowered queries, zero padded to kblocks*64
-  uint32_t q_stride;
+  const void* q_lowered;     // [nq][q_stride bytes] lowered queries (fp16, or E4M3 codes), zero padded to kblocks*128 bytes
+  uint32_t q_stride;         // bytes
   const float* row_norm2;    // [n_rows]
-  const uint8_t* rows;       // the shard's row matrix (linear L2 prefetch; the operands themselves go through TMA)
+  const float* row_scale;    // [n_rows] E4M3 stores only (nullable): folded into the per-row key coefficient
+  const uint8_t* rows;       // the shard's row matrix (the operands themselves go through TMA)
   uint32_t row_stride;       // bytes
   int metric, nearest;
-  uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over CTAs), zero-initialised
-  float* pub;                // [grid_x][nq] best key each CTA has seen per query, initialised to NaN
-  GemmCand* cand_buf;        // scratch [grid_y*grid_x][cand_cap][128]: per-(CTA,query) candidate buffers
-  GemmCand* cand_out;        // [nq][grid_x][cand_cap]
-  uint32_t* cand_cnt;        // [nq][grid_x]
+  uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over columns), zero-initialised
+  float* pub;                // [n_cols][nq] the order statistic each column publishes per query, initialised to NaN
+  GemmCand* cand_buf;        // scratch [grid_y*grid_x*2][cand_cap][128]: per-(column,query) candidate buffers
+  GemmCand* cand_out;        // [nq][n_cols][cand_out_cap]
+  uint32_t* cand_cnt;        // [nq][n_cols]
   uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages;  // filled from the plan
+  uint32_t pub_kth, groups;  // bound scheme (gemm_common.cuh): what a column publishes, and the number of column classes
   float* dbg_acc;            // nullable (tests): raw accumulators [nq][n_rows]
-  unsigned long long* dbg_prof;  // nullable (profiling): [grid][8] cycle counters per role
+  unsigned long long* dbg_prof;  // nullable (profiling builds, -DCOLTT_K2_PROF=1): [grid][8] cycle counters per role
   unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
-  uint32_t mma_split;        // independent accumulation chains per tile (1, 2 or 4)
-  uint32_t pf_inner, pf_dist; // L2 prefetch box width (fp16 elements per row, multiple of 32) and lead in stages
-  uint32_t dbg_flags;        // bit0: epilogue only drains TMEM (pipeline speed probe); bit1: no L2 prefetch; bit4: no evict_first hint on the operand loads
+  uint32_t pf_inner;         // L2 prefetch box width in bytes (multiple of 64)
+  uint32_t dbg_flags;        // profiling builds only. bit0: epilogue only drains TMEM; bit1: no L2 prefetch
 };
 struct GemmPlan {
-  uint32_t kblocks, kprime, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols;
+  uint32_t kblocks, kprime, kp, pub_kth, groups, cand_cap, cand_out_cap, n_stages, grid_x, grid_y, q_stride, tile_rows, pair, n_cols, fp8;
+  uint32_t sb;               // bytes per row of a shard-tile stage (64 or 128; CTA-pair kernel)
   size_t smem_bytes;
 };
 // The three TMA descriptors of a launch (shard tiles, query tile, L2-prefetch view), kept with the search scratch
@@ -107,20 +116,25 @@ struct GemmMapCache {
   alignas(64) unsigned char maps[3][128];   // CUtensorMap x3 (opaque here: this header does not pull in <cuda.h>)
   const void* rows = nullptr;
   const void* q = nullptr;
-  uint32_t n_rows = 0, dim = 0, row_stride = 0, box_rows = 0, pf_inner = 0, nq = 0, q_stride = 0;
+  uint32_t n_rows = 0, row_bytes = 0, row_stride = 0, box_rows = 0, pf_inner = 0, nq = 0, q_stride = 0, sb = 0;
 };
-int plan_gemm_filter(uint32_t dim, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
+// row_bytes = dim * element size; fp8 = E4M3 operands (kind::f8f6f4) instead of fp16 (kind::f16)
+int plan_gemm_filter(uint32_t row_bytes, bool fp8, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
 int launch_gemm_filter(const GemmParams& p, const GemmPlan& plan, const void* d_rows, uint32_t row_stride, cudaStream_t stream,
                        GemmMapCache* cache = nullptr);
 uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows);
 
 struct RerankParams {
   uint32_t nq, k, dim, q_stride, row_stride, grid_x, cand_cap;
+  uint32_t max_rows;         // rows re-scored exactly per query: 64 (top-10/24) or 256 (top-100)
+  float eps_rel;             // certificate margin: |filter score - exact score| <= eps_rel * ||q|| ||row|| (fast_eps_rel(dim))
   int metric, nearest, elem;
   const float* queries;      // [nq][q_stride] dequantized fp32 (exact path operand)
   const float* q_norm2;      // [nq]
+  const float* q_scale;      // [nq] E4M3 stores only (nullable): the filter's keys are in units of 1/q_scale
   const uint8_t* rows;
   const float* row_norm2;
+  const float* row_scale;    // [slot] E4M3 stores only
   const uint64_t* ids;
   const GemmCand* cand_in;   // [nq][grid_x][cand_cap]
   const uint32_t* cand_cnt;  // [nq][grid_x]
@@ -136,6 +150,12 @@ struct RerankParams {
   unsigned long long* stat_fallbacks;  // nullable: running total of flagged queries (statistics)
 };
 int launch_rerank(const RerankParams& p, cudaStream_t stream);
+// Certificate margin of COLTT_MATH_FAST, relative to ||q|| ||row|| (DESIGN.md §5 has the derivation): the tensor core adds
+// `dim` exact products into an fp32 accumulator truncating each addend to the accumulator's ulp (<= dim * 2^-23), the exact
+// kernel rounds (dim/8 + 3) times per AVX lane (<= (dim/8+3) * 2^-24); 25 % slack and 2^-20 for the epilogue roundings.
+inline float fast_eps_rel(uint32_t dim) {
+  return 1.25f * ((float)dim * 1.1920929e-7f + ((float)dim / 8.0f + 3.0f) * 5.9604645e-8f) + 9.5367432e-7f;
+}
 
 // ---- topk_merge.cu (K5) -----------------------------------------------------------------
 struct MergeParams {
@@ -149,6 +169,7 @@ struct MergeParams {
   int in_best_first;         // 1: lists are best-first (internal); 0: lists are in T order (public)
   const uint32_t* q_map;     // nullable: compact query index -> output row
   const uint32_t* n_active;  // nullable: number of queries, on the device
+  uint32_t q_base;           // with n_active: this launch serves compact indices [q_base, q_base + nq)
   uint32_t out_stride;       // hits per output row (0 = k)
   size_t list_stride_hits;   // Hits between consecutive lists (0 = nq*k_in, the dense layout)
   size_t count_stride;       // ints between consecutive lists' counts (0 = nq)

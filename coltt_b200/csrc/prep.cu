@@ -63,9 +63,31 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
     // Lower + write the stored row; keep the dequantized value in smem for the norm pass.
     const size_t slot = p.slots ? (size_t)p.slots[i] : (size_t)p.slot_base + i;
     uint8_t* row = p.rows_out ? p.rows_out + slot * (size_t)p.row_stride : nullptr;
+    float e_scale = 1.0f, e_inv = 1.0f;
+    if (ELEM == ELEM_F8E) {
+      // builder-defined E4M3 store: one power-of-two scale per vector from max|v| (common.cuh, include/coltt_b200.h)
+      float mx = 0.0f;
+      bool bad = false;
+      for (uint32_t d = lane; d < dim; d += 32) {
+        const float a = fabsf(x[d]);
+        if (!(a <= 3.402823466e+38f)) bad = true; else mx = fmaxf(mx, a);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      bad = __any_sync(0xffffffffu, bad);
+      e_scale = bad ? 1.0f : e4m3_scale_from_maxabs(mx);
+      e_inv = __uint_as_float((uint32_t)(254 - (int)(__float_as_uint(e_scale) >> 23)) << 23);   // 1 / 2^es, exact
+      if (lane == 0 && p.scale_out) p.scale_out[p.norm2_by_slot ? slot : i] = e_scale;
+    }
+    uint8_t* code_row = (ELEM == ELEM_F8E && p.code_out) ? p.code_out + i * (size_t)p.code_stride : nullptr;
     for (uint32_t d = lane; d < dim; d += 32) {
       float v = x[d];
-      if (ELEM == ELEM_F32) {
+      if (ELEM == ELEM_F8E) {
+        const uint8_t c = e4m3_encode(mul_rn(v, e_inv));
+        if (row) row[d] = c;
+        if (code_row) code_row[d] = c;
+        v = mul_rn(e_scale, e4m3_decode(c));
+      } else if (ELEM == ELEM_F32) {
         if (row) reinterpret_cast<float*>(row)[d] = v;
       } else if (ELEM == ELEM_F16) {
         // compresshelper.Fromfloat32 (float16.go:124,274-321): IEEE RNE incl. subnormals and
@@ -85,6 +107,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
       const uint32_t es = ELEM == ELEM_F32 ? 4 : (ELEM == ELEM_F16 ? 2 : 1);
       for (uint32_t b = dim * es + lane; b < p.row_stride; b += 32) row[b] = 0;
     }
+    if (code_row)
+      for (uint32_t b = dim + lane; b < p.code_stride; b += 32) code_row[b] = 0;   // +0.0 in E4M3
     __syncwarp();
 
     // ||x||^2 exactly as cosine_similarity_dot_norm accumulates it for one operand
@@ -123,7 +147,8 @@ int launch_prep_rows(const PrepParams& p, int elem, cudaStream_t stream) {
   const size_t smem = per_warp * warps;
   const size_t blocks_needed = (p.n + warps - 1) / warps;
   const int grid = (int)(blocks_needed < 148 * 8 ? blocks_needed : 148 * 8);
-  auto k = elem == ELEM_F32 ? prep_rows_kernel<ELEM_F32> : (elem == ELEM_F16 ? prep_rows_kernel<ELEM_F16> : prep_rows_kernel<ELEM_F8C>);
+  auto k = elem == ELEM_F32 ? prep_rows_kernel<ELEM_F32>
+                            : (elem == ELEM_F16 ? prep_rows_kernel<ELEM_F16> : (elem == ELEM_F8C ? prep_rows_kernel<ELEM_F8C> : prep_rows_kernel<ELEM_F8E>));
   { int arc = kernel_attrs(k, smem); if (arc) return arc; }
   k<<<grid, warps * 32, smem, stream>>>(p);
   count_launch();

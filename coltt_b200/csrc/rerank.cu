@@ -17,39 +17,42 @@
 namespace coltt {
 
 static constexpr int kRerankThreads = 256;
-static constexpr uint32_t kRerankMaxCand = 1024;   // survivors gathered per query (keys only)
-static constexpr uint32_t kRerankRows = 64;        // rows re-scored exactly per query (>= 2 K')
+static constexpr uint32_t kRerankChunk = 64;       // rows staged in shared memory at a time
 
 // shared-memory layout (byte offsets from the dynamic base; offsets, not rounded pointers, so that every access
-// stays in the shared address space and compiles to LDS/STS)
+// stays in the shared address space and compiles to LDS/STS).  MC = survivors gathered per query (keys only),
+// MR = rows re-scored exactly per query (>= 2 K').
 struct RerankSmem {
-  uint32_t q, row, key, sel, score, n2, id, rows, total;
-  __host__ __device__ RerankSmem(uint32_t q_stride, uint32_t row_stride) {
+  uint32_t q, row, key, sel, score, n2, sc, id, rows, total;
+  __host__ __device__ RerankSmem(uint32_t q_stride, uint32_t row_stride, uint32_t MC, uint32_t MR) {
     q = 0;                                   // float  [q_stride]        (bulk-copied: 16-byte multiple)
-    row = q + q_stride * 4;                  // u32    [kRerankMaxCand]
-    key = row + kRerankMaxCand * 4;          // float  [kRerankMaxCand]
-    sel = key + kRerankMaxCand * 4;          // u32    [kRerankRows]
-    score = sel + kRerankRows * 4;           // float  [kRerankRows]
-    n2 = score + kRerankRows * 4;            // float  [kRerankRows]     ||row||^2 of the selected rows
-    id = n2 + kRerankRows * 4;               // u64    [kRerankRows]
-    rows = (id + kRerankRows * 8 + 127u) & ~127u;   // bytes [kRerankRows][row_stride + 16]
-    total = rows + kRerankRows * (row_stride + 16);
+    row = q + q_stride * 4;                  // u32    [MC]
+    key = row + MC * 4;                      // float  [MC]
+    sel = key + MC * 4;                      // u32    [MR]
+    score = sel + MR * 4;                    // float  [MR]
+    n2 = score + MR * 4;                     // float  [MR]     ||row||^2 of the selected rows
+    sc = n2 + MR * 4;                        // float  [MR]     E4M3 row scales
+    id = sc + MR * 4;                        // u64    [MR]
+    rows = (id + MR * 8 + 127u) & ~127u;     // bytes [kRerankChunk][row_stride + 16]
+    total = rows + kRerankChunk * (row_stride + 16);
   }
 };
 
-template <int ELEM, int METRIC>
+template <int ELEM, int METRIC, int MR>
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
+  constexpr uint32_t MC = MR == 64 ? 1024u : 4096u;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t n_s, ovf_s, last_s;
   __shared__ float kth_s, bound_s;
-  __shared__ __align__(8) uint64_t bar_s[2];   // [0] query copy, [1] row copies
-  const RerankSmem L(p.q_stride, p.row_stride);
+  __shared__ __align__(8) uint64_t bar_s[2];   // [0] query copy, [1] row copies (one phase per chunk)
+  const RerankSmem L(p.q_stride, p.row_stride, MC, MR);
   float* q_s = reinterpret_cast<float*>(smem + L.q);
   uint32_t* row_s = reinterpret_cast<uint32_t*>(smem + L.row);
   float* key_s = reinterpret_cast<float*>(smem + L.key);
   uint32_t* sel_row = reinterpret_cast<uint32_t*>(smem + L.sel);
   float* score_s = reinterpret_cast<float*>(smem + L.score);
   float* n2_s = reinterpret_cast<float*>(smem + L.n2);
+  float* sc_s = reinterpret_cast<float*>(smem + L.sc);
   uint64_t* id_s = reinterpret_cast<uint64_t*>(smem + L.id);
   uint8_t* rows_s = smem + L.rows;
   const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
     bulk_g2s(smem_u32(q_s), p.queries + (size_t)q * p.q_stride, p.q_stride * 4, smem_u32(&bar_s[0]));
   }
   // padding keys: never better than anything, never tie-break ahead of anything
-  for (uint32_t e = tid; e < kRerankMaxCand; e += blockDim.x) { key_s[e] = __int_as_float(0xff800000); row_s[e] = 0xffffffffu; }
+  for (uint32_t e = tid; e < MC; e += blockDim.x) { key_s[e] = __int_as_float(0xff800000); row_s[e] = 0xffffffffu; }
   __syncthreads();
 
   // ---- 1. gather the survivors of every filter column that clear the final threshold.  One column per
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
         for (int v = 0; v < 4; v++) {
           if (s0 + v < cn && (!have_bound || e4[v].key >= B || e4[v].key != e4[v].key)) {
             const uint32_t pos = atomicAdd(&n_s, 1u);
-            if (pos < kRerankMaxCand) { row_s[pos] = e4[v].row; key_s[pos] = e4[v].key; }
+            if (pos < MC) { row_s[pos] = e4[v].row; key_s[pos] = e4[v].key; }
           }
         }
       }
@@ -103,11 +106,11 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   }
   __syncthreads();
   const uint32_t n_all = n_s;
-  const uint32_t n = n_all < kRerankMaxCand ? n_all : kRerankMaxCand;
+  const uint32_t n = n_all < MC ? n_all : MC;
 
   // ---- 2. keep the M best by approximate key (rank counting; ties by row) — everything else, gathered or
   //         not, has key <= bound': the (M+1)-th best key, or B when fewer than M were gathered
-  const uint32_t M = n < kRerankRows ? n : kRerankRows;
+  const uint32_t M = n < (uint32_t)MR ? n : (uint32_t)MR;
   if (tid == 0) bound_s = have_bound ? B : __int_as_float(0xff800000);
   __syncthreads();
   const uint32_t n4 = (n + 3) & ~3u;         // the padding entries rank behind everything
@@ -129,52 +132,58 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   }
   __syncthreads();
 
-  // ---- 3. fetch the M rows with one bulk async copy each (all in flight at once; their norms and ids are
-  //         fetched by the same threads meanwhile), then re-score them from shared memory with the exact
-  //         AVX-order arithmetic of flat_scan.cu
-  if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bar_s[1]), M * p.row_stride);
-  __syncthreads();
-  for (uint32_t j = tid; j < M; j += blockDim.x) {
-    const uint32_t row = sel_row[j];
-    bulk_g2s(smem_u32(rows_s + (size_t)j * RS), p.rows + (size_t)row * p.row_stride, p.row_stride, smem_u32(&bar_s[1]));
-    n2_s[j] = METRIC == COLTT_COSINE ? p.row_norm2[row] : 0.0f;
-    id_s[j] = p.ids[row];
-  }
+  // ---- 3. fetch the M rows, kRerankChunk at a time, with one bulk async copy each (a chunk's copies are all in
+  //         flight at once; norms, scales and ids are fetched by the same threads meanwhile), and re-score them from
+  //         shared memory with the exact AVX-order arithmetic of flat_scan.cu
   mbar_wait(smem_u32(&bar_s[0]), 0);
-  if (M) mbar_wait(smem_u32(&bar_s[1]), 0);
-  __syncthreads();      // n2_s / id_s of every selected row are in place
   const uint32_t r = lane_row16(lane), g = lane_half(lane);
   const uint32_t full8 = (p.dim / 8) * 8;
   const float qn = METRIC == COLTT_COSINE ? p.q_norm2[q] : 0.0f;
-  for (uint32_t base = warp * 16; base < M; base += (blockDim.x >> 5) * 16) {
-    const uint32_t j = base + r;
-    const bool valid = j < M;
-    const uint8_t* rowp = rows_s + (size_t)(valid ? j : 0) * RS;
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (uint32_t j = tid; j < M; j += blockDim.x) {
+    const uint32_t row = sel_row[j];
+    n2_s[j] = METRIC == COLTT_COSINE ? p.row_norm2[row] : 0.0f;
+    sc_s[j] = ELEM == ELEM_F8E ? p.row_scale[row] : 1.0f;
+    id_s[j] = p.ids[row];
+  }
+  for (uint32_t c0 = 0, ph = 0; c0 < M; c0 += kRerankChunk, ph ^= 1) {
+    const uint32_t mc = M - c0 < kRerankChunk ? M - c0 : kRerankChunk;
+    if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bar_s[1]), mc * p.row_stride);
+    __syncthreads();    // the previous chunk's reads are done; expect_tx precedes the copies; n2_s / sc_s / id_s are in place
+    for (uint32_t j = tid; j < mc; j += blockDim.x)
+      bulk_g2s(smem_u32(rows_s + (size_t)j * RS), p.rows + (size_t)sel_row[c0 + j] * p.row_stride, p.row_stride, smem_u32(&bar_s[1]));
+    mbar_wait(smem_u32(&bar_s[1]), ph);
+    for (uint32_t base = warp * 16; base < mc; base += (blockDim.x >> 5) * 16) {
+      const uint32_t jl = base + r;
+      const bool valid = jl < mc;
+      const uint32_t j = c0 + (valid ? jl : 0);
+      const uint8_t* rowp = rows_s + (size_t)(valid ? jl : 0) * RS;
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
-    for (uint32_t e = 0; e < full8; e += 8) {
-      float rv[4];
-      load4<ELEM>(rowp + (size_t)(e + 4 * g) * ES, nullptr, rv);
-      const float4 qv = *reinterpret_cast<const float4*>(q_s + e + 4 * g);
-      if (METRIC == COLTT_COSINE) {
-        acc[0] = dot_step<ELEM>(acc[0], qv.x, rv[0]); acc[1] = dot_step<ELEM>(acc[1], qv.y, rv[1]);
-        acc[2] = dot_step<ELEM>(acc[2], qv.z, rv[2]); acc[3] = dot_step<ELEM>(acc[3], qv.w, rv[3]);
-      } else {
-        float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
-        acc[0] = add_rn(acc[0], mul_rn(d0, d0)); acc[1] = add_rn(acc[1], mul_rn(d1, d1));
-        acc[2] = add_rn(acc[2], mul_rn(d2, d2)); acc[3] = add_rn(acc[3], mul_rn(d3, d3));
+      for (uint32_t e = 0; e < full8; e += 8) {
+        float rv[4];
+        load4<ELEM>(rowp + (size_t)(e + 4 * g) * ES, nullptr, rv);
+        const float4 qv = *reinterpret_cast<const float4*>(q_s + e + 4 * g);
+        if (METRIC == COLTT_COSINE) {
+          acc[0] = dot_step<ELEM>(acc[0], qv.x, rv[0]); acc[1] = dot_step<ELEM>(acc[1], qv.y, rv[1]);
+          acc[2] = dot_step<ELEM>(acc[2], qv.z, rv[2]); acc[3] = dot_step<ELEM>(acc[3], qv.w, rv[3]);
+        } else {
+          float d0 = sub_rn(qv.x, rv[0]), d1 = sub_rn(qv.y, rv[1]), d2 = sub_rn(qv.z, rv[2]), d3 = sub_rn(qv.w, rv[3]);
+          acc[0] = add_rn(acc[0], mul_rn(d0, d0)); acc[1] = add_rn(acc[1], mul_rn(d1, d1));
+          acc[2] = add_rn(acc[2], mul_rn(d2, d2)); acc[3] = add_rn(acc[3], mul_rn(d3, d3));
+        }
       }
+      float h = add_rn(add_rn(acc[0], acc[1]), add_rn(acc[2], acc[3]));
+      float o = __shfl_xor_sync(0xffffffffu, h, 8);
+      float tot = g == 0 ? add_rn(h, o) : add_rn(o, h);
+      for (uint32_t d = full8; d < p.dim; d++) {
+        float rv = load1<ELEM>(rowp, d, nullptr);
+        float qv = q_s[d];
+        if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
+        else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
+      }
+      if (ELEM == ELEM_F8E) tot = mul_rn(tot, sc_s[j]);   // the row's power-of-two scale, applied once (flat_scan.cu)
+      if (valid && g == 0) score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, n2_s[j]) : sqrt_via_f64(tot);
     }
-    float h = add_rn(add_rn(acc[0], acc[1]), add_rn(acc[2], acc[3]));
-    float o = __shfl_xor_sync(0xffffffffu, h, 8);
-    float tot = g == 0 ? add_rn(h, o) : add_rn(o, h);
-    for (uint32_t d = full8; d < p.dim; d++) {
-      float rv = load1<ELEM>(rowp, d, nullptr);
-      float qv = q_s[d];
-      if (METRIC == COLTT_COSINE) tot = dot_step<ELEM>(tot, qv, rv);
-      else { float df = sub_rn(qv, rv); tot = add_rn(tot, mul_rn(df, df)); }
-    }
-    if (valid && g == 0) score_s[j] = METRIC == COLTT_COSINE ? cosine_epilogue(tot, qn, n2_s[j]) : sqrt_via_f64(tot);
   }
   __syncthreads();
 
@@ -197,23 +206,26 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   // ---- 5. certificate: every row that was not re-scored has approximate key <= bound'
   if (tid == 0) {
     p.out_counts[q] = (int)n_out;
-    bool ok = n_all <= kRerankMaxCand && ovf_s == 0;
+    bool ok = n_all <= MC && ovf_s == 0;
     const float Bp = bound_s;
     if (ok && Bp > __int_as_float(0xff800000)) {
       const float dK = kth_s;  // exact score (a distance) of the worst row we return
       if (!(dK == dK)) {
         ok = !p.nearest;       // NaN is the best COMPAT score and the worst NEAREST one
       } else if (METRIC == COLTT_COSINE) {
-        const float invq = rsqrtf(qn);
-        const float eps = 1.5e-4f;
-        // key = +-dot/||row||; exact sim within eps of key*invq; distance = |1 - sim|
+        // key = +-dot' * s_row/||row|| with dot' in units of 1/s_q (E4M3) — the exact similarity lies within
+        // eps_rel of key * s_q/||q||; distance = |1 - sim|
+        const float invq = rsqrtf(qn) * (p.q_scale ? p.q_scale[q] : 1.0f);
+        const float eps = p.eps_rel;
         if (p.nearest) ok = dK < 1.0f - Bp * invq - eps;        // dropped rows: distance >= 1 - B'*invq - eps
         else ok = dK > 1.0f + Bp * invq + eps;                  // dropped rows: distance <= 1 + B'*invq + eps
       } else {
+        // key = +-(2 dot - ||row||^2); the dot product is off by at most eps_rel * ||q|| ||row||, and
+        // 2 ||q|| ||row|| <= ||q||^2 + (||q|| + d)^2 for a row at distance d
         const float nq2 = p.q_norm2[q];
         const float d2 = dK * dK;
         const float scale = nq2 + (sqrtf(nq2) + dK) * (sqrtf(nq2) + dK);
-        const float eps = 2.0e-4f * scale;
+        const float eps = p.eps_rel * scale;
         if (p.nearest) ok = d2 < nq2 - Bp - eps;                // key = 2dot - ||row||^2  =>  d^2 = ||q||^2 - key
         else ok = d2 > nq2 + Bp + eps;                          // key = ||row||^2 - 2dot  =>  d^2 = ||q||^2 + key
       }
@@ -242,18 +254,22 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
 
 int launch_rerank(const RerankParams& p, cudaStream_t stream) {
   if (p.nq == 0) return COLTT_OK;
-  const size_t smem = RerankSmem(p.q_stride, p.row_stride).total;
+  if (p.max_rows != 64 && p.max_rows != 256) return fail(COLTT_ERR_INVALID, "rerank: max_rows must be 64 or 256");
+  const size_t smem = RerankSmem(p.q_stride, p.row_stride, p.max_rows == 64 ? 1024u : 4096u, p.max_rows).total;
   if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "rerank: rows too wide for shared memory");
   const bool cosine = p.metric == COLTT_COSINE;
-#define COLTT_RR(E, M)                                                                                    \
+#define COLTT_RR(E, M, R)                                                                                 \
   {                                                                                                       \
-    auto kfn = rerank_kernel<E, M>;                                                                       \
+    auto kfn = rerank_kernel<E, M, R>;                                                                    \
     { int arc = kernel_attrs(kfn, smem); if (arc) return arc; }                                           \
     kfn<<<p.nq, kRerankThreads, smem, stream>>>(p);                                                        \
   }
-  if (p.elem == ELEM_F16) { if (cosine) COLTT_RR(ELEM_F16, COLTT_COSINE) else COLTT_RR(ELEM_F16, COLTT_EUCLIDEAN) }
-  else if (p.elem == ELEM_F32) { if (cosine) COLTT_RR(ELEM_F32, COLTT_COSINE) else COLTT_RR(ELEM_F32, COLTT_EUCLIDEAN) }
-  else return fail(COLTT_ERR_UNSUPPORTED, "rerank: element type");
+#define COLTT_RR_R(E, M) { if (p.max_rows == 64) COLTT_RR(E, M, 64) else COLTT_RR(E, M, 256) }
+  if (p.elem == ELEM_F16) { if (cosine) COLTT_RR_R(ELEM_F16, COLTT_COSINE) else COLTT_RR_R(ELEM_F16, COLTT_EUCLIDEAN) }
+  else if (p.elem == ELEM_F32) { if (cosine) COLTT_RR_R(ELEM_F32, COLTT_COSINE) else COLTT_RR_R(ELEM_F32, COLTT_EUCLIDEAN) }
+  else if (p.elem == ELEM_F8E && cosine) COLTT_RR_R(ELEM_F8E, COLTT_COSINE)
+  else return fail(COLTT_ERR_UNSUPPORTED, "rerank: element type / metric");
+#undef COLTT_RR_R
 #undef COLTT_RR
   count_launch();
   COLTT_CUDA(cudaGetLastError());

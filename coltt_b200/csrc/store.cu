@@ -150,6 +150,7 @@ Store::~Store() {
   pool.clear();
   if (d_rows) cudaFree(d_rows);
   if (d_norm2) cudaFree(d_norm2);
+  if (d_scale) cudaFree(d_scale);
   if (d_ids) cudaFree(d_ids);
   if (d_stat) cudaFree(d_stat);
   if (stream) cudaStreamDestroy(stream);
@@ -165,7 +166,7 @@ int Store::create(const coltt_store_cfg* cfg, Store** out) {
     case COLTT_QUANT_F16:
     case COLTT_QUANT_BF16: elem = ELEM_F16; break;  // the reference's bf16 IS binary16
     case COLTT_QUANT_F8: elem = ELEM_F8C; break;
-    case COLTT_QUANT_F8_E4M3: return fail(COLTT_ERR_UNSUPPORTED, "F8_E4M3 store not built yet");
+    case COLTT_QUANT_F8_E4M3: elem = ELEM_F8E; break;  // builder-defined real fp8: E4M3 codes + one scale per row
     default: return fail(COLTT_ERR_INVALID, "not support quantization type");  // edge/vectorstore.go:78
   }
   int rc = require_device(cfg->device);
@@ -196,17 +197,19 @@ int Store::reserve(size_t rows) {
   if (rows > 0xfffffff0ull) return fail(COLTT_ERR_UNSUPPORTED, "more than 2^32 rows per GPU shard");
   size_t nc = std::max<size_t>(rows, std::max<size_t>(capacity * 2, 1024));
   uint8_t* nr = nullptr;
-  float* nn = nullptr;
+  float *nn = nullptr, *nsc = nullptr;
   uint64_t* ni = nullptr;
+  const bool scaled = elem == ELEM_F8E;
   auto try_alloc = [&](size_t c) {
-    nr = nullptr; nn = nullptr; ni = nullptr;
+    nr = nullptr; nn = nullptr; ni = nullptr; nsc = nullptr;
     if (cudaMalloc(&nr, c * row_stride) == cudaSuccess && cudaMalloc(&nn, c * 4) == cudaSuccess &&
-        cudaMalloc(&ni, c * 8) == cudaSuccess)
+        cudaMalloc(&ni, c * 8) == cudaSuccess && (!scaled || cudaMalloc(&nsc, c * 4) == cudaSuccess))
       return true;
     cudaGetLastError();
     if (nr) cudaFree(nr);
     if (nn) cudaFree(nn);
     if (ni) cudaFree(ni);
+    if (nsc) cudaFree(nsc);
     return false;
   };
   if (!try_alloc(nc)) {
@@ -217,13 +220,16 @@ int Store::reserve(size_t rows) {
     COLTT_CUDA(cudaMemcpyAsync(nr, d_rows, n_rows * row_stride, cudaMemcpyDeviceToDevice, stream));
     COLTT_CUDA(cudaMemcpyAsync(nn, d_norm2, n_rows * 4, cudaMemcpyDeviceToDevice, stream));
     COLTT_CUDA(cudaMemcpyAsync(ni, d_ids, n_rows * 8, cudaMemcpyDeviceToDevice, stream));
+    if (scaled) COLTT_CUDA(cudaMemcpyAsync(nsc, d_scale, n_rows * 4, cudaMemcpyDeviceToDevice, stream));
     COLTT_CUDA(cudaStreamSynchronize(stream));
   }
   if (d_rows) cudaFree(d_rows);
   if (d_norm2) cudaFree(d_norm2);
+  if (d_scale) cudaFree(d_scale);
   if (d_ids) cudaFree(d_ids);
   d_rows = nr;
   d_norm2 = nn;
+  d_scale = nsc;
   d_ids = ni;
   capacity = nc;
   return COLTT_OK;
@@ -237,6 +243,7 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
   std::unique_lock<std::shared_mutex> lk(mu);
   if (anonymous) return fail(COLTT_ERR_UNSUPPORTED, "store was filled from device memory: search only");
   COLTT_CUDA(cudaSetDevice(device));
+  { int wrc = wait_for_searches(); if (wrc) return wrc; }
   std::unordered_map<uint64_t, size_t> last;
   last.reserve(n * 2);
   for (size_t i = 0; i < n; i++) last[ids[i]] = i;
@@ -269,7 +276,7 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
     pp.in = (const float*)up_in.p; pp.n = c; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
     pp.normalize = cfg.metric == COLTT_COSINE;  // `if vertex.distance.Type() == T_COSINE` (none_vectorstore.go:96-98)
     pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slots = (const uint32_t*)up_slots.p;
-    pp.norm2_out = d_norm2; pp.norm2_by_slot = 1;
+    pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale;
     rc = launch_prep_rows(pp, elem, stream);
     if (rc) return rc;
     scatter_ids_kernel<<<(unsigned)((c + 255) / 256), 256, 0, stream>>>((const uint64_t*)up_ids.p, (const uint32_t*)up_slots.p, d_ids, c);
@@ -285,30 +292,31 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
   return COLTT_OK;
 }
 
-__global__ void iota_ids_kernel(uint64_t* ids, size_t base, size_t n) {
+__global__ void iota_ids_kernel(uint64_t* ids, size_t base, size_t n, uint64_t id_base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ids[base + i] = base + i;
+  if (i < n) ids[base + i] = id_base + base + i;
 }
 
-// Bulk ingest of rows that already live on the device (the HNSW builder's temporary per-level shards):
-// Normalize + Lower + ||row||^2 exactly as upsert does, ids = slot numbers.  The host id map is not maintained,
-// so the store is search-only afterwards.
-int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats) {
+// Bulk ingest of rows that already live on the device (the HNSW builder's temporary per-level shards; shards too large
+// to stage through host memory): Normalize + Lower + ||row||^2 exactly as upsert does, ids = id_base + slot number.
+// The host id map is not maintained, so the store is search-only afterwards.
+int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base) {
   if (n == 0) return COLTT_OK;
   if (!d_vecs || stride_floats < dim) return fail(COLTT_ERR_INVALID, "append_dev: bad argument");
   std::unique_lock<std::shared_mutex> lk(mu);
   if (n_rows && !anonymous) return fail(COLTT_ERR_UNSUPPORTED, "append_dev on a store with host-mapped ids");
   COLTT_CUDA(cudaSetDevice(device));
+  { int wrc = wait_for_searches(); if (wrc) return wrc; }
   int rc = reserve(n_rows + n);
   if (rc) return rc;
   PrepParams pp{};
   pp.in = d_vecs; pp.n = n; pp.in_stride = stride_floats; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
   pp.normalize = cfg.metric == COLTT_COSINE;
   pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slot_base = (uint32_t)n_rows;
-  pp.norm2_out = d_norm2; pp.norm2_by_slot = 1;
+  pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale;
   rc = launch_prep_rows(pp, elem, stream);
   if (rc) return rc;
-  iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ids, n_rows, n);
+  iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ids, n_rows, n, id_base);
   COLTT_CUDA(cudaGetLastError());
   COLTT_CUDA(cudaStreamSynchronize(stream));
   n_rows += n;
@@ -322,6 +330,7 @@ int Store::remove(const uint64_t* ids, size_t n) {
   std::unique_lock<std::shared_mutex> lk(mu);
   if (anonymous) return fail(COLTT_ERR_UNSUPPORTED, "store was filled from device memory: search only");
   COLTT_CUDA(cudaSetDevice(device));
+  { int wrc = wait_for_searches(); if (wrc) return wrc; }
   for (size_t i = 0; i < n; i++) {
     auto it = id2slot.find(ids[i]);
     if (it == id2slot.end()) continue;  // Go's delete() on a missing key is a no-op
@@ -331,6 +340,7 @@ int Store::remove(const uint64_t* ids, size_t n) {
     if (s != lastslot) {
       COLTT_CUDA(cudaMemcpyAsync(d_rows + (size_t)s * row_stride, d_rows + (size_t)lastslot * row_stride, row_stride, cudaMemcpyDeviceToDevice, stream));
       COLTT_CUDA(cudaMemcpyAsync(d_norm2 + s, d_norm2 + lastslot, 4, cudaMemcpyDeviceToDevice, stream));
+      if (d_scale) COLTT_CUDA(cudaMemcpyAsync(d_scale + s, d_scale + lastslot, 4, cudaMemcpyDeviceToDevice, stream));
       COLTT_CUDA(cudaMemcpyAsync(d_ids + s, d_ids + lastslot, 8, cudaMemcpyDeviceToDevice, stream));
       h_ids[s] = h_ids[lastslot];
       id2slot[h_ids[s]] = s;
@@ -339,6 +349,16 @@ int Store::remove(const uint64_t* ids, size_t n) {
     n_rows--;
   }
   COLTT_CUDA(cudaStreamSynchronize(stream));
+  return COLTT_OK;
+}
+
+// Mutations edit rows / norms / ids in place on the store's own stream.  A search enqueued on a caller stream
+// (search_dev) may still be running after its call returned and dropped the shared lock, so every mutation, once it
+// holds the exclusive lock, first waits for the last work recorded on each pooled search scratch.
+int Store::wait_for_searches() {
+  std::lock_guard<std::mutex> g(pool_mu);
+  for (auto& c : pool)
+    if (c->used) COLTT_CUDA(cudaEventSynchronize(c->done));
   return COLTT_OK;
 }
 
@@ -430,7 +450,7 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
     }
     ScanParams sp{};
     sp.rows = d_rows; sp.row_stride = row_stride; sp.dim = dim; sp.n_items = (uint32_t)n_items; sp.subset = d_subset;
-    sp.row_norm2 = d_norm2; sp.ids = d_ids;
+    sp.row_norm2 = d_norm2; sp.row_scale = d_scale; sp.ids = d_ids;
     sp.queries = (const float*)c.q_deq.p + q0 * q_stride; sp.q_norm2 = (const float*)c.q_n2.p + q0; sp.q_stride = q_stride;
     sp.nq = (uint32_t)nqb; sp.k = k_eff; sp.nearest = nearest; sp.metric = cfg.metric;
     sp.warp_lists = (Hit*)c.warp_lists.p; sp.cta_lists = (Hit*)c.cta_lists.p; sp.cta_counts = (int*)c.cta_counts.p;
@@ -461,16 +481,20 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
 int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int nearest, Hit* d_out,
                         int* d_counts, bool timed, float* dbg_acc, bool* used_fast) {
   *used_fast = false;
-  if (elem != ELEM_F16 || n_rows < 4096 || (size_t)k > n_rows) return COLTT_OK;
+  // fp16 rows (kind::f16) and E4M3 rows (kind::f8f6f4; cosine: the row scale folds into the per-row coefficient)
+  const bool fp8 = elem == ELEM_F8E;
+  if (!(elem == ELEM_F16 || (fp8 && cfg.metric == COLTT_COSINE)) || n_rows < 4096 || (size_t)k > n_rows) return COLTT_OK;
   GemmPlan gp;
-  if (plan_gemm_filter(dim, (uint32_t)nq, (uint32_t)k, n_sms, &gp) != COLTT_OK) return COLTT_OK;  // unsupported shape -> exact
+  if (plan_gemm_filter(dim * elem_size(elem), fp8, (uint32_t)nq, (uint32_t)k, n_sms, &gp) != COLTT_OK) return COLTT_OK;  // unsupported shape -> exact
+  const uint32_t n_cols = gemm_filter_cols(gp, (uint32_t)n_rows);   // columns that see one query
+  if (n_cols < gp.groups) return COLTT_OK;                           // too few columns for the bound scheme -> exact
   const uint32_t q_stride = (dim + 7) / 8 * 8;
   int rc;
   rc = c.q_deq.ensure(nq * q_stride * 4); if (rc) return rc;
   rc = c.q_n2.ensure(nq * 4); if (rc) return rc;
-  rc = c.q_f16.ensure(nq * (size_t)gp.q_stride * 2); if (rc) return rc;
+  rc = c.q_f16.ensure(nq * (size_t)gp.q_stride); if (rc) return rc;   // lowered queries: fp16 or E4M3 codes, gp.q_stride bytes each
+  rc = c.q_scale.ensure(nq * 4); if (rc) return rc;
   rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
-  const uint32_t n_cols = gemm_filter_cols(gp, (uint32_t)n_rows);   // CTAs that see one query
   rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_out_cap * sizeof(GemmCand)); if (rc) return rc;
   rc = c.cand_cnt.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
@@ -487,8 +511,9 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   pp.normalize = cfg.metric == COLTT_COSINE;
   pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
   pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
-  pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride;
-  // scratch initialisation rides in the prep launch: bound = 0, counts = 0, published maxima = -NaN ("nothing yet":
+  if (fp8) { pp.code_out = (uint8_t*)c.q_f16.p; pp.code_stride = gp.q_stride; pp.scale_out = (float*)c.q_scale.p; }
+  else { pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride / 2; }
+  // scratch initialisation rides in the prep launch: bound = 0, counts = 0, published values = -NaN ("nothing yet":
   // never greater than anything)
   pp.fill_ptr[0] = (uint32_t*)c.g_thr.p;    pp.fill_words[0] = nq;                    pp.fill_value[0] = 0u;
   pp.fill_ptr[1] = (uint32_t*)c.cand_cnt.p; pp.fill_words[1] = nq * (size_t)n_cols;  pp.fill_value[1] = 0u;
@@ -496,16 +521,14 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[1], st);
   GemmParams g{};
-  g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_f16 = (const __half*)c.q_f16.p; g.q_stride = gp.q_stride;
-  g.row_norm2 = d_norm2; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
+  g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_lowered = c.q_f16.p; g.q_stride = gp.q_stride;
+  g.row_norm2 = d_norm2; g.row_scale = fp8 ? d_scale : nullptr; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
   g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p; g.cand_buf = (GemmCand*)c.cand_buf.p;
-  {
+#if COLTT_K2_PROF
+  {   // role timers of the filter kernel: profiling builds only (make EXTRA=-DCOLTT_K2_PROF=1)
     static const char* prof_env = getenv("COLTT_DEBUG_PROF");
     static const char* flags_env = getenv("COLTT_DEBUG_FLAGS");
     g.dbg_flags = flags_env ? (uint32_t)atoi(flags_env) : 0u;
-    static const char* split_env = getenv("COLTT_MMA_SPLIT");
-    g.mma_split = split_env ? (uint32_t)atoi(split_env) : 4u;
-    if (g.mma_split != 1 && g.mma_split != 2 && g.mma_split != 4) g.mma_split = 4;
     if (prof_env) {
       rc = c.prof.ensure((size_t)gp.grid_x * gp.grid_y * 16 * 8); if (rc) return rc;
       COLTT_CUDA(cudaMemsetAsync(c.prof.p, 0, (size_t)gp.grid_x * gp.grid_y * 16 * 8, st));
@@ -513,18 +536,23 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
       g.dbg_prof2 = g.dbg_prof + (size_t)gp.grid_x * gp.grid_y * 8;
     }
   }
+#endif
   rc = launch_gemm_filter(g, gp, d_rows, row_stride, st, &c.maps); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
   r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
   r.grid_x = n_cols; r.cand_cap = gp.cand_out_cap;
+  r.max_rows = gp.pub_kth ? 256u : 64u;
+  r.eps_rel = fast_eps_rel(dim);
   r.metric = cfg.metric; r.nearest = nearest; r.elem = elem;
-  r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.rows = d_rows; r.row_norm2 = d_norm2; r.ids = d_ids;
+  r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.q_scale = fp8 ? (const float*)c.q_scale.p : nullptr;
+  r.rows = d_rows; r.row_norm2 = d_norm2; r.row_scale = d_scale; r.ids = d_ids;
   r.cand_in = (const GemmCand*)c.cand.p; r.cand_cnt = (const uint32_t*)c.cand_cnt.p; r.g_thr = (const uint32_t*)c.g_thr.p;
   r.out = d_out; r.out_stride = (uint32_t)k; r.out_counts = d_counts; r.flags = (uint32_t*)c.flags.p;
   r.n_bad = (uint32_t*)c.fb_cnt.p; r.done_ctr = (uint32_t*)c.fb_cnt.p + 1; r.q_map = (uint32_t*)c.fb_q.p; r.stat_fallbacks = d_stat;
   rc = launch_rerank(r, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[3], st);
+#if COLTT_K2_PROF
   if (g.dbg_prof) {
     static int printed = 0;
     COLTT_CUDA(cudaStreamSynchronize(st));
@@ -540,39 +568,45 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
           const double v = (double)(k2 < 8 ? h[i * 8 + k2] : h[nc * 8 + i * 8 + (k2 - 8)]);
           sum += v; if (v > mx) mx = v;
         }
-        fprintf(stderr, "[coltt prof] split=%u %-16s avg %.0f max %.0f\n", g.mma_split, names[k2], sum / nc, mx);
+        fprintf(stderr, "[coltt prof] %-16s avg %.0f max %.0f\n", names[k2], sum / nc, mx);
       }
     }
   }
+#endif
   *used_fast = true;
   fast_queries += nq;
   // Certificate check, on the device: the queries rerank.cu could not certify were compacted into a list by
   // its last CTA and are re-run by the exact kernel, which takes its query count from device memory — no host
-  // round trip; with nothing flagged the two launches below are one empty wave each.
-  static const bool no_tail = getenv("COLTT_DEBUG_NOTAIL") != nullptr;   // timing probe only: results unverified
-  if (!no_tail) {
+  // round trip; with nothing flagged the launches below are one empty wave each.  The flagged list is served in
+  // windows so that the exact kernel's per-warp lists stay bounded (512 MB) whatever nq and k are.
+  {
     const uint32_t k_eff = (uint32_t)k;   // fast path requires k <= n_rows
     ScanPlan plan;
     rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_rows, (uint32_t)nq, k_eff, n_sms, &plan); if (rc) return rc;
+    const size_t per_q = (size_t)plan.grid_x * 8 * k_eff * sizeof(Hit);
+    size_t win = std::max<size_t>(8, (512u << 20) / per_q / 8 * 8);
+    if (win > nq) win = nq;
+    rc = plan_flat_scan(elem, dim, row_stride, (uint32_t)n_rows, (uint32_t)win, k_eff, n_sms, &plan); if (rc) return rc;
     plan.grid_y = 1;                      // each CTA loops over the (few) flagged query groups
-    plan.warp_list_bytes = (size_t)plan.grid_x * 8 * nq * k_eff * sizeof(Hit);
     rc = c.warp_lists.ensure(plan.warp_list_bytes); if (rc) return rc;
     rc = c.cta_lists.ensure(plan.cta_list_bytes); if (rc) return rc;
     rc = c.cta_counts.ensure(plan.cta_count_bytes); if (rc) return rc;
-    ScanParams sp{};
-    sp.rows = d_rows; sp.row_stride = row_stride; sp.dim = dim; sp.n_items = (uint32_t)n_rows; sp.subset = nullptr;
-    sp.row_norm2 = d_norm2; sp.ids = d_ids;
-    sp.queries = (const float*)c.q_deq.p; sp.q_norm2 = (const float*)c.q_n2.p; sp.q_stride = q_stride;
-    sp.nq = (uint32_t)nq; sp.k = k_eff; sp.nearest = nearest; sp.metric = cfg.metric;
-    sp.warp_lists = (Hit*)c.warp_lists.p; sp.cta_lists = (Hit*)c.cta_lists.p; sp.cta_counts = (int*)c.cta_counts.p;
-    sp.q_map = (const uint32_t*)c.fb_q.p; sp.n_active = (const uint32_t*)c.fb_cnt.p;
-    rc = launch_flat_scan(sp, plan, elem, st); if (rc) return rc;
-    MergeParams mp{};
-    mp.lists = (const Hit*)c.cta_lists.p; mp.counts = (const int*)c.cta_counts.p; mp.n_lists = plan.grid_x;
-    mp.nq = (uint32_t)nq; mp.k_in = k_eff; mp.k = k_eff; mp.nearest = nearest; mp.in_best_first = 1;
-    mp.out = d_out; mp.out_counts = d_counts; mp.out_stride = (uint32_t)k;
-    mp.q_map = (const uint32_t*)c.fb_q.p; mp.n_active = (const uint32_t*)c.fb_cnt.p;
-    rc = launch_merge_topk(mp, st); if (rc) return rc;
+    for (size_t w0 = 0; w0 < nq; w0 += win) {
+      ScanParams sp{};
+      sp.rows = d_rows; sp.row_stride = row_stride; sp.dim = dim; sp.n_items = (uint32_t)n_rows; sp.subset = nullptr;
+      sp.row_norm2 = d_norm2; sp.row_scale = d_scale; sp.ids = d_ids;
+      sp.queries = (const float*)c.q_deq.p; sp.q_norm2 = (const float*)c.q_n2.p; sp.q_stride = q_stride;
+      sp.nq = (uint32_t)win; sp.k = k_eff; sp.nearest = nearest; sp.metric = cfg.metric;
+      sp.warp_lists = (Hit*)c.warp_lists.p; sp.cta_lists = (Hit*)c.cta_lists.p; sp.cta_counts = (int*)c.cta_counts.p;
+      sp.q_map = (const uint32_t*)c.fb_q.p; sp.n_active = (const uint32_t*)c.fb_cnt.p; sp.q_base = (uint32_t)w0;
+      rc = launch_flat_scan(sp, plan, elem, st); if (rc) return rc;
+      MergeParams mp{};
+      mp.lists = (const Hit*)c.cta_lists.p; mp.counts = (const int*)c.cta_counts.p; mp.n_lists = plan.grid_x;
+      mp.nq = (uint32_t)win; mp.k_in = k_eff; mp.k = k_eff; mp.nearest = nearest; mp.in_best_first = 1;
+      mp.out = d_out; mp.out_counts = d_counts; mp.out_stride = (uint32_t)k;
+      mp.q_map = (const uint32_t*)c.fb_q.p; mp.n_active = (const uint32_t*)c.fb_cnt.p; mp.q_base = (uint32_t)w0;
+      rc = launch_merge_topk(mp, st); if (rc) return rc;
+    }
   }
   return COLTT_OK;
 }
@@ -728,6 +762,11 @@ COLTT_API int coltt_b200_store_upsert(coltt_store* s, const uint64_t* ids, const
   if (!s) return fail(COLTT_ERR_INVALID, "null store");
   return reinterpret_cast<Store*>(s)->upsert(ids, vecs, n);
 }
+COLTT_API int coltt_b200_store_append_dev(coltt_store* s, const void* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base) {
+  if (!s) return fail(COLTT_ERR_INVALID, "null store");
+  return reinterpret_cast<Store*>(s)->append_dev((const float*)d_vecs, n, stride_floats, id_base);
+}
+COLTT_API float coltt_b200_fast_eps_rel(uint32_t dim) { return coltt::fast_eps_rel(dim); }
 COLTT_API int coltt_b200_store_remove(coltt_store* s, const uint64_t* ids, size_t n) {
   if (!s) return fail(COLTT_ERR_INVALID, "null store");
   return reinterpret_cast<Store*>(s)->remove(ids, n);

@@ -51,7 +51,7 @@ struct SearchCtx {
   cudaStream_t last_stream = nullptr;
   bool used = false, have_times = false, timed_last = false;
   float ms[4] = {0, 0, 0, 0};
-  DeviceBuf q_in, q_deq, q_n2, q_f16, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf, multi_acc;
+  DeviceBuf q_in, q_deq, q_n2, q_f16, q_scale, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf, multi_acc;
   PinnedBuf h_q, h_out;
   GemmMapCache maps;                // TMA descriptors of the last FAST launch on this scratch
   ~SearchCtx();
@@ -64,6 +64,7 @@ struct Store {
   size_t n_rows = 0, capacity = 0;
   uint8_t* d_rows = nullptr;
   float* d_norm2 = nullptr;
+  float* d_scale = nullptr;                        // ELEM_F8E only: per-row power-of-two scale
   uint64_t* d_ids = nullptr;
   unsigned long long* d_stat = nullptr;            // queries the FAST path re-ran exactly (counted on the device)
   std::atomic<bool> timing{false};                 // record per-phase CUDA events around searches (diagnostics)
@@ -86,7 +87,8 @@ struct Store {
   int reserve(size_t rows);
   int upsert(const uint64_t* ids, const float* vecs, size_t n);
   int remove(const uint64_t* ids, size_t n);
-  int append_dev(const float* d_vecs, size_t n, uint32_t stride_floats);   // internal: rows already on the device, ids = slots
+  int append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base = 0);   // rows already on the device, ids = id_base + slot
+  int wait_for_searches();                         // mutations: order after outstanding asynchronous searches
   bool anonymous = false;                          // filled by append_dev: no host id map, search only
   int search_host(const float* queries, size_t nq, const uint64_t* cand_ids, size_t n_cand, bool use_subset, int k,
                   int select_mode, int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts);

@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
   __shared__ uint32_t P_s, M_s, overflow_s, has_tau_s;
   __shared__ Hit tau_s;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
-  if (p.n_active && q >= *p.n_active) return;
-  const uint32_t q_out = p.q_map ? p.q_map[q] : q;
+  if (p.n_active && p.q_base + q >= *p.n_active) return;
+  const uint32_t q_out = p.q_map ? p.q_map[p.q_base + q] : q;
   const uint32_t ostride = p.out_stride ? p.out_stride : p.k;
   const int rev = (!p.in_best_first && !p.nearest) ? 1 : 0;  // public T-order lists are worst-first for COMPAT
   const size_t lstr = p.list_stride_hits ? p.list_stride_hits : (size_t)p.nq * p.k_in;

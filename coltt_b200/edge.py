@@ -28,6 +28,7 @@ from . import _lib
 # edgepb.Distance / edgepb.Quantization (idl/proto/v4/edge.proto:69-80)
 Distance_Cosine, Distance_Euclidean = 0, 1
 Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16 = 0, 1, 2, 3
+Quantization_F8_E4M3 = 16   # builder extension: real fp8 rows (include/coltt_b200.h), not in edge.proto
 SELECT_COMPAT, SELECT_NEAREST = 0, 1   # coltt_select
 MATH_EXACT, MATH_FAST = 0, 1           # coltt_math
 
@@ -36,7 +37,7 @@ ErrCollectionNotFound = "collection: %s not found"         # edge/constants.go:2
 
 _u64p, _f32p, _i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_int32)
 _ELEM_DTYPE = {Quantization_None: np.float32, Quantization_F16: np.uint16, Quantization_BF16: np.uint16,
-               Quantization_F8: np.uint8}
+               Quantization_F8: np.uint8, Quantization_F8_E4M3: np.uint8}
 
 
 @dataclass
@@ -122,6 +123,15 @@ class VectorSpace:
         if vecs.shape[0] != ids.size:
             raise ValueError("ids and vectors disagree on the number of rows")
         _lib.check(_lib.lib().coltt_b200_store_upsert(self._h, ids.ctypes.data_as(_u64p), vecs.ctypes.data_as(_f32p), ids.size))
+
+    def AppendDeviceRows(self, d_ptr: int, n: int, stride_floats: int = 0, id_base: int = 0) -> None:
+        """Bulk ChangedVertex of rows already in device memory (coltt_b200_store_append_dev): ids = id_base + slot."""
+        _lib.check(_lib.lib().coltt_b200_store_append_dev(self._h, C.c_void_p(d_ptr), n, stride_floats or self.Dim(), id_base))
+
+    def fast_stats(self):
+        fs = (C.c_uint64 * 2)()
+        _lib.check(_lib.lib().coltt_b200_store_fast_stats(self._h, fs))
+        return {"queries": int(fs[0]), "exact_reruns": int(fs[1])}
 
     def RemoveVertex(self, drop_ids) -> None:
         """vectorspace.RemoveVertex (none_vectorstore.go:105-127) after dropFilter -> ids."""
@@ -212,7 +222,7 @@ class Vectorstore:
         with self.slock:
             if collectionName in self.Space:
                 raise KeyError(ErrCollectionExists % collectionName)
-            if metadata.Quantization not in (Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16):
+            if metadata.Quantization not in (Quantization_None, Quantization_F16, Quantization_F8, Quantization_BF16, Quantization_F8_E4M3):
                 raise ValueError("not support quantization type")  # edge/vectorstore.go:78
             self.Space[collectionName] = VectorSpace(collectionName, metadata, self.device, 0, self.select_mode, self.math_mode)
 

@@ -49,7 +49,12 @@ typedef enum coltt_metric { COLTT_COSINE = 0, COLTT_EUCLIDEAN = 1 } coltt_metric
 /* edgepb.Quantization (edge.proto:75-80).  BF16 is stored and decoded as IEEE binary16
  * because the reference's "bf16" codec is (pkg/compresshelper/bf16.go:233-317).
  * F8 is the reference's literal (broken) 8-bit code (float8.go:233-313).
- * F8_E4M3 is a builder extension (real fp8 rows, per-row scale) with no reference parity. */
+ * F8_E4M3 is a builder extension with no reference arithmetic (the reference's f8 is unusable): rows are
+ * OCP E4M3 codes (round-to-nearest-even, saturating) plus one power-of-two scale per row,
+ *   s = 2^clamp(floor(log2(max|v|)) - 7, -40, 40),  code_i = e4m3(v_i / s),  value_i = s * decode(code_i),
+ * the query is lowered the same way (as f8_vectorstore.go:136-139 lowers it) and the distance is the reference's
+ * arithmetic over the dequantized values (f8_quantization.go:33-43 -> pkg/distance).  SaveVertex/LoadVertex have no
+ * layout for it (export/import return COLTT_ERR_UNSUPPORTED). */
 typedef enum coltt_quant {
   COLTT_QUANT_NONE = 0,
   COLTT_QUANT_F16 = 1,
@@ -109,6 +114,13 @@ COLTT_API int coltt_b200_store_upsert(coltt_store* s, const uint64_t* ids, const
 /* vectorspace.RemoveVertex after the Go side resolved dropFilter to ids
  * (none_vectorstore.go:105-127).  Unknown ids are ignored like the Go `delete`. */
 COLTT_API int coltt_b200_store_remove(coltt_store* s, const uint64_t* ids, size_t n);
+
+/* Bulk ChangedVertex for rows that already live in device memory (shards too large to stage through host memory:
+ * BASELINE config 4 is 10 M x 1536 fp32 = 61 GB per GPU): d_vecs is device fp32 [n][stride_floats] (stride_floats >=
+ * dim), normalized + lowered exactly as coltt_b200_store_upsert does; row j of the call gets id = id_base + slot,
+ * slot = rows already stored + j.  The store keeps no host id map for such rows: it answers searches, and rejects
+ * upsert / remove / export / search_subset with COLTT_ERR_UNSUPPORTED. */
+COLTT_API int coltt_b200_store_append_dev(coltt_store* s, const void* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base);
 
 /* vectorspace.VertexSearch (edge/none_vectorstore.go:129-180 and the bf16/f16/f8 twins),
  * batched: nq un-normalized fp32 queries (host), top-k each.  The reference call is nq = 1;
@@ -223,6 +235,12 @@ COLTT_API int coltt_b200_store_last_timing(coltt_store* s, float* ms, int n);
 /* Per-phase events are recorded only while timing is on (default off: the event records sit between
  * kernels of a sub-millisecond search). */
 COLTT_API int coltt_b200_store_set_timing(coltt_store* s, int on);
+/* COLTT_MATH_FAST statistics of a handle: out2[0] = queries answered through the tensor-core filter, out2[1] = how many of
+ * them the certificate sent to the exact re-run. */
+COLTT_API int coltt_b200_store_fast_stats(coltt_store* s, uint64_t* out2);
+/* The certificate margin COLTT_MATH_FAST uses for a collection of this dimension, relative to ||q|| * ||row||
+ * (DESIGN.md section 5): tests compare the filter's raw scores against it. */
+COLTT_API float coltt_b200_fast_eps_rel(uint32_t dim);
 /* Kernels this library has launched in this process so far (bench.py's gpu_launches). */
 COLTT_API uint64_t coltt_b200_kernel_launches(void);
 

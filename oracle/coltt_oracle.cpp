@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <string>
@@ -168,6 +169,64 @@ ORC_API void orc_f32_to_f8_array(const float* in, uint8_t* out, size_t n) {
 }
 ORC_API void orc_f8_to_f32_array(const uint8_t* in, float* out, size_t n) {
   for (size_t i = 0; i < n; i++) out[i] = bitsf32(orc_f8bits_to_f32bits(in[i]));
+}
+
+// ---------------------------------------------------------------------------
+// F8_E4M3 — BUILDER-DEFINED extension, NOT reference arithmetic (the reference's f8
+// codec is broken, so BASELINE config 4's performance mode is a real fp8 store).  PARITY UNPINNED against
+// the reference by construction; the codec itself is pinned against an independent IEEE-style implementation
+// (torch.float8_e4m3fn) in tests/test_oracle.py.  Format: OCP FP8 E4M3 ("fn": no infinities, 0x7f = NaN,
+// max 448), round-to-nearest-even, saturating.  A vector v is lowered as
+//     s     = 2^clamp(floor(log2(max|v_i|)) - 7, -40, 40)        (1.0 when max|v_i| is 0 or not finite)
+//     c_i   = e4m3_rne_sat(v_i / s)                               (so max|v_i|/s lies in [128, 256))
+//     x_i   = s * e4m3_decode(c_i)                                (the dequantized value; exact: s is a power of two)
+// and, as in every quantized store of the reference ({f16,bf16,f8}_quantization.go:33-43), Similarity
+// dequantizes BOTH operands (the query is lowered too, f8_vectorstore.go:136-139) and calls dist.Distance.
+// ---------------------------------------------------------------------------
+ORC_API float orc_e4m3_decode(uint8_t c) {
+  const int e = (c >> 3) & 15, m = c & 7;
+  float v;
+  if (e == 15 && m == 7) v = std::numeric_limits<float>::quiet_NaN();
+  else if (e == 0) v = std::ldexp((float)m, -9);
+  else v = std::ldexp((float)(8 + m), e - 10);
+  return (c & 0x80) ? -v : v;
+}
+ORC_API uint8_t orc_e4m3_encode(float x) {
+  const uint8_t sign = std::signbit(x) ? 0x80 : 0x00;
+  const float a = std::fabs(x);
+  if (a != a) return (uint8_t)(sign | 0x7f);
+  if (a > 448.0f) return (uint8_t)(sign | 0x7e);        // saturate (values in (448, 464) would round down to 448 anyway)
+  if (a < 0.015625f) {                                   // below 2^-6: subnormal grid of 2^-9
+    const int q = (int)std::nearbyint(std::ldexp(a, 9)); // exact scaling, RNE (default rounding mode)
+    return (uint8_t)(sign | q);                          // q == 8 is the smallest normal, 0x08
+  }
+  int e;
+  const float m = std::frexp(a, &e);                     // a = m * 2^e, m in [0.5, 1)
+  int q = (int)std::nearbyint(std::ldexp(m, 4));         // significand on a grid of 1/8: q in [8, 16]
+  e -= 1;
+  if (q == 16) { q = 8; e += 1; }
+  return (uint8_t)(sign | ((e + 7) << 3) | (q - 8));
+}
+ORC_API float orc_e4m3_scale(const float* v, size_t n) {
+  float mx = 0.0f;
+  bool bad = false;
+  for (size_t i = 0; i < n; i++) { const float a = std::fabs(v[i]); if (!(a <= std::numeric_limits<float>::max())) bad = true; else if (a > mx) mx = a; }
+  if (bad || mx == 0.0f) return 1.0f;
+  int e;
+  std::frexp(mx, &e);                                    // mx in [2^(e-1), 2^e)
+  int es = (e - 1) - 7;
+  if (es < -40) es = -40;
+  if (es > 40) es = 40;
+  return std::ldexp(1.0f, es);
+}
+ORC_API float orc_f32_to_e4m3_array(const float* in, uint8_t* out, size_t n) {
+  const float s = orc_e4m3_scale(in, n);
+  const float inv = 1.0f / s;                            // exact: power of two
+  for (size_t i = 0; i < n; i++) out[i] = orc_e4m3_encode(in[i] * inv);
+  return s;
+}
+ORC_API void orc_e4m3_to_f32_array(const uint8_t* in, float scale, float* out, size_t n) {
+  for (size_t i = 0; i < n; i++) out[i] = scale * orc_e4m3_decode(in[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -440,7 +499,7 @@ struct EdgePQ {
 // ---------------------------------------------------------------------------
 // edge FLAT store restatement: {none,f16,bf16,f8}_vectorstore.go
 // ---------------------------------------------------------------------------
-enum { Q_NONE = 0, Q_F16 = 1, Q_F8 = 2, Q_BF16 = 3 };  // idl/proto/v4/edge.proto:75-80
+enum { Q_NONE = 0, Q_F16 = 1, Q_F8 = 2, Q_BF16 = 3, Q_F8E = 16 };  // idl/proto/v4/edge.proto:75-80; 16 = builder-defined E4M3 (see codecs)
 enum { M_COSINE = 0, M_EUCLID = 1 };                  // edge.proto:69-72
 static const int kShards = 16;                        // edge/constants.go:49
 
@@ -451,11 +510,12 @@ struct OrcStore {
   std::vector<float> f32[kShards];
   std::vector<uint16_t> f16[kShards];
   std::vector<uint8_t> f8[kShards];
+  std::vector<float> scale[kShards];   // Q_F8E: per-row power-of-two scale
   std::vector<size_t> free_slots[kShards];
 };
 
 ORC_API OrcStore* orc_store_create(uint32_t dim, int metric, int quant) {
-  if (quant < 0 || quant > 3 || metric < 0 || metric > 1 || dim == 0) return nullptr;
+  if (!((quant >= 0 && quant <= 3) || quant == Q_F8E) || metric < 0 || metric > 1 || dim == 0) return nullptr;
   OrcStore* s = new OrcStore();
   s->dim = dim; s->metric = metric; s->quant = quant;
   return s;
@@ -484,6 +544,7 @@ ORC_API int orc_store_upsert(OrcStore* s, const uint64_t* ids, const float* vecs
         size_t need = (slot + 1) * (size_t)s->dim;
         if (s->quant == Q_NONE) { if (s->f32[sh].size() < need) s->f32[sh].resize(need); }
         else if (s->quant == Q_F8) { if (s->f8[sh].size() < need) s->f8[sh].resize(need); }
+        else if (s->quant == Q_F8E) { if (s->f8[sh].size() < need) s->f8[sh].resize(need); if (s->scale[sh].size() < slot + 1) s->scale[sh].resize(slot + 1); }
         else { if (s->f16[sh].size() < need) s->f16[sh].resize(need); }
       }
       s->index[sh][ids[r]] = slot;
@@ -491,6 +552,7 @@ ORC_API int orc_store_upsert(OrcStore* s, const uint64_t* ids, const float* vecs
     size_t off = slot * (size_t)s->dim;
     if (s->quant == Q_NONE) std::memcpy(&s->f32[sh][off], v, 4 * (size_t)s->dim);
     else if (s->quant == Q_F8) orc_f32_to_f8_array(v, &s->f8[sh][off], s->dim);     // f8_quantization.go:45-51
+    else if (s->quant == Q_F8E) s->scale[sh][slot] = orc_f32_to_e4m3_array(v, &s->f8[sh][off], s->dim);
     else orc_f32_to_f16_array(v, &s->f16[sh][off], s->dim);                         // f16/bf16_quantization.go Lower
   }
   return 0;
@@ -512,6 +574,7 @@ struct QueryCtx {
   std::vector<float> q32;       // normalized (cosine) query, fp32 path
   std::vector<uint16_t> q16;    // Lower(query) for f16/bf16 stores
   std::vector<uint8_t> q8;      // Lower(query) for f8 store
+  float q_scale = 1.0f;         // Q_F8E
 };
 
 static void prep_query(const OrcStore* s, const float* query, QueryCtx& c) {
@@ -520,6 +583,7 @@ static void prep_query(const OrcStore* s, const float* query, QueryCtx& c) {
   else std::memcpy(c.q32.data(), query, 4 * (size_t)s->dim);
   if (s->quant == Q_F16 || s->quant == Q_BF16) { c.q16.resize(s->dim); orc_f32_to_f16_array(c.q32.data(), c.q16.data(), s->dim); }
   if (s->quant == Q_F8) { c.q8.resize(s->dim); orc_f32_to_f8_array(c.q32.data(), c.q8.data(), s->dim); }
+  if (s->quant == Q_F8E) { c.q8.resize(s->dim); c.q_scale = orc_f32_to_e4m3_array(c.q32.data(), c.q8.data(), s->dim); }
 }
 
 // Quantization.Similarity: quantization.go:43-45 (none) and
@@ -539,6 +603,9 @@ static inline float similarity(const OrcStore* s, const QueryCtx& c, int sh, siz
     float* bx = sc.bx.get(d); float* by = sc.by.get(d);
     if (s->quant == Q_F8) {
       for (size_t i = 0; i < d; i++) { bx[i] = bitsf32(orc_f8bits_to_f32bits(c.q8[i])); by[i] = bitsf32(orc_f8bits_to_f32bits(s->f8[sh][off + i])); }
+    } else if (s->quant == Q_F8E) {
+      orc_e4m3_to_f32_array(c.q8.data(), c.q_scale, bx, d);
+      orc_e4m3_to_f32_array(&s->f8[sh][off], s->scale[sh][slot], by, d);
     } else {
       for (size_t i = 0; i < d; i++) { bx[i] = bitsf32(orc_f16bits_to_f32bits(c.q16[i])); by[i] = bitsf32(orc_f16bits_to_f32bits(s->f16[sh][off + i])); }
     }
@@ -669,7 +736,7 @@ ORC_API int orc_store_get_row(OrcStore* s, uint64_t id, void* out) {
   if (it == s->index[sh].end()) return -1;
   size_t off = it->second * (size_t)s->dim;
   if (s->quant == Q_NONE) std::memcpy(out, &s->f32[sh][off], 4 * (size_t)s->dim);
-  else if (s->quant == Q_F8) std::memcpy(out, &s->f8[sh][off], s->dim);
+  else if (s->quant == Q_F8 || s->quant == Q_F8E) std::memcpy(out, &s->f8[sh][off], s->dim);
   else std::memcpy(out, &s->f16[sh][off], 2 * (size_t)s->dim);
   return 0;
 }

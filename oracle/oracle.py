@@ -54,6 +54,16 @@ def lib() -> C.CDLL:
                            ("orc_f32_to_f8_array", f32p, u8p), ("orc_f8_to_f32_array", u8p, f32p)):
             getattr(L, name).argtypes = [a, b, C.c_size_t]
             getattr(L, name).restype = None
+        L.orc_e4m3_decode.argtypes = [C.c_uint8]
+        L.orc_e4m3_decode.restype = C.c_float
+        L.orc_e4m3_encode.argtypes = [C.c_float]
+        L.orc_e4m3_encode.restype = C.c_uint8
+        L.orc_e4m3_scale.argtypes = [f32p, C.c_size_t]
+        L.orc_e4m3_scale.restype = C.c_float
+        L.orc_f32_to_e4m3_array.argtypes = [f32p, u8p, C.c_size_t]
+        L.orc_f32_to_e4m3_array.restype = C.c_float
+        L.orc_e4m3_to_f32_array.argtypes = [u8p, C.c_float, f32p, C.c_size_t]
+        L.orc_e4m3_to_f32_array.restype = None
         L.orc_normalize.argtypes = [f32p, C.c_size_t, f32p]
         L.orc_normalize.restype = None
         L.orc_cosine_dot_norm.argtypes = [C.c_size_t, f32p, f32p, f32p, f32p]
@@ -202,6 +212,34 @@ def f8_to_f32(a):
     return out
 
 
+def e4m3_encode(a):
+    """Element-wise OCP E4M3 (fn) encode, RNE, saturating — builder-defined F8_E4M3 store (no scaling here)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    L = lib()
+    return np.array([L.orc_e4m3_encode(float(x)) for x in a.ravel()], dtype=np.uint8).reshape(a.shape)
+
+
+def e4m3_decode(c):
+    c = np.ascontiguousarray(c, dtype=np.uint8)
+    L = lib()
+    return np.array([L.orc_e4m3_decode(int(x)) for x in c.ravel()], dtype=np.float32).reshape(c.shape)
+
+
+def f32_to_e4m3(v):
+    """Lower one vector the way the F8_E4M3 store does: (codes, power-of-two scale)."""
+    v, vp = _f32(v)
+    out = np.empty(v.shape, dtype=np.uint8)
+    s = lib().orc_f32_to_e4m3_array(vp, out.ctypes.data_as(u8p), v.size)
+    return out, np.float32(s)
+
+
+def e4m3_to_f32(codes, scale):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    out = np.empty(codes.shape, dtype=np.float32)
+    lib().orc_e4m3_to_f32_array(codes.ctypes.data_as(u8p), float(scale), out.ctypes.data_as(f32p), codes.size)
+    return out
+
+
 def cosine_distance(a, b):
     a, ap = _f32(a)
     b, bp = _f32(b)
@@ -225,6 +263,7 @@ def shard_vertex(x: int, c: int = 16) -> int:
 
 COSINE, EUCLIDEAN = 0, 1
 Q_NONE, Q_F16, Q_F8, Q_BF16 = 0, 1, 2, 3
+Q_F8_E4M3 = 16   # builder-defined real-fp8 store (no reference arithmetic: parity unpinned)
 COLTT_COMPAT, NEAREST = 0, 1
 
 
@@ -288,7 +327,7 @@ class FlatStore:
         return ids[:n], sc[:n]
 
     def get_row(self, id_: int):
-        dt = {Q_NONE: np.float32, Q_F8: np.uint8}.get(self.quant, np.uint16)
+        dt = {Q_NONE: np.float32, Q_F8: np.uint8, Q_F8_E4M3: np.uint8}.get(self.quant, np.uint16)
         out = np.zeros(self.dim, dtype=dt)
         if lib().orc_store_get_row(self._h, id_, out.ctypes.data_as(C.c_void_p)) != 0:
             raise KeyError(id_)

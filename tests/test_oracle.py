@@ -339,3 +339,57 @@ def test_lane_emulation_reproduces_the_committed_reference_outputs(oracle):
         L.orc_cosine_dot_norm(c["dim"], ap, bp, C.byref(dot), C.byref(n2))
         L.orc_l2sq(c["dim"], ap, bp, C.byref(l2))
         assert (bits(dot.value), bits(n2.value), bits(l2.value)) == (c["dot"], c["norm2"], c["l2sq"]), c
+
+
+def test_e4m3_codec_against_torch_float8(oracle):
+    """The builder-defined F8_E4M3 store has no reference arithmetic (parity unpinned); its codec is pinned here against
+    an independent implementation, torch.float8_e4m3fn: all 256 decodes, and RNE encodes of random values, every
+    representable value, every midpoint between neighbours and their fp32 neighbours (|x| <= 448; above that we
+    saturate to 448 where torch's cast yields NaN)."""
+    import torch
+    codes = np.arange(256, dtype=np.uint8)
+    t = torch.from_numpy(codes).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+    d = oracle.e4m3_decode(codes)
+    nan = np.isnan(t)
+    assert np.array_equal(nan, np.isnan(d)) and np.array_equal(t[~nan].view(np.uint32), d[~nan].view(np.uint32))
+    r = np.random.Generator(np.random.Philox(7))
+    x = r.standard_normal(100_000).astype(np.float32) * r.choice(np.array([1e-3, 1e-2, .1, 1, 10, 100], np.float32), 100_000)
+    vals = np.sort(np.unique(d[~nan]))
+    mids = ((vals[:-1].astype(np.float64) + vals[1:]) / 2).astype(np.float32)
+    x = np.concatenate([x, vals, mids, np.nextafter(mids, np.float32(1e9)), np.nextafter(mids, np.float32(-1e9))])
+    x = x[np.abs(x) <= 448]
+    want = torch.from_numpy(x).to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+    assert np.array_equal(oracle.e4m3_encode(x), want)
+    assert oracle.e4m3_encode(np.float32([1e9, -1e9, 460.0]))[:3].tolist() == [0x7e, 0xfe, 0x7e]   # saturating
+
+
+def test_e4m3_lowering_scale_and_store(oracle):
+    """Lower(v): s = 2^clamp(floor(log2 max|v|) - 7, -40, 40) puts max|v|/s in [128, 256); zero / non-finite vectors use 1."""
+    r = np.random.Generator(np.random.Philox(9))
+    for mag in (1e-30, 1e-3, 1.0, 77.0, 1e20):
+        v = (r.standard_normal(300) * mag).astype(np.float32)
+        c, s = oracle.f32_to_e4m3(v)
+        m = np.abs(v).max()
+        lo, hi = (128, 256) if 2.0 ** -40 * 128 <= m < 2.0 ** 40 * 256 else (0, np.inf)
+        assert lo <= m / s < hi and np.log2(s) == np.round(np.log2(s))
+        back = oracle.e4m3_to_f32(c, s)
+        if lo:
+            assert np.abs(back - v).max() <= m / 16 + 1e-30      # 3 mantissa bits at the top of the range
+    assert oracle.f32_to_e4m3(np.zeros(8, np.float32))[1] == 1.0
+    assert oracle.f32_to_e4m3(np.float32([1, np.inf, 2]))[1] == 1.0
+    # the store: scores equal the reference arithmetic over the dequantized operands
+    n, d = 300, 40
+    vecs = r.standard_normal((n, d)).astype(np.float32)
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    st = oracle.FlatStore(d, oracle.COSINE, oracle.Q_F8_E4M3)
+    st.upsert(ids, vecs)
+    q = r.standard_normal(d).astype(np.float32)
+    wi, ws = st.search_total_order(q, 5, select_mode=oracle.NEAREST)
+    cq, sq = oracle.f32_to_e4m3(oracle.normalize(q))
+    qd = oracle.e4m3_to_f32(cq, sq)
+    sc = []
+    for v in vecs:
+        cr, sr = oracle.f32_to_e4m3(oracle.normalize(v))
+        sc.append(oracle.cosine_distance(qd, oracle.e4m3_to_f32(cr, sr)))
+    order = np.lexsort((ids, np.float32(sc)))[:5]
+    assert np.array_equal(wi, ids[order]) and np.array_equal(ws, np.float32(sc)[order])
