@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--quant", default=None, choices=["bf16", "none", "f8_e4m3"],
+                    help="store quantization (default: the workload's); none = fp32 rows, filtered through their fp16 shadow")
     ap.add_argument("--no-extras", action="store_true", help="skip the compact c3 / c4 records of the default line")
     ap.add_argument("--math", default="auto", choices=["auto", "exact", "fast"])
     ap.add_argument("--cpu-rows", type=int, default=250_000, help="rows of the bounded CPU-baseline sample")
@@ -55,7 +57,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / recall legs (profiling runs)")
     a = ap.parse_args()
     wl = WORKLOADS["flat" if a.workload == "hnsw" else a.workload]
-    for key in ("rows", "dim", "batch", "k", "steps", "warmup"):
+    for key in ("rows", "dim", "batch", "k", "steps", "warmup", "quant"):
         if getattr(a, key) is None:
             setattr(a, key, wl[key])
     return a
@@ -375,8 +377,9 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
     L = _lib.lib()
     dev = torch.device("cuda", local)
     n, d, nq, k = args.rows, args.dim, args.batch, args.k
-    fp8 = wl["quant"] == "f8_e4m3"
-    quant = cb.Quantization_F8_E4M3 if fp8 else cb.Quantization_BF16
+    qname = getattr(args, "quant", None) or wl["quant"]
+    fp8 = qname == "f8_e4m3"
+    quant = {"f8_e4m3": cb.Quantization_F8_E4M3, "bf16": cb.Quantization_BF16, "none": cb.Quantization_None}[qname]
     math_mode = {"auto": cb.MATH_FAST,   # tcgen05 filter + exact re-rank: bit-identical results to EXACT (tests/test_gpu_fast.py, test_gpu_f8e.py)
                  "exact": cb.MATH_EXACT, "fast": cb.MATH_FAST}[args.math]
     t0 = time.perf_counter()
@@ -400,24 +403,21 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
     out = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)      # coltt_hit = 16 B
     cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(device=dev)
+    comm = None
     if world > 1:
-        packed = torch.zeros((nq * k * 4 + nq,), dtype=torch.int32, device=dev)          # hits + counts of this shard
-        gathered_flat = torch.zeros((world * (nq * k * 4 + nq),), dtype=torch.int32, device=dev)
+        # the sharded search lives behind the C-ABI (csrc/comm.cu): local search -> ONE ncclAllGather of per-shard top-k ->
+        # K5 merge, on one stream inside the library; torch.distributed only carries the rendezvous blob and the barriers
+        from coltt_b200.dist import Comm
+        comm = Comm.from_torch_distributed(local)
         fin = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
         fcnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
 
     def step_dev(i):
-        _lib.check(L.coltt_b200_store_search_dev(sp._h, q_dev[i % n_qsets].data_ptr(), nq, k, cb.SELECT_NEAREST, math_mode,
-                                                  out.data_ptr(), cnt.data_ptr(), stream.cuda_stream))
         if world > 1:
-            # the one exchange step of the sharded search: all-gather of per-shard top-k (counts ride along in
-            # the same message), then the K5 merge on every rank
-            with torch.cuda.stream(stream):
-                packed[:nq * k * 4].copy_(out.view(-1), non_blocking=True)
-                packed[nq * k * 4:].copy_(cnt, non_blocking=True)
-                dist.all_gather_into_tensor(gathered_flat, packed)
-            _lib.check(L.coltt_b200_merge_topk_dev2(local, gathered_flat.data_ptr(), world, nq, k, k, cb.SELECT_NEAREST, (nq * k * 4 + nq) * 4,
-                                                     nq * k * 16, fin.data_ptr(), fcnt.data_ptr(), stream.cuda_stream))
+            comm.search_dev(sp, q_dev[i % n_qsets].data_ptr(), nq, k, cb.SELECT_NEAREST, math_mode, fin.data_ptr(), fcnt.data_ptr(), stream.cuda_stream)
+        else:
+            _lib.check(L.coltt_b200_store_search_dev(sp._h, q_dev[i % n_qsets].data_ptr(), nq, k, cb.SELECT_NEAREST, math_mode,
+                                                      out.data_ptr(), cnt.data_ptr(), stream.cuda_stream))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -485,17 +485,12 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
             merge_check = "ok" if ok else "MISMATCH"
 
     # ---- end to end: host buffers in, host results out.  N=1: the host-pointer C-ABI call.  N>1: the sharded
-    # public API (coltt_b200.dist.ShardedSearch): H2D of the queries, per-shard search, all-gather, merge, D2H.
+    # C-ABI call coltt_b200_sharded_search: H2D of the queries, per-shard search, all-gather, merge, D2H.
     e2e_value = e2e_steps = None
     if not light:
         if world > 1:
-            from coltt_b200.dist import ShardedSearch, cuda_callables, unpack_hits
-            ls, mg = cuda_callables(sp, local, math_mode=math_mode)
-            sharded = ShardedSearch(ls, mg)
-
-            def e2e_step(i):
-                hits, c2 = sharded.search(q_host[i % n_qsets], k, cb.SELECT_NEAREST)
-                return unpack_hits(hits, c2)
+            def e2e_step(i):     # coltt_b200_sharded_search: host queries in, merged host results out, on every rank
+                return comm.search(sp, q_host[i % n_qsets], k, cb.SELECT_NEAREST, math_mode)
         else:
             def e2e_step(i):
                 return sp.BatchVertexSearch(q_host[i % n_qsets], k)
@@ -535,13 +530,15 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
         recall = float(np.mean([len(np.intersect1d(gt[j], gi[j, :k])) / k for j in range(rq)]))   # edge/resultset.go:55-65
         recall_note = f"{rq} queries vs fp32 exact ground truth (torch fp32 matmul over the regenerated rows) over all {n} rows"
 
+    if comm is not None:
+        comm.close()
     if rank != 0:
         sp.close()
         return None
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peaks = measured_peaks()
-    es = wl["es"]
+    es = {"f8_e4m3": 1, "bf16": 2, "none": 2}[qname]      # bytes per element the dominant kernel streams (fp32 stores: the fp16 shadow)
     passes = (nq + 7) // 8 if math_mode == cb.MATH_EXACT else 1
     alg_bytes = n * d * es + n * 4 + (n * 4 if fp8 else 0) + nq * d * 4 + nq * k * 16          # SURVEY §8(d), one pass (+ row scales)
     flops = 2.0 * nq * n * d
@@ -562,7 +559,8 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
     line = {"metric": wl["metric"], "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
-            "config": {"workload": wl["name"], "rows_per_gpu": n, "dim": d, "batch": nq, "k": k, "select": "nearest",
+            "config": {"workload": wl["name"] if qname == wl["quant"] else wl["name"] + f" [store quantization overridden: {qname}]",
+                       "rows_per_gpu": n, "dim": d, "batch": nq, "k": k, "select": "nearest",
                        "math": "exact" if math_mode == cb.MATH_EXACT else "fast(tcgen05)+exact rerank",
                        "l2": f"shard {n * d * es / 1e9:.2f} GB > 126 MB L2 (inputs larger than L2)", "unit_note":
                        "weak scaling: every rank holds its own shard of rows_per_gpu rows and every query is answered over all "
@@ -656,7 +654,7 @@ def main():
         try:
             a4 = argparse.Namespace(**vars(args))
             w4 = WORKLOADS["c4"]
-            for key in ("rows", "dim", "batch", "k", "steps", "warmup"):
+            for key in ("rows", "dim", "batch", "k", "steps", "warmup", "quant"):
                 setattr(a4, key, w4[key])
             r4 = flat_arm(a4, w4, torch, None, 1, 0, local, light=True)
             line["c4"] = {kk: r4[kk] for kk in ("value", "unit", "ms_per_step", "steps", "kernel_ms", "fast_path", "clocks", "recall_at_100", "recall_note") if kk in r4}

@@ -33,6 +33,14 @@ func NewBatcher(s *Store, dim, maxBatch int, maxWait time.Duration, selectMode, 
 
 // VertexSearch: what Edge.Search calls instead of Vectorstore.VertexSearch (edge/edge.go:653).
 func (b *Batcher) VertexSearch(target []float32, topK int) ([]Hit, error) {
+	// validated here, before the request can reach the shared batch: one wrong-length query would shift every later
+	// query of the flattened batch, and topK <= 0 would panic the single flusher goroutine
+	if len(target) != b.dim {
+		return nil, errDim(b.dim, len(target))
+	}
+	if topK <= 0 {
+		return nil, errTopK
+	}
 	r := batchReq{q: target, topK: topK, out: make(chan batchRes, 1)}
 	b.in <- r
 	res := <-r.out

@@ -19,6 +19,7 @@ import "C"
 
 import (
 	"errors"
+	"fmt"
 	"runtime"
 	"unsafe"
 )
@@ -31,15 +32,30 @@ const (
 	MathFast      = 1
 )
 
-func lastErr(rc C.int) error {
-	if rc == 0 {
-		return nil
+// call runs one C-ABI call and, on failure, fetches its message.  coltt_b200_last_error() is thread-local on the C
+// side and a goroutine may migrate between OS threads from one cgo call to the next, so the call and the read of
+// its message are pinned to one OS thread.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != 0 {
+		return errors.New(C.GoString(C.coltt_b200_last_error()))
 	}
-	return errors.New(C.GoString(C.coltt_b200_last_error()))
+	return nil
 }
 
+// errDim is the reference's dimension error (edge/none_vectorstore.go:86-88).
+func errDim(want, got int) error {
+	return fmt.Errorf("Dim Length UnmatchdError: expect dimension: [%d], but got [%d]", want, got)
+}
+
+var errTopK = errors.New("topK must be positive")
+
 // Store is one edge collection's vectors on one GPU.
-type Store struct{ h *C.coltt_store }
+type Store struct {
+	h   *C.coltt_store
+	dim int
+}
 
 // NewStore replaces newNoneVectorstore / newF16Vectorstore / newBF16Vectorstore / newF8Vectorstore
 // (edge/vectorstore.go:62-85).  distance and quantization are the edgepb enum values.
@@ -47,10 +63,10 @@ func NewStore(dim uint32, distance, quantization int32, device int32, capacityHi
 	cfg := C.coltt_store_cfg{dim: C.uint32_t(dim), metric: C.int32_t(distance), quant: C.int32_t(quantization),
 		device: C.int32_t(device), capacity_hint: C.uint64_t(capacityHint)}
 	var h *C.coltt_store
-	if err := lastErr(C.coltt_b200_store_create(&cfg, &h)); err != nil {
+	if err := call(func() C.int { return C.coltt_b200_store_create(&cfg, &h) }); err != nil {
 		return nil, err
 	}
-	s := &Store{h: h}
+	s := &Store{h: h, dim: int(dim)}
 	runtime.SetFinalizer(s, func(s *Store) { s.Close() })
 	return s, nil
 }
@@ -64,8 +80,12 @@ func (s *Store) Close() {
 
 // ChangedVertex: edge/none_vectorstore.go:66-103 (normalize + Lower happen on the GPU).
 func (s *Store) ChangedVertex(id uint64, vector []float32) error {
-	return lastErr(C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&id)),
-		(*C.float)(unsafe.Pointer(&vector[0])), 1))
+	if len(vector) != s.dim {
+		return errDim(s.dim, len(vector))
+	}
+	return call(func() C.int {
+		return C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&id)), (*C.float)(unsafe.Pointer(&vector[0])), 1)
+	})
 }
 
 // ChangedVertices is the batched form (bulk load).
@@ -73,8 +93,12 @@ func (s *Store) ChangedVertices(ids []uint64, vectors []float32) error {
 	if len(ids) == 0 {
 		return nil
 	}
-	return lastErr(C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])),
-		(*C.float)(unsafe.Pointer(&vectors[0])), C.size_t(len(ids))))
+	if len(vectors) != len(ids)*s.dim {
+		return errDim(len(ids)*s.dim, len(vectors))
+	}
+	return call(func() C.int {
+		return C.coltt_b200_store_upsert(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&vectors[0])), C.size_t(len(ids)))
+	})
 }
 
 // RemoveVertex after dropFilter was resolved to ids (none_vectorstore.go:105-127).
@@ -82,7 +106,9 @@ func (s *Store) RemoveVertex(ids []uint64) error {
 	if len(ids) == 0 {
 		return nil
 	}
-	return lastErr(C.coltt_b200_store_remove(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])), C.size_t(len(ids))))
+	return call(func() C.int {
+		return C.coltt_b200_store_remove(s.h, (*C.uint64_t)(unsafe.Pointer(&ids[0])), C.size_t(len(ids)))
+	})
 }
 
 // Hit is edge.SearchResultItem without the metadata map (the caller re-attaches it by Id).
@@ -93,12 +119,19 @@ type Hit struct {
 
 // VertexSearch: edge/none_vectorstore.go:129-180.  highCpu has no meaning on the GPU.
 func (s *Store) VertexSearch(target []float32, topK int, selectMode, mathMode int) ([]Hit, error) {
+	if len(target) != s.dim {
+		return nil, errDim(s.dim, len(target))
+	}
+	if topK <= 0 {
+		return nil, errTopK
+	}
 	ids := make([]uint64, topK)
 	scores := make([]float32, topK)
 	var count C.int32_t
-	rc := C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1, C.int(topK), C.int(selectMode), C.int(mathMode),
-		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
-	if err := lastErr(rc); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1, C.int(topK), C.int(selectMode), C.int(mathMode),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	}); err != nil {
 		return nil, err
 	}
 	out := make([]Hit, int(count))
@@ -113,13 +146,20 @@ func (s *Store) FilterableVertexSearch(candidates []uint64, target []float32, to
 	if len(candidates) == 0 {
 		return nil, nil
 	}
+	if len(target) != s.dim {
+		return nil, errDim(s.dim, len(target))
+	}
+	if topK <= 0 {
+		return nil, errTopK
+	}
 	ids := make([]uint64, topK)
 	scores := make([]float32, topK)
 	var count C.int32_t
-	rc := C.coltt_b200_store_search_subset(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1,
-		(*C.uint64_t)(unsafe.Pointer(&candidates[0])), C.size_t(len(candidates)), C.int(topK), C.int(selectMode),
-		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
-	if err := lastErr(rc); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_store_search_subset(s.h, (*C.float)(unsafe.Pointer(&target[0])), 1,
+			(*C.uint64_t)(unsafe.Pointer(&candidates[0])), C.size_t(len(candidates)), C.int(topK), C.int(selectMode),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	}); err != nil {
 		return nil, err
 	}
 	out := make([]Hit, int(count))
@@ -131,22 +171,33 @@ func (s *Store) FilterableVertexSearch(candidates []uint64, target []float32, to
 
 // BatchVertexSearch is the new surface a micro-batcher in Edge.Search (edge/edge.go:610-690) would call.
 func (s *Store) BatchVertexSearch(targets []float32, nq, topK int, selectMode, mathMode int) ([]uint64, []float32, []int32, error) {
+	if nq <= 0 {
+		return nil, nil, nil, nil
+	}
+	if len(targets) != nq*s.dim {
+		return nil, nil, nil, errDim(nq*s.dim, len(targets))
+	}
+	if topK <= 0 {
+		return nil, nil, nil, errTopK
+	}
 	ids := make([]uint64, nq*topK)
 	scores := make([]float32, nq*topK)
 	counts := make([]int32, nq)
-	rc := C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&targets[0])), C.size_t(nq), C.int(topK), C.int(selectMode), C.int(mathMode),
-		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&counts[0])))
-	return ids, scores, counts, lastErr(rc)
+	err := call(func() C.int {
+		return C.coltt_b200_store_search(s.h, (*C.float)(unsafe.Pointer(&targets[0])), C.size_t(nq), C.int(topK), C.int(selectMode), C.int(mathMode),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&counts[0])))
+	})
+	return ids, scores, counts, err
 }
 
 // SaveVertex / LoadVertex: edge/none_vectorstore.go:308-516 (metaCount = 0; metadata is saved by the Go side).
 func (s *Store) SaveVertex() ([]byte, error) {
 	var n C.size_t
-	if err := lastErr(C.coltt_b200_store_export(s.h, nil, &n)); err != nil {
+	if err := call(func() C.int { return C.coltt_b200_store_export(s.h, nil, &n) }); err != nil {
 		return nil, err
 	}
 	buf := make([]byte, int(n)+1)
-	if err := lastErr(C.coltt_b200_store_export(s.h, unsafe.Pointer(&buf[0]), &n)); err != nil {
+	if err := call(func() C.int { return C.coltt_b200_store_export(s.h, unsafe.Pointer(&buf[0]), &n) }); err != nil {
 		return nil, err
 	}
 	return buf[:int(n)], nil
@@ -154,29 +205,46 @@ func (s *Store) SaveVertex() ([]byte, error) {
 
 func (s *Store) LoadVertex(data []byte) error {
 	if len(data) == 0 {
-		return lastErr(C.coltt_b200_store_import(s.h, nil, 0))
+		return call(func() C.int { return C.coltt_b200_store_import(s.h, nil, 0) })
 	}
-	return lastErr(C.coltt_b200_store_import(s.h, unsafe.Pointer(&data[0]), C.size_t(len(data))))
+	return call(func() C.int { return C.coltt_b200_store_import(s.h, unsafe.Pointer(&data[0]), C.size_t(len(data))) })
 }
 
 func (s *Store) LoadSize() (int64, error) {
 	var n C.uint64_t
-	err := lastErr(C.coltt_b200_store_size(s.h, &n))
+	err := call(func() C.int { return C.coltt_b200_store_size(s.h, &n) })
 	return int64(n), err
 }
 
 // Hnsw wraps a device-resident vectorindex.Hnsw built from Hnsw.Commit(w, true).
-type Hnsw struct{ h *C.coltt_hnsw }
+type Hnsw struct {
+	h   *C.coltt_hnsw
+	dim int
+}
+
+func newHnsw(h *C.coltt_hnsw) (*Hnsw, error) {
+	var d C.uint32_t
+	if err := call(func() C.int { return C.coltt_b200_hnsw_dim(h, &d) }); err != nil {
+		C.coltt_b200_hnsw_destroy(h)
+		return nil, err
+	}
+	g := &Hnsw{h: h, dim: int(d)}
+	runtime.SetFinalizer(g, func(g *Hnsw) { g.Close() })
+	return g, nil
+}
 
 // LoadHnsw: core/vectorindex/hnsw_commit.go:164-278.
 func LoadHnsw(commitBlob []byte, device int32) (*Hnsw, error) {
+	if len(commitBlob) == 0 {
+		return nil, errors.New("empty Hnsw.Commit blob")
+	}
 	var h *C.coltt_hnsw
-	if err := lastErr(C.coltt_b200_hnsw_load(unsafe.Pointer(&commitBlob[0]), C.size_t(len(commitBlob)), C.int(device), &h)); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_hnsw_load(unsafe.Pointer(&commitBlob[0]), C.size_t(len(commitBlob)), C.int(device), &h)
+	}); err != nil {
 		return nil, err
 	}
-	g := &Hnsw{h: h}
-	runtime.SetFinalizer(g, func(g *Hnsw) { g.Close() })
-	return g, nil
+	return newHnsw(h)
 }
 
 func (g *Hnsw) Close() {
@@ -188,12 +256,19 @@ func (g *Hnsw) Close() {
 
 // Search: core/vectorindex/hnsw.go:243-278 (ef <= 0 uses the ef stored in the blob).
 func (g *Hnsw) Search(query []float32, k int, ef int) ([]Hit, error) {
+	if len(query) != g.dim {
+		return nil, errDim(g.dim, len(query))
+	}
+	if k <= 0 {
+		return nil, errTopK
+	}
 	ids := make([]uint64, k)
 	scores := make([]float32, k)
 	var count C.int32_t
-	rc := C.coltt_b200_hnsw_search(g.h, (*C.float)(unsafe.Pointer(&query[0])), 1, C.int(k), C.int(ef),
-		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
-	if err := lastErr(rc); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_hnsw_search(g.h, (*C.float)(unsafe.Pointer(&query[0])), 1, C.int(k), C.int(ef),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	}); err != nil {
 		return nil, err
 	}
 	out := make([]Hit, int(count))
@@ -212,24 +287,26 @@ func BuildHnsw(dim uint32, distance int32, m, ef, efConstruction int32, device i
 	if len(levels) > 0 {
 		lv = (*C.int32_t)(unsafe.Pointer(&levels[0]))
 	}
+	if len(ids) == 0 || len(vectors) != len(ids)*int(dim) || (len(levels) > 0 && len(levels) != len(ids)) {
+		return nil, errDim(len(ids)*int(dim), len(vectors))
+	}
 	var h *C.coltt_hnsw
-	rc := C.coltt_b200_hnsw_build(&cfg, (*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&vectors[0])), lv, C.size_t(len(ids)), &h)
-	if err := lastErr(rc); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_hnsw_build(&cfg, (*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&vectors[0])), lv, C.size_t(len(ids)), &h)
+	}); err != nil {
 		return nil, err
 	}
-	g := &Hnsw{h: h}
-	runtime.SetFinalizer(g, func(g *Hnsw) { g.Close() })
-	return g, nil
+	return newHnsw(h)
 }
 
 // Commit: Hnsw.Commit(w, true) (core/vectorindex/hnsw_commit.go:69-162).
 func (g *Hnsw) Commit() ([]byte, error) {
 	var n C.size_t
-	if err := lastErr(C.coltt_b200_hnsw_commit(g.h, nil, &n)); err != nil {
+	if err := call(func() C.int { return C.coltt_b200_hnsw_commit(g.h, nil, &n) }); err != nil {
 		return nil, err
 	}
 	buf := make([]byte, int(n)+1)
-	if err := lastErr(C.coltt_b200_hnsw_commit(g.h, unsafe.Pointer(&buf[0]), &n)); err != nil {
+	if err := call(func() C.int { return C.coltt_b200_hnsw_commit(g.h, unsafe.Pointer(&buf[0]), &n) }); err != nil {
 		return nil, err
 	}
 	return buf[:int(n)], nil
@@ -239,6 +316,17 @@ func (g *Hnsw) Commit() ([]byte, error) {
 // (request order); hits come back with descending Score like multi_priority_queue.go ToSlice().
 func MultiVertexSearch(fields []*Store, queries [][]float32, ratios []int32, topK int) ([]Hit, error) {
 	nf := len(fields)
+	if nf == 0 || len(queries) != nf || len(ratios) != nf {
+		return nil, errors.New("fields, queries and ratios must have the same non-zero length")
+	}
+	if topK <= 0 {
+		return nil, errTopK
+	}
+	for j := range queries {
+		if len(queries[j]) != fields[j].dim {
+			return nil, errDim(fields[j].dim, len(queries[j]))
+		}
+	}
 	// C arrays of handles / query pointers live in C memory: cgo forbids passing Go memory that holds Go pointers
 	hs := (*[1 << 20]*C.coltt_store)(C.malloc(C.size_t(nf) * C.size_t(unsafe.Sizeof(uintptr(0)))))
 	qs := (*[1 << 20]*C.float)(C.malloc(C.size_t(nf) * C.size_t(unsafe.Sizeof(uintptr(0)))))
@@ -256,9 +344,10 @@ func MultiVertexSearch(fields []*Store, queries [][]float32, ratios []int32, top
 	ids := make([]uint64, topK)
 	scores := make([]float32, topK)
 	var count C.int32_t
-	rc := C.coltt_b200_multi_search(&hs[0], &qs[0], (*C.int32_t)(unsafe.Pointer(&ratios[0])), C.int(nf), C.int(topK),
-		(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
-	if err := lastErr(rc); err != nil {
+	if err := call(func() C.int {
+		return C.coltt_b200_multi_search(&hs[0], &qs[0], (*C.int32_t)(unsafe.Pointer(&ratios[0])), C.int(nf), C.int(topK),
+			(*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])), &count)
+	}); err != nil {
 		return nil, err
 	}
 	out := make([]Hit, int(count))
@@ -266,4 +355,95 @@ func MultiVertexSearch(fields []*Store, queries [][]float32, ratios []int32, top
 		out[i] = Hit{ids[i], scores[i]}
 	}
 	return out, nil
+}
+
+// ---- sharded collections: one shard per GPU, one NCCL all-gather of per-shard top-k, merge ---------------------------
+// Reference analogue: the 16 in-process map shards of a vectorspace re-merged after the scan
+// (edge/none_vectorstore.go:152-178).  Rows go to GPU ShardVertex(id, 16) % nGPU (pkg/sharding/shard.go:34-41).
+
+// Cluster is every GPU of this process: coltt_b200_init (ncclCommInitAll) + one Store per GPU.
+type Cluster struct {
+	comms  []*C.coltt_comm
+	Shards []*Store
+	dim    int
+}
+
+// NewCluster opens the communicators and one shard store per device.
+func NewCluster(devices []int32, dim uint32, distance, quantization int32, capacityHintPerShard uint64) (*Cluster, error) {
+	n := len(devices)
+	if n == 0 {
+		return nil, errors.New("no devices")
+	}
+	// C arrays live in C memory (cgo forbids handing C Go memory that holds pointers)
+	devs := (*[64]C.int)(C.malloc(C.size_t(n) * 4))
+	cms := (*[64]*C.coltt_comm)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(devs))
+	defer C.free(unsafe.Pointer(cms))
+	for i, d := range devices {
+		devs[i] = C.int(d)
+	}
+	if err := call(func() C.int { return C.coltt_b200_init(&devs[0], C.int(n), &cms[0]) }); err != nil {
+		return nil, err
+	}
+	c := &Cluster{dim: int(dim)}
+	for i := 0; i < n; i++ {
+		c.comms = append(c.comms, cms[i])
+		s, err := NewStore(dim, distance, quantization, devices[i], capacityHintPerShard)
+		if err != nil {
+			return nil, err
+		}
+		c.Shards = append(c.Shards, s)
+	}
+	return c, nil
+}
+
+// ShardOf is the row -> GPU map: the reference's shard identity folded onto the GPUs.
+func (c *Cluster) ShardOf(id uint64) int {
+	h := uint64(14695981039346656037)
+	for i := 0; i < 8; i++ {
+		h ^= (id >> (8 * uint(i))) & 0xff
+		h *= 1099511628211
+	}
+	return int((h % 16) % uint64(len(c.Shards)))
+}
+
+// BatchVertexSearch answers nq queries over all shards: coltt_b200_sharded_search_all runs one library thread per
+// rank (local search -> ncclAllGather -> merge) and returns rank 0's merged answer.
+func (c *Cluster) BatchVertexSearch(targets []float32, nq, topK int, selectMode, mathMode int) ([]uint64, []float32, []int32, error) {
+	if nq <= 0 {
+		return nil, nil, nil, nil
+	}
+	if len(targets) != nq*c.dim {
+		return nil, nil, nil, errDim(nq*c.dim, len(targets))
+	}
+	if topK <= 0 {
+		return nil, nil, nil, errTopK
+	}
+	n := len(c.comms)
+	cms := (*[64]*C.coltt_comm)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	shs := (*[64]*C.coltt_store)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(cms))
+	defer C.free(unsafe.Pointer(shs))
+	for i := 0; i < n; i++ {
+		cms[i] = c.comms[i]
+		shs[i] = c.Shards[i].h
+	}
+	ids := make([]uint64, nq*topK)
+	scores := make([]float32, nq*topK)
+	counts := make([]int32, nq)
+	err := call(func() C.int {
+		return C.coltt_b200_sharded_search_all(&cms[0], &shs[0], C.int(n), (*C.float)(unsafe.Pointer(&targets[0])), C.size_t(nq), C.int(topK),
+			C.int(selectMode), C.int(mathMode), (*C.uint64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&scores[0])),
+			(*C.int32_t)(unsafe.Pointer(&counts[0])))
+	})
+	return ids, scores, counts, err
+}
+
+// Close destroys the shard stores and every communicator of the process.
+func (c *Cluster) Close() {
+	for _, s := range c.Shards {
+		s.Close()
+	}
+	C.coltt_b200_shutdown()
+	c.comms = nil
 }

@@ -41,6 +41,16 @@ __global__ void __launch_bounds__(256) norm2_stored_kernel(const uint8_t* rows, 
   }
 }
 
+__global__ void shadow_from_rows_kernel(const uint8_t* rows, uint32_t row_stride, uint32_t dim, size_t n, uint8_t* shadow, uint32_t shadow_stride) {
+  // fp16 shadow of stored fp32 rows (store.cu): element-wise round to nearest, padding zeroed
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float* src = reinterpret_cast<const float*>(rows + w * row_stride);
+  __half* dst = reinterpret_cast<__half*>(shadow + w * (size_t)shadow_stride);
+  for (uint32_t d = lane; d < shadow_stride / 2; d += 32) dst[d] = d < dim ? __float2half_rn(src[d]) : __half(0);
+}
+
 int launch_norm2_stored_f32(const uint8_t* rows, uint32_t row_stride, uint32_t dim, size_t n, float* norm2, cudaStream_t stream) {
   if (n == 0) return COLTT_OK;
   const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
@@ -159,6 +169,7 @@ int Store::import_blob(const void* buf, size_t len) {
     if (elem == ELEM_F32) norm2_stored_kernel<ELEM_F32><<<blocks, 256, 0, stream>>>(d_rows, row_stride, dim, n, d_norm2);
     else if (elem == ELEM_F16) norm2_stored_kernel<ELEM_F16><<<blocks, 256, 0, stream>>>(d_rows, row_stride, dim, n, d_norm2);
     else norm2_stored_kernel<ELEM_F8C><<<blocks, 256, 0, stream>>>(d_rows, row_stride, dim, n, d_norm2);
+    if (d_shadow) shadow_from_rows_kernel<<<blocks, 256, 0, stream>>>(d_rows, row_stride, dim, n, d_shadow, shadow_stride);
     COLTT_CUDA(cudaGetLastError());
     COLTT_CUDA(cudaStreamSynchronize(stream));
   }

@@ -1,0 +1,336 @@
+// comm.cu — the multi-GPU exchange step of a sharded collection, behind the C-ABI.
+//
+// Reference analogue: a vectorspace scans its 16 in-process map shards into shard-local queues and re-Adds them into
+// one queue (edge/none_vectorstore.go:152-178); rows -> shard by ShardVertex (pkg/sharding/shard.go:34-41).  Here a
+// shard is one GPU's coltt_store (or coltt_hnsw sub-graph) and the re-merge is ONE ncclAllGather of the
+// per-shard top-k lists over NVLink followed by the K5 merge kernel (topk_merge.cu) on every rank.  There is no other
+// collective in the path.
+//
+// A coltt_comm is one rank: a device, its NCCL communicator, a stream and persistent send / receive / pinned staging
+// buffers (no allocation per call).  The local search writes its hits and counts straight into the send buffer (one
+// message per rank: coltt_hit[nq][k] then int32 counts[nq]), so nothing is repacked between the search and the
+// all-gather.  Two ways to build the ranks:
+//   * one process per GPU (bench.py under torchrun): coltt_b200_comm_unique_id on rank 0, the 128-byte blob travels
+//     through the host's own channel, coltt_b200_comm_init_rank everywhere;
+//   * one process driving all GPUs (the Go host): coltt_b200_init(device_ids, n) = ncclCommInitAll, and
+//     either n threads (goroutines) calling coltt_b200_sharded_search with their rank's handle, or one call of
+//     coltt_b200_sharded_search_all, which runs the ranks on n library threads.
+// NCCL is loaded at run time (dlopen of libnccl.so.2, preferring the copy already mapped into the process), so
+// libcoltt_b200.so has no link-time dependency on it and single-GPU hosts never touch it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "hnsw.h"
+#include "kernels.cuh"
+#include "store.h"
+
+namespace coltt {
+
+int hnsw_search_keep_device(Hnsw* h, const float* queries, size_t nq, int k, int ef, const Hit** d_hits, const int** d_counts,
+                            cudaStream_t* st);   // hnsw.cu
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // the copy the host process already uses, if any
+    if (!h) { const char* e = getenv("COLTT_NCCL_LIB"); if (e) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL); }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.why = std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "?"); return; }
+    bool all = true;
+    auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) { all = false; api.why = std::string("NCCL symbol missing: ") + name; } return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    api.ok = all;
+  });
+  return api;
+}
+
+#define COLTT_NCCL(expr)                                                                                              \
+  do {                                                                                                                \
+    ncclResult_t _r = (expr);                                                                                         \
+    if (_r != ncclSuccess) return ::coltt::fail(COLTT_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(_r)); \
+  } while (0)
+
+struct Comm {
+  int device = 0, rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;                       // one collective at a time per rank
+  DeviceBuf send, recv, q_in, out, counts;
+  PinnedBuf h_q, h_out;
+  ~Comm() {
+    cudaSetDevice(device);
+    if (comm && nccl().ok) nccl().CommDestroy(comm);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static std::mutex g_all_mu;
+static std::vector<Comm*> g_all;       // ranks created by coltt_b200_init (destroyed by coltt_b200_shutdown)
+
+static size_t msg_bytes(size_t nq, int k) { return (nq * (size_t)k * sizeof(Hit) + nq * 4 + 15) / 16 * 16; }
+
+static int make_comm(int device, int rank, int world, ncclComm_t c, Comm** out) {
+  std::unique_ptr<Comm> cm(new Comm());
+  cm->device = device; cm->rank = rank; cm->world = world; cm->comm = c;
+  COLTT_CUDA(cudaSetDevice(device));
+  COLTT_CUDA(cudaStreamCreateWithFlags(&cm->stream, cudaStreamNonBlocking));
+  *out = cm.release();
+  return COLTT_OK;
+}
+
+// The exchange: this rank's message is already in cm.send; all-gather, then merge the `world` lists per query.
+static int exchange_and_merge(Comm& cm, size_t nq, int k, int nearest, Hit* d_out, int* d_counts, cudaStream_t st) {
+  const size_t mb = msg_bytes(nq, k);
+  if (cm.world > 1) COLTT_NCCL(nccl().AllGather(cm.send.p, cm.recv.p, mb, ncclChar, cm.comm, st));
+  MergeParams mp{};
+  const uint8_t* base = (const uint8_t*)(cm.world > 1 ? cm.recv.p : cm.send.p);
+  mp.lists = (const Hit*)base; mp.counts = (const int*)(base + nq * (size_t)k * sizeof(Hit)); mp.n_lists = cm.world;
+  mp.nq = (uint32_t)nq; mp.k_in = (uint32_t)k; mp.k = (uint32_t)k; mp.nearest = nearest; mp.in_best_first = 0;
+  mp.list_stride_hits = mb / 16; mp.count_stride = mb / 4;
+  mp.out = d_out; mp.out_counts = d_counts;
+  return launch_merge_topk(mp, st);
+}
+
+static int ensure_bufs(Comm& cm, size_t nq, int k) {
+  const size_t mb = msg_bytes(nq, k);
+  int rc;
+  if ((rc = cm.send.ensure(mb))) return rc;
+  if (cm.world > 1 && (rc = cm.recv.ensure(mb * cm.world))) return rc;
+  return COLTT_OK;
+}
+
+// Enqueue-only: local search into the send buffer, all-gather, merge into d_out / d_counts, all on `st`.
+static int sharded_search_enqueue(Comm& cm, Store* shard, const void* d_queries, size_t nq, int k, int select_mode, int math_mode,
+                                  Hit* d_out, int* d_counts, cudaStream_t st) {
+  if (select_mode != COLTT_SELECT_COMPAT && select_mode != COLTT_SELECT_NEAREST) return fail(COLTT_ERR_INVALID, "bad select mode");
+  if (shard->device != cm.device) return fail(COLTT_ERR_INVALID, "shard and communicator live on different devices");
+  int rc = ensure_bufs(cm, nq, k);
+  if (rc) return rc;
+  Hit* s_hits = (Hit*)cm.send.p;
+  int* s_cnt = (int*)((uint8_t*)cm.send.p + nq * (size_t)k * sizeof(Hit));
+  rc = shard->search_dev(d_queries, nq, k, select_mode, math_mode, s_hits, s_cnt, st);   // caller stream: enqueue only
+  if (rc) return rc;
+  return exchange_and_merge(cm, nq, k, select_mode == COLTT_SELECT_NEAREST, d_out, d_counts, st);
+}
+
+static void unpack(const Hit* h, const int* c, size_t nq, int k, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  for (size_t q = 0; q < nq; q++) {
+    out_counts[q] = c[q];
+    for (int i = 0; i < c[q]; i++) {
+      out_ids[q * (size_t)k + i] = h[q * (size_t)k + i].id;
+      out_scores[q * (size_t)k + i] = h[q * (size_t)k + i].score;
+    }
+  }
+}
+
+static int sharded_search_host(Comm& cm, Store* shard, const float* queries, size_t nq, int k, int select_mode, int math_mode,
+                               uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (nq == 0) return COLTT_OK;
+  if (!queries || k <= 0) return fail(COLTT_ERR_INVALID, "bad argument");
+  std::lock_guard<std::mutex> g(cm.mu);
+  COLTT_CUDA(cudaSetDevice(cm.device));
+  const size_t qb = nq * (size_t)shard->dim * 4, hb = nq * (size_t)k * sizeof(Hit);
+  int rc;
+  if ((rc = cm.q_in.ensure(qb)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_q.ensure(qb)) ||
+      (rc = cm.h_out.ensure(hb + nq * 4)))
+    return rc;
+  std::memcpy(cm.h_q.p, queries, qb);
+  COLTT_CUDA(cudaMemcpyAsync(cm.q_in.p, cm.h_q.p, qb, cudaMemcpyHostToDevice, cm.stream));
+  rc = sharded_search_enqueue(cm, shard, cm.q_in.p, nq, k, select_mode, math_mode, (Hit*)cm.out.p, (int*)cm.counts.p, cm.stream);
+  if (rc) return rc;
+  const bool want = out_ids && out_scores && out_counts;     // ranks other than the caller's front rank may pass NULL outputs
+  if (want) {
+    COLTT_CUDA(cudaMemcpyAsync(cm.h_out.p, cm.out.p, hb, cudaMemcpyDeviceToHost, cm.stream));
+    COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.h_out.p + hb, cm.counts.p, nq * 4, cudaMemcpyDeviceToHost, cm.stream));
+  }
+  COLTT_CUDA(cudaStreamSynchronize(cm.stream));
+  if (want) unpack((const Hit*)cm.h_out.p, (const int*)((uint8_t*)cm.h_out.p + hb), nq, k, out_ids, out_scores, out_counts);
+  return COLTT_OK;
+}
+
+// HNSW shards: one independent sub-graph per GPU over its row shard; the same all-gather + merge (nearest first).
+static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq, int k, int ef, uint64_t* out_ids, float* out_scores,
+                             int32_t* out_counts) {
+  if (nq == 0) return COLTT_OK;
+  if (!queries || k <= 0) return fail(COLTT_ERR_INVALID, "bad argument");
+  if (h->device != cm.device) return fail(COLTT_ERR_INVALID, "sub-graph and communicator live on different devices");
+  std::lock_guard<std::mutex> g(cm.mu);
+  COLTT_CUDA(cudaSetDevice(cm.device));
+  const size_t hb = nq * (size_t)k * sizeof(Hit);
+  int rc;
+  if ((rc = ensure_bufs(cm, nq, k)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_out.ensure(hb + nq * 4))) return rc;
+  const Hit* d_hits = nullptr; const int* d_cnt = nullptr; cudaStream_t hst = nullptr;
+  rc = hnsw_search_keep_device(h, queries, nq, k, ef, &d_hits, &d_cnt, &hst);     // returns after the walk finished
+  if (rc) return rc;
+  COLTT_CUDA(cudaMemcpyAsync(cm.send.p, d_hits, hb, cudaMemcpyDeviceToDevice, cm.stream));
+  COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.send.p + hb, d_cnt, nq * 4, cudaMemcpyDeviceToDevice, cm.stream));
+  rc = exchange_and_merge(cm, nq, k, 1, (Hit*)cm.out.p, (int*)cm.counts.p, cm.stream);
+  if (rc) return rc;
+  const bool want = out_ids && out_scores && out_counts;
+  if (want) {
+    COLTT_CUDA(cudaMemcpyAsync(cm.h_out.p, cm.out.p, hb, cudaMemcpyDeviceToHost, cm.stream));
+    COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.h_out.p + hb, cm.counts.p, nq * 4, cudaMemcpyDeviceToHost, cm.stream));
+  }
+  COLTT_CUDA(cudaStreamSynchronize(cm.stream));
+  if (want) unpack((const Hit*)cm.h_out.p, (const int*)((uint8_t*)cm.h_out.p + hb), nq, k, out_ids, out_scores, out_counts);
+  return COLTT_OK;
+}
+
+}  // namespace coltt
+
+using coltt::Comm;
+using coltt::fail;
+using coltt::nccl;
+
+extern "C" {
+
+COLTT_API int coltt_b200_comm_unique_id(void* out, size_t len) {
+  if (!out || len < sizeof(ncclUniqueId)) return fail(COLTT_ERR_INVALID, "unique id buffer must hold 128 bytes");
+  if (!nccl().ok) return fail(COLTT_ERR_UNSUPPORTED, nccl().why);
+  ncclUniqueId id;
+  COLTT_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(out, &id, sizeof(id));
+  return COLTT_OK;
+}
+
+COLTT_API int coltt_b200_comm_init_rank(const void* unique_id, int rank, int world, int device, coltt_comm** out) {
+  if (!unique_id || !out || world < 1 || rank < 0 || rank >= world) return fail(COLTT_ERR_INVALID, "bad communicator arguments");
+  int rc = coltt::require_device(device);
+  if (rc) return rc;
+  if (!nccl().ok) return fail(COLTT_ERR_UNSUPPORTED, nccl().why);
+  COLTT_CUDA(cudaSetDevice(device));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t c = nullptr;
+  COLTT_NCCL(nccl().CommInitRank(&c, world, id, rank));
+  Comm* cm = nullptr;
+  rc = coltt::make_comm(device, rank, world, c, &cm);
+  if (rc) { nccl().CommDestroy(c); return rc; }
+  *out = reinterpret_cast<coltt_comm*>(cm);
+  return COLTT_OK;
+}
+
+COLTT_API int coltt_b200_init(const int* device_ids, int n_dev, coltt_comm** out_comms) {
+  if (!device_ids || !out_comms || n_dev < 1 || n_dev > 64) return fail(COLTT_ERR_INVALID, "bad device list");
+  for (int i = 0; i < n_dev; i++) { int rc = coltt::require_device(device_ids[i]); if (rc) return rc; }
+  std::vector<ncclComm_t> cs(n_dev, nullptr);
+  if (n_dev > 1) {
+    if (!nccl().ok) return fail(COLTT_ERR_UNSUPPORTED, nccl().why);
+    COLTT_NCCL(nccl().CommInitAll(cs.data(), n_dev, device_ids));
+  }
+  std::lock_guard<std::mutex> g(coltt::g_all_mu);
+  for (int i = 0; i < n_dev; i++) {
+    Comm* cm = nullptr;
+    int rc = coltt::make_comm(device_ids[i], i, n_dev, cs[i], &cm);
+    if (rc) return rc;
+    coltt::g_all.push_back(cm);
+    out_comms[i] = reinterpret_cast<coltt_comm*>(cm);
+  }
+  return COLTT_OK;
+}
+
+COLTT_API void coltt_b200_comm_destroy(coltt_comm* c) {
+  Comm* cm = reinterpret_cast<Comm*>(c);
+  if (!cm) return;
+  {
+    std::lock_guard<std::mutex> g(coltt::g_all_mu);
+    for (auto it = coltt::g_all.begin(); it != coltt::g_all.end(); ++it)
+      if (*it == cm) { coltt::g_all.erase(it); break; }
+  }
+  delete cm;
+}
+
+COLTT_API void coltt_b200_shutdown(void) {
+  std::vector<Comm*> all;
+  {
+    std::lock_guard<std::mutex> g(coltt::g_all_mu);
+    all.swap(coltt::g_all);
+  }
+  for (Comm* cm : all) delete cm;
+}
+
+COLTT_API int coltt_b200_comm_info(coltt_comm* c, int* rank, int* world, int* device) {
+  Comm* cm = reinterpret_cast<Comm*>(c);
+  if (!cm) return fail(COLTT_ERR_INVALID, "null communicator");
+  if (rank) *rank = cm->rank;
+  if (world) *world = cm->world;
+  if (device) *device = cm->device;
+  return COLTT_OK;
+}
+
+COLTT_API int coltt_b200_sharded_search(coltt_comm* c, coltt_store* shard, const float* queries, size_t nq, int k, int select_mode,
+                                        int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (!c || !shard) return fail(COLTT_ERR_INVALID, "null handle");
+  return coltt::sharded_search_host(*reinterpret_cast<Comm*>(c), reinterpret_cast<coltt::Store*>(shard), queries, nq, k, select_mode, math_mode,
+                                    out_ids, out_scores, out_counts);
+}
+
+COLTT_API int coltt_b200_sharded_search_dev(coltt_comm* c, coltt_store* shard, const void* d_queries, size_t nq, int k, int select_mode,
+                                            int math_mode, void* d_out, void* d_counts, void* stream) {
+  if (!c || !shard || !d_queries || !d_out || !d_counts) return fail(COLTT_ERR_INVALID, "null argument");
+  if (nq == 0) return COLTT_OK;
+  if (k <= 0) return fail(COLTT_ERR_INVALID, "top-k must be positive");
+  Comm& cm = *reinterpret_cast<Comm*>(c);
+  std::lock_guard<std::mutex> g(cm.mu);
+  COLTT_CUDA(cudaSetDevice(cm.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : cm.stream;
+  int rc = coltt::sharded_search_enqueue(cm, reinterpret_cast<coltt::Store*>(shard), d_queries, nq, k, select_mode, math_mode, (coltt::Hit*)d_out,
+                                         (int*)d_counts, st);
+  if (rc) return rc;
+  if (!stream) COLTT_CUDA(cudaStreamSynchronize(st));
+  return COLTT_OK;
+}
+
+COLTT_API int coltt_b200_sharded_search_all(coltt_comm* const* comms, coltt_store* const* shards, int n, const float* queries, size_t nq, int k,
+                                            int select_mode, int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (!comms || !shards || n < 1) return fail(COLTT_ERR_INVALID, "bad argument");
+  std::vector<int> rcs(n, COLTT_OK);
+  std::vector<std::string> msgs(n);
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; i++)
+    th.emplace_back([&, i] {
+      rcs[i] = coltt_b200_sharded_search(comms[i], shards[i], queries, nq, k, select_mode, math_mode, nullptr, nullptr, nullptr);
+      if (rcs[i]) msgs[i] = coltt::last_error_cstr();
+    });
+  rcs[0] = coltt_b200_sharded_search(comms[0], shards[0], queries, nq, k, select_mode, math_mode, out_ids, out_scores, out_counts);
+  for (auto& t : th) t.join();
+  for (int i = 1; i < n; i++)
+    if (rcs[i]) return fail(rcs[i], "rank " + std::to_string(i) + ": " + msgs[i]);
+  return rcs[0];
+}
+
+COLTT_API int coltt_b200_sharded_hnsw_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef, uint64_t* out_ids,
+                                             float* out_scores, int32_t* out_counts) {
+  if (!c || !sub) return fail(COLTT_ERR_INVALID, "null handle");
+  return coltt::sharded_hnsw_host(*reinterpret_cast<Comm*>(c), reinterpret_cast<coltt::Hnsw*>(sub), queries, nq, k, ef, out_ids, out_scores,
+                                  out_counts);
+}
+
+}  // extern "C"

@@ -154,6 +154,35 @@ __device__ __forceinline__ float pick32(const float (&k)[32], uint32_t c) {
   return (c & 1u) ? e[1] : e[0];
 }
 
+// Cross-column bound G of filter_epilogue (see its header comment): reads the n_cols published values of query q.  The loads of
+// one pass (one per class) are issued together BEFORE any of them is consumed: each is an L2 round trip, and a sweep that
+// serialises them (load, max, load, max ...) costs ~100 K cycles — measured: it doubled the kernel time.  Out of line: the
+// epilogue calls it from three places and its body is cold code next to the per-tile hot loop.
+template <int KP>
+__device__ __noinline__ float cross_column_bound(const float* pub, uint32_t nq, uint32_t q, uint32_t col, uint32_t n_cols, uint32_t groups) {
+  const float NEG_INF = __int_as_float(0xff800000);
+  float gmax[KP];
+#pragma unroll
+  for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
+#pragma unroll 2
+  for (uint32_t c0 = 0; c0 < n_cols; c0 += groups) {
+    float pv[KP];
+#pragma unroll
+    for (int i = 0; i < KP; i++) {
+      const uint32_t c = c0 + i;
+      const bool ok = (uint32_t)i < groups && c < n_cols;
+      pv[i] = __ldcg(pub + (size_t)(ok ? c : col) * nq + q);   // own column when masked: a valid address, value unused
+      if (!ok) pv[i] = NEG_INF;
+    }
+#pragma unroll
+    for (int i = 0; i < KP; i++) gmax[i] = fmaxf(gmax[i], pv[i]);   // fmaxf ignores the NaN "nothing published yet" marker
+  }
+  float G = gmax[0];
+#pragma unroll
+  for (int i = 1; i < KP; i++) if ((uint32_t)i < groups) G = fminf(G, gmax[i]);
+  return G;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Epilogue of the filter GEMM (warps 2-9, thread = query).  For every 256-row tile: tcgen05.ld the
 // 128x256 fp32 accumulator 32 columns at a time, one FFMA turns each score into a "larger is better" key
@@ -226,25 +255,7 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     coef_a[idx] = a;
     coef_b[idx] = b;
   };
-  // cross-column bound (see the header comment); reads n_cols published values of this query
-  auto sweep = [&]() {
-    float gmax[KP];
-#pragma unroll
-    for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
-    for (uint32_t c0 = 0; c0 < n_cols; c0 += groups) {
-#pragma unroll
-      for (int i = 0; i < KP; i++) {
-        if ((uint32_t)i < groups) {
-          const float pv = c0 + i < n_cols ? __ldcg(p.pub + (size_t)(c0 + i) * p.nq + q) : NEG_INF;
-          gmax[i] = fmaxf(gmax[i], pv);   // fmaxf ignores the NaN "nothing published yet" marker
-        }
-      }
-    }
-    float G = gmax[0];
-#pragma unroll
-    for (int i = 1; i < KP; i++) if ((uint32_t)i < groups) G = fminf(G, gmax[i]);
-    thr = fmaxf(thr, G);
-  };
+  auto sweep = [&]() { thr = fmaxf(thr, cross_column_bound<KP>(p.pub, p.nq, q, col, n_cols, groups)); };
   // ||row||^2 (and the E4M3 row scale) of the next tile are fetched while the current one is processed (one row per epilogue thread)
   float n2_a = 0.0f, sc_a = 1.0f;
   {

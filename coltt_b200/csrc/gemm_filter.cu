@@ -90,7 +90,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       // the query tile: A operand, loaded once (rows beyond nq are zero-filled by TMA)
       mbar_arrive_expect_tx(smem_u32(a_bar), KB * ABLK_BYTES);
       for (uint32_t kb = 0; kb < KB; kb++)
-        tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)(kb * kBK), (int)q_tile0, smem_u32(a_bar));
+        tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)((kb * kBK) >> p.tma_shift), (int)q_tile0, smem_u32(a_bar));
     }
     __syncwarp();
     uint32_t s = 0, ph = 0;
@@ -102,7 +102,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const uint32_t pf_mask = p.pf_inner / kBKB - 1;          // pf_inner / kBKB is a power of two
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
     if (do_pf && blockIdx.x < n_tiles && elect_one())
-      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), (int)(blockIdx.x * kBN));
+      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)((st * kBKB) >> p.tma_shift), (int)(blockIdx.x * kBN));
     __syncwarp();
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int row = (int)(t * kBN), row_pf = row + (int)(gridDim.x * kBN);
@@ -111,8 +111,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         mbar_wait(empty0 + s * 8, ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(full0 + s * 8, STAGE_BYTES);
-          tma_load_2d(stage0 + s * STAGE_BYTES, &tmap, (int)(st * kBKB), row, full0 + s * 8);
-          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * kBKB), row_pf);
+          tma_load_2d(stage0 + s * STAGE_BYTES, &tmap, (int)((st * kBKB) >> p.tma_shift), row, full0 + s * 8);
+          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)((st * kBKB) >> p.tma_shift), row_pf);
         }
         __syncwarp();
         if (++s == NS) { s = 0; ph ^= 1; }
@@ -254,16 +254,20 @@ int plan_gemm_filter(uint32_t row_bytes, bool fp8, uint32_t nq, uint32_t k, int 
   return COLTT_OK;
 }
 
-// All maps describe BYTES (dtype UINT8): the swizzle patterns and box shapes are byte geometry, identical for fp16 and E4M3.
-static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner,
-                      uint32_t box_rows, CUtensorMapSwizzle swz) {
+// Tensor maps describe the operands as rows of `ew`-byte words (ew = 1, 2 or 4): swizzle patterns and box shapes are byte
+// geometry, identical for fp16 and E4M3, and every extent here is a multiple of 4 bytes (stored rows are zero padded to 16
+// bytes, query rows to 128), so the word width is free to choose — it only changes how many elements the TMA unit counts
+// per box.  Kernel-side coordinates are in BYTES and are divided by ew on the host side of the map (p.tma_shift).
+static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner_bytes,
+                      uint32_t box_rows, CUtensorMapSwizzle swz, uint32_t ew) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(COLTT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t gdim[2] = {inner_bytes, rows};
+  const cuuint64_t gdim[2] = {inner_bytes / ew, rows};
   const cuuint64_t gstride[1] = {row_stride_bytes};
-  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t box[2] = {box_inner_bytes / ew, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType dt = ew == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (ew == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(COLTT_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return COLTT_OK;
@@ -287,32 +291,35 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   GemmPlan plan = plan_in;
   const uint32_t cols = gemm_filter_cols(plan, p_in.n_rows) / kEpiSets;   // CTAs (or pairs) along x
   if (cols * kEpiSets < plan.groups) return fail(COLTT_ERR_UNSUPPORTED, "FAST: fewer columns than bound classes");
-  const uint32_t row_bytes = p_in.dim * (plan.fp8 ? 1u : 2u);
+  const uint32_t row_bytes = (p_in.dim * (plan.fp8 ? 1u : 2u) + 3) / 4 * 4;   // stored rows are zero padded to 16 bytes
+  static const uint32_t env_ew = [] { const char* e = getenv("COLTT_TMA_WORD"); const int v = e ? atoi(e) : 4; return v == 1 ? 1u : (v == 2 ? 2u : 4u); }();
+  const uint32_t ew = env_ew, tma_shift = ew == 4 ? 2u : (ew == 2 ? 1u : 0u);
   const uint32_t pf_inner = 256;                                           // bytes per L2-prefetch request row
   const uint32_t box_rows = plan.pair ? kBN / 2 : kBN;
   int rc;
   if (mc.rows != d_rows || mc.n_rows != p_in.n_rows || mc.row_bytes != row_bytes || mc.row_stride != row_stride || mc.box_rows != box_rows ||
-      mc.pf_inner != pf_inner || mc.sb != plan.sb) {
+      mc.pf_inner != pf_inner || mc.sb != plan.sb || mc.ew != ew) {
     mc.rows = nullptr;
     // shard tile stages: 256 (or 128 per CTA of a pair) rows x 64 B, 64B swizzle
-    rc = encode_map(&tm, d_rows, row_bytes, p_in.n_rows, row_stride, plan.sb, box_rows, plan.sb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = encode_map(&tm, d_rows, row_bytes, p_in.n_rows, row_stride, plan.sb, box_rows, plan.sb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, ew);
     if (rc) return rc;
     // L2 prefetch view of the shard: whole 128-byte lines, 128 rows per request
-    rc = encode_map(&tmpf, d_rows, row_bytes, p_in.n_rows, row_stride, pf_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = encode_map(&tmpf, d_rows, row_bytes, p_in.n_rows, row_stride, pf_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_NONE, ew);
     if (rc) return rc;
-    mc.rows = d_rows; mc.n_rows = p_in.n_rows; mc.row_bytes = row_bytes; mc.row_stride = row_stride; mc.box_rows = box_rows; mc.pf_inner = pf_inner; mc.sb = plan.sb;
+    mc.rows = d_rows; mc.n_rows = p_in.n_rows; mc.row_bytes = row_bytes; mc.row_stride = row_stride; mc.box_rows = box_rows; mc.pf_inner = pf_inner; mc.sb = plan.sb; mc.ew = ew;
   }
-  if (mc.q != p_in.q_lowered || mc.nq != p_in.nq || mc.q_stride != p_in.q_stride) {
+  if (mc.q != p_in.q_lowered || mc.nq != p_in.nq || mc.q_stride != p_in.q_stride || mc.q_ew != ew) {
     mc.q = nullptr;
     // queries: [nq][q_stride bytes], zero padded to kblocks*128 bytes; box = 128 B x 128 rows, 128B swizzle
-    rc = encode_map(&tmq, p_in.q_lowered, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_map(&tmq, p_in.q_lowered, p_in.q_stride, p_in.nq, (uint64_t)p_in.q_stride, kBK, 128, CU_TENSOR_MAP_SWIZZLE_128B, ew);
     if (rc) return rc;
-    mc.q = p_in.q_lowered; mc.nq = p_in.nq; mc.q_stride = p_in.q_stride;
+    mc.q = p_in.q_lowered; mc.nq = p_in.nq; mc.q_stride = p_in.q_stride; mc.q_ew = ew;
   }
   GemmParams p = p_in;
   p.rows = static_cast<const uint8_t*>(d_rows);
   p.row_stride = row_stride;
   p.pf_inner = pf_inner;
+  p.tma_shift = tma_shift;
   p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.cand_out_cap = plan.cand_out_cap; p.n_stages = plan.n_stages;
   p.pub_kth = plan.pub_kth; p.groups = plan.groups;
   if (plan.pair) {

@@ -66,7 +66,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
   if (warp == 0 && lane == 0) {
     mbar_arrive_expect_tx(smem_u32(a_bar), KB * ABLK_BYTES);
     for (uint32_t kb = 0; kb < KB; kb++)
-      tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)(kb * kBK), (int)q_tile0, smem_u32(a_bar));
+      tma_load_2d(smem_u32(a_smem + (size_t)kb * ABLK_BYTES), &tmap_q, (int)((kb * kBK) >> p.tma_shift), (int)q_tile0, smem_u32(a_bar));
     mbar_wait(smem_u32(a_bar), 0);
   }
   tc_fence_before();
@@ -91,7 +91,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     const uint32_t pf_mask = p.pf_inner / SB - 1;            // pf_inner / SB is a power of two
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), stage0 = smem_u32(b_stages);
     if (do_pf && pair < n_tiles && elect_one())
-      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)(st * SB), (int)(pair * kBN) + row_off);
+      for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)((st * SB) >> p.tma_shift), (int)(pair * kBN) + row_off);
     __syncwarp();
     for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
       const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
@@ -101,8 +101,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (elect_one()) {
           // the leader's barrier collects both halves: it expects 2 x STAGE_BYTES, each CTA's load signals it
           if (rank == 0) mbar_arrive_expect_tx(full0 + s * 8, 2 * STAGE_BYTES);
-          tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)(st * SB), row, full0 + s * 8);
-          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)(st * SB), row_pf);
+          tma_load_2d_pair(stage0 + s * STAGE_BYTES, &tmap, (int)((st * SB) >> p.tma_shift), row, full0 + s * 8);
+          if (pf && (st & pf_mask) == 0) tma_prefetch_2d(&tmap_pf, (int)((st * SB) >> p.tma_shift), row_pf);
         }
         __syncwarp();
         if (++s == NS) { s = 0; ph ^= 1; }

@@ -1032,6 +1032,13 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
     if (again.empty()) return fail(COLTT_ERR_UNSUPPORTED, "HNSW re-run bookkeeping lost its queries");
     redo.swap(again);
   }
+  // HnswSearchHeuristic (hnsw.go:262-266,399-447) with the defaults a loaded index gets (extendCandidates = false,
+  // keepPruned = true; the Commit header does not carry them, hnsw_config.go:179-245) keeps the k smallest of the ef
+  // results exactly like selectNeighbors — except among EQUAL priorities, where Go's two heap walks may keep different
+  // vertices.  The walk above replays selectNeighbors' heaps; rather than answer a heuristic-configured index with
+  // simple-mode tie-breaking, fail loudly when a query of this batch actually met equal priorities.
+  if (h->search_algo == 1 && ties > 0)
+    return fail(COLTT_ERR_UNSUPPORTED, "HnswSearchHeuristic: this batch met equal priorities, whose order under the heuristic selector is not reproduced");
   stats[0] = evals;
   stats[1] = exps;
   h->last_ties = ties;
@@ -1043,6 +1050,26 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
       out_ids[q * (size_t)k + i] = hits[q * (size_t)k + i].id;
       out_scores[q * (size_t)k + i] = hits[q * (size_t)k + i].score;
     }
+  return COLTT_OK;
+}
+
+// Hnsw.Search whose per-query hits also stay in device memory (the sharded search's send side, comm.cu).  The pointers
+// are the handle's own scratch: valid until the next search on this handle.
+int hnsw_search_keep_device(Hnsw* h, const float* queries, size_t nq, int k, int ef, const Hit** d_hits, const int** d_counts, cudaStream_t* st) {
+  std::vector<uint64_t> ids(nq * (size_t)k);
+  std::vector<float> sc(nq * (size_t)k);
+  std::vector<int32_t> cnt(nq);
+  int rc = hnsw_search(h, queries, nq, k, ef, ids.data(), sc.data(), cnt.data());
+  if (rc) return rc;
+  if (h->n == 0) {   // empty sub-graph: hnsw_search answered on the host, the device scratch may not exist yet
+    std::lock_guard<std::mutex> lk(h->mu);
+    COLTT_CUDA(cudaSetDevice(h->device));
+    if ((rc = h->out.ensure(nq * (size_t)k * sizeof(Hit))) || (rc = h->counts.ensure(nq * 4))) return rc;
+    COLTT_CUDA(cudaMemset(h->counts.p, 0, nq * 4));
+  }
+  *d_hits = (const Hit*)h->out.p;
+  *d_counts = (const int*)h->counts.p;
+  *st = h->stream;
   return COLTT_OK;
 }
 
@@ -1060,6 +1087,11 @@ COLTT_API int coltt_b200_hnsw_load(const void* commit_blob, size_t len, int devi
   return rc;
 }
 COLTT_API void coltt_b200_hnsw_destroy(coltt_hnsw* h) { delete reinterpret_cast<Hnsw*>(h); }
+COLTT_API int coltt_b200_hnsw_dim(coltt_hnsw* h, uint32_t* dim) {
+  if (!h || !dim) return fail(COLTT_ERR_INVALID, "null argument");
+  *dim = reinterpret_cast<Hnsw*>(h)->dim;
+  return COLTT_OK;
+}
 COLTT_API int coltt_b200_hnsw_len(coltt_hnsw* h, uint64_t* n) {
   if (!h || !n) return fail(COLTT_ERR_INVALID, "null argument");
   *n = reinterpret_cast<Hnsw*>(h)->n;

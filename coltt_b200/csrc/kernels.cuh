@@ -27,6 +27,8 @@ struct PrepParams {
   uint32_t deq_stride;
   __half* f16_out;        // nullable: fp16 copy [n][f16_stride], zero padded
   uint32_t f16_stride;
+  uint8_t* shadow_out;    // nullable (ELEM_F32 rows): fp16 copy of the stored row [slot][shadow_stride bytes], zero padded —
+  uint32_t shadow_stride; //   the operand of the tensor-core filter for fp32 stores (store.cu)
   float* scale_out;       // ELEM_F8E: per-vector scale, indexed like norm2_out
   uint8_t* code_out;      // nullable (ELEM_F8E queries): the lowered codes [n][code_stride], zero padded
   uint32_t code_stride;
@@ -103,6 +105,7 @@ struct GemmParams {
   unsigned long long* dbg_prof;  // nullable (profiling builds, -DCOLTT_K2_PROF=1): [grid][8] cycle counters per role
   unsigned long long* dbg_prof2; // second bank of counters (epilogue detail)
   uint32_t pf_inner;         // L2 prefetch box width in bytes (multiple of 64)
+  uint32_t tma_shift;        // log2 of the tensor maps' word width in bytes: TMA coordinates = byte offsets >> tma_shift
   uint32_t dbg_flags;        // profiling builds only. bit0: epilogue only drains TMEM; bit1: no L2 prefetch
 };
 struct GemmPlan {
@@ -116,7 +119,7 @@ struct GemmMapCache {
   alignas(64) unsigned char maps[3][128];   // CUtensorMap x3 (opaque here: this header does not pull in <cuda.h>)
   const void* rows = nullptr;
   const void* q = nullptr;
-  uint32_t n_rows = 0, row_bytes = 0, row_stride = 0, box_rows = 0, pf_inner = 0, nq = 0, q_stride = 0, sb = 0;
+  uint32_t n_rows = 0, row_bytes = 0, row_stride = 0, box_rows = 0, pf_inner = 0, nq = 0, q_stride = 0, sb = 0, ew = 0, q_ew = 0;
 };
 // row_bytes = dim * element size; fp8 = E4M3 operands (kind::f8f6f4) instead of fp16 (kind::f16)
 int plan_gemm_filter(uint32_t row_bytes, bool fp8, uint32_t nq, uint32_t k, int n_sms, GemmPlan* plan);
@@ -127,6 +130,7 @@ uint32_t gemm_filter_cols(const GemmPlan& plan, uint32_t n_rows);
 struct RerankParams {
   uint32_t nq, k, dim, q_stride, row_stride, grid_x, cand_cap;
   uint32_t max_rows;         // rows re-scored exactly per query: 64 (top-10/24) or 256 (top-100)
+  uint32_t chunk_rows;       // rows staged in shared memory at a time (filled by launch_rerank)
   float eps_rel;             // certificate margin: |filter score - exact score| <= eps_rel * ||q|| ||row|| (fast_eps_rel(dim))
   int metric, nearest, elem;
   const float* queries;      // [nq][q_stride] dequantized fp32 (exact path operand)
@@ -153,8 +157,17 @@ int launch_rerank(const RerankParams& p, cudaStream_t stream);
 // Certificate margin of COLTT_MATH_FAST, relative to ||q|| ||row|| (DESIGN.md §5 has the derivation): the tensor core adds
 // `dim` exact products into an fp32 accumulator truncating each addend to the accumulator's ulp (<= dim * 2^-23), the exact
 // kernel rounds (dim/8 + 3) times per AVX lane (<= (dim/8+3) * 2^-24); 25 % slack and 2^-20 for the epilogue roundings.
+// fp32 stores are filtered through an fp16 shadow of the (unit-norm) rows and query: every element is off by at most 2^-11
+// relative (round to nearest; 2^-25 absolute below 2^-14), so the dot product moves by <= (2^-10 + 2^-22) ||q|| ||row|| plus
+// 2^-24 sqrt(dim); added to the accumulation-order margin above.
+inline float fast_eps_rel_f32_shadow(uint32_t dim);
 inline float fast_eps_rel(uint32_t dim) {
   return 1.25f * ((float)dim * 1.1920929e-7f + ((float)dim / 8.0f + 3.0f) * 5.9604645e-8f) + 9.5367432e-7f;
+}
+inline float fast_eps_rel_f32_shadow(uint32_t dim) {
+  float r = 1.0f;
+  while (r * r < (float)dim) r += 1.0f;      // ceil(sqrt(dim)) without <cmath> in this header
+  return fast_eps_rel(dim) + 9.7656250e-4f + 2.3841858e-7f + 5.9604645e-8f * r;
 }
 
 // ---- topk_merge.cu (K5) -----------------------------------------------------------------

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
         v = mul_rn(e_scale, e4m3_decode(c));
       } else if (ELEM == ELEM_F32) {
         if (row) reinterpret_cast<float*>(row)[d] = v;
+        if (p.shadow_out) reinterpret_cast<__half*>(p.shadow_out + slot * (size_t)p.shadow_stride)[d] = __float2half_rn(v);
       } else if (ELEM == ELEM_F16) {
         // compresshelper.Fromfloat32 (float16.go:124,274-321): IEEE RNE incl. subnormals and
         // overflow->inf == __float2half_rn for every non-NaN input (tests/test_gpu_codec.py).
@@ -109,6 +110,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
     }
     if (code_row)
       for (uint32_t b = dim + lane; b < p.code_stride; b += 32) code_row[b] = 0;   // +0.0 in E4M3
+    if (ELEM == ELEM_F32 && p.shadow_out)
+      for (uint32_t b = dim * 2 + lane; b < p.shadow_stride; b += 32) p.shadow_out[slot * (size_t)p.shadow_stride + b] = 0;
     __syncwarp();
 
     // ||x||^2 exactly as cosine_similarity_dot_norm accumulates it for one operand

@@ -17,14 +17,14 @@
 namespace coltt {
 
 static constexpr int kRerankThreads = 256;
-static constexpr uint32_t kRerankChunk = 64;       // rows staged in shared memory at a time
+static constexpr uint32_t kRerankChunkMax = 64;    // rows staged in shared memory at a time (fewer when rows are wide)
 
 // shared-memory layout (byte offsets from the dynamic base; offsets, not rounded pointers, so that every access
 // stays in the shared address space and compiles to LDS/STS).  MC = survivors gathered per query (keys only),
 // MR = rows re-scored exactly per query (>= 2 K').
 struct RerankSmem {
   uint32_t q, row, key, sel, score, n2, sc, id, rows, total;
-  __host__ __device__ RerankSmem(uint32_t q_stride, uint32_t row_stride, uint32_t MC, uint32_t MR) {
+  __host__ __device__ RerankSmem(uint32_t q_stride, uint32_t row_stride, uint32_t MC, uint32_t MR, uint32_t chunk) {
     q = 0;                                   // float  [q_stride]        (bulk-copied: 16-byte multiple)
     row = q + q_stride * 4;                  // u32    [MC]
     key = row + MC * 4;                      // float  [MC]
@@ -33,8 +33,8 @@ struct RerankSmem {
     n2 = score + MR * 4;                     // float  [MR]     ||row||^2 of the selected rows
     sc = n2 + MR * 4;                        // float  [MR]     E4M3 row scales
     id = sc + MR * 4;                        // u64    [MR]
-    rows = (id + MR * 8 + 127u) & ~127u;     // bytes [kRerankChunk][row_stride + 16]
-    total = rows + kRerankChunk * (row_stride + 16);
+    rows = (id + MR * 8 + 127u) & ~127u;     // bytes [chunk][row_stride + 16]
+    total = rows + chunk * (row_stride + 16);
   }
 };
 
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   __shared__ uint32_t n_s, ovf_s, last_s;
   __shared__ float kth_s, bound_s;
   __shared__ __align__(8) uint64_t bar_s[2];   // [0] query copy, [1] row copies (one phase per chunk)
-  const RerankSmem L(p.q_stride, p.row_stride, MC, MR);
+  const RerankSmem L(p.q_stride, p.row_stride, MC, MR, p.chunk_rows);
+  const uint32_t kRerankChunk = p.chunk_rows;
   float* q_s = reinterpret_cast<float*>(smem + L.q);
   uint32_t* row_s = reinterpret_cast<uint32_t*>(smem + L.row);
   float* key_s = reinterpret_cast<float*>(smem + L.key);
@@ -252,10 +253,14 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   }
 }
 
-int launch_rerank(const RerankParams& p, cudaStream_t stream) {
-  if (p.nq == 0) return COLTT_OK;
-  if (p.max_rows != 64 && p.max_rows != 256) return fail(COLTT_ERR_INVALID, "rerank: max_rows must be 64 or 256");
-  const size_t smem = RerankSmem(p.q_stride, p.row_stride, p.max_rows == 64 ? 1024u : 4096u, p.max_rows).total;
+int launch_rerank(const RerankParams& p_in, cudaStream_t stream) {
+  if (p_in.nq == 0) return COLTT_OK;
+  if (p_in.max_rows != 64 && p_in.max_rows != 256) return fail(COLTT_ERR_INVALID, "rerank: max_rows must be 64 or 256");
+  RerankParams p = p_in;
+  const uint32_t MCv = p.max_rows == 64 ? 1024u : 4096u;
+  p.chunk_rows = kRerankChunkMax;
+  while (p.chunk_rows > 16 && RerankSmem(p.q_stride, p.row_stride, MCv, p.max_rows, p.chunk_rows).total > 200 * 1024) p.chunk_rows -= 16;
+  const size_t smem = RerankSmem(p.q_stride, p.row_stride, MCv, p.max_rows, p.chunk_rows).total;
   if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "rerank: rows too wide for shared memory");
   const bool cosine = p.metric == COLTT_COSINE;
 #define COLTT_RR(E, M, R)                                                                                 \

@@ -151,6 +151,7 @@ Store::~Store() {
   if (d_rows) cudaFree(d_rows);
   if (d_norm2) cudaFree(d_norm2);
   if (d_scale) cudaFree(d_scale);
+  if (d_shadow) cudaFree(d_shadow);
   if (d_ids) cudaFree(d_ids);
   if (d_stat) cudaFree(d_stat);
   if (stream) cudaStreamDestroy(stream);
@@ -178,6 +179,11 @@ int Store::create(const coltt_store_cfg* cfg, Store** out) {
   s->elem = elem;
   s->dim = cfg->dim;
   s->row_stride = (cfg->dim * elem_size(elem) + 15) / 16 * 16;
+  // fp32 cosine stores keep an fp16 shadow of their (unit-norm) rows, +50 % memory: COLTT_MATH_FAST filters through it on
+  // the tensor cores and re-ranks on the fp32 rows, so results stay bit-identical to EXACT.  L2 rows can leave the fp16
+  // range and rows wider than 1536 shadow bytes have no resident-query kernel: those stores are served exactly.
+  static const bool shadow_on = [] { const char* e = getenv("COLTT_F32_SHADOW"); return !e || atoi(e) != 0; }();
+  if (elem == ELEM_F32 && cfg->metric == COLTT_COSINE && shadow_on && cfg->dim * 2 <= 1536) s->shadow_stride = (cfg->dim * 2 + 15) / 16 * 16;
   cudaDeviceProp pr;
   COLTT_CUDA(cudaGetDeviceProperties(&pr, cfg->device));
   s->n_sms = pr.multiProcessorCount;
@@ -196,20 +202,22 @@ int Store::reserve(size_t rows) {
   if (rows <= capacity) return COLTT_OK;
   if (rows > 0xfffffff0ull) return fail(COLTT_ERR_UNSUPPORTED, "more than 2^32 rows per GPU shard");
   size_t nc = std::max<size_t>(rows, std::max<size_t>(capacity * 2, 1024));
-  uint8_t* nr = nullptr;
+  uint8_t *nr = nullptr, *nsh = nullptr;
   float *nn = nullptr, *nsc = nullptr;
   uint64_t* ni = nullptr;
   const bool scaled = elem == ELEM_F8E;
   auto try_alloc = [&](size_t c) {
-    nr = nullptr; nn = nullptr; ni = nullptr; nsc = nullptr;
+    nr = nullptr; nn = nullptr; ni = nullptr; nsc = nullptr; nsh = nullptr;
     if (cudaMalloc(&nr, c * row_stride) == cudaSuccess && cudaMalloc(&nn, c * 4) == cudaSuccess &&
-        cudaMalloc(&ni, c * 8) == cudaSuccess && (!scaled || cudaMalloc(&nsc, c * 4) == cudaSuccess))
+        cudaMalloc(&ni, c * 8) == cudaSuccess && (!scaled || cudaMalloc(&nsc, c * 4) == cudaSuccess) &&
+        (!shadow_stride || cudaMalloc(&nsh, c * (size_t)shadow_stride) == cudaSuccess))
       return true;
     cudaGetLastError();
     if (nr) cudaFree(nr);
     if (nn) cudaFree(nn);
     if (ni) cudaFree(ni);
     if (nsc) cudaFree(nsc);
+    if (nsh) cudaFree(nsh);
     return false;
   };
   if (!try_alloc(nc)) {
@@ -221,15 +229,18 @@ int Store::reserve(size_t rows) {
     COLTT_CUDA(cudaMemcpyAsync(nn, d_norm2, n_rows * 4, cudaMemcpyDeviceToDevice, stream));
     COLTT_CUDA(cudaMemcpyAsync(ni, d_ids, n_rows * 8, cudaMemcpyDeviceToDevice, stream));
     if (scaled) COLTT_CUDA(cudaMemcpyAsync(nsc, d_scale, n_rows * 4, cudaMemcpyDeviceToDevice, stream));
+    if (shadow_stride) COLTT_CUDA(cudaMemcpyAsync(nsh, d_shadow, n_rows * (size_t)shadow_stride, cudaMemcpyDeviceToDevice, stream));
     COLTT_CUDA(cudaStreamSynchronize(stream));
   }
   if (d_rows) cudaFree(d_rows);
   if (d_norm2) cudaFree(d_norm2);
   if (d_scale) cudaFree(d_scale);
+  if (d_shadow) cudaFree(d_shadow);
   if (d_ids) cudaFree(d_ids);
   d_rows = nr;
   d_norm2 = nn;
   d_scale = nsc;
+  d_shadow = nsh;
   d_ids = ni;
   capacity = nc;
   return COLTT_OK;
@@ -276,7 +287,7 @@ int Store::upsert(const uint64_t* ids, const float* vecs, size_t n) {
     pp.in = (const float*)up_in.p; pp.n = c; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
     pp.normalize = cfg.metric == COLTT_COSINE;  // `if vertex.distance.Type() == T_COSINE` (none_vectorstore.go:96-98)
     pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slots = (const uint32_t*)up_slots.p;
-    pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale;
+    pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale; pp.shadow_out = d_shadow; pp.shadow_stride = shadow_stride;
     rc = launch_prep_rows(pp, elem, stream);
     if (rc) return rc;
     scatter_ids_kernel<<<(unsigned)((c + 255) / 256), 256, 0, stream>>>((const uint64_t*)up_ids.p, (const uint32_t*)up_slots.p, d_ids, c);
@@ -313,7 +324,7 @@ int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uin
   pp.in = d_vecs; pp.n = n; pp.in_stride = stride_floats; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
   pp.normalize = cfg.metric == COLTT_COSINE;
   pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slot_base = (uint32_t)n_rows;
-  pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale;
+  pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale; pp.shadow_out = d_shadow; pp.shadow_stride = shadow_stride;
   rc = launch_prep_rows(pp, elem, stream);
   if (rc) return rc;
   iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_ids, n_rows, n, id_base);
@@ -341,6 +352,7 @@ int Store::remove(const uint64_t* ids, size_t n) {
       COLTT_CUDA(cudaMemcpyAsync(d_rows + (size_t)s * row_stride, d_rows + (size_t)lastslot * row_stride, row_stride, cudaMemcpyDeviceToDevice, stream));
       COLTT_CUDA(cudaMemcpyAsync(d_norm2 + s, d_norm2 + lastslot, 4, cudaMemcpyDeviceToDevice, stream));
       if (d_scale) COLTT_CUDA(cudaMemcpyAsync(d_scale + s, d_scale + lastslot, 4, cudaMemcpyDeviceToDevice, stream));
+      if (d_shadow) COLTT_CUDA(cudaMemcpyAsync(d_shadow + (size_t)s * shadow_stride, d_shadow + (size_t)lastslot * shadow_stride, shadow_stride, cudaMemcpyDeviceToDevice, stream));
       COLTT_CUDA(cudaMemcpyAsync(d_ids + s, d_ids + lastslot, 8, cudaMemcpyDeviceToDevice, stream));
       h_ids[s] = h_ids[lastslot];
       id2slot[h_ids[s]] = s;
@@ -481,11 +493,14 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
 int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int nearest, Hit* d_out,
                         int* d_counts, bool timed, float* dbg_acc, bool* used_fast) {
   *used_fast = false;
-  // fp16 rows (kind::f16) and E4M3 rows (kind::f8f6f4; cosine: the row scale folds into the per-row coefficient)
-  const bool fp8 = elem == ELEM_F8E;
-  if (!(elem == ELEM_F16 || (fp8 && cfg.metric == COLTT_COSINE)) || n_rows < 4096 || (size_t)k > n_rows) return COLTT_OK;
+  // fp16 rows (kind::f16), E4M3 rows (kind::f8f6f4; cosine: the row scale folds into the per-row coefficient) and fp32
+  // cosine rows through their fp16 shadow (kind::f16 on the shadow, exact re-rank on the fp32 rows)
+  const bool fp8 = elem == ELEM_F8E, shadow = elem == ELEM_F32 && d_shadow != nullptr;
+  if (!(elem == ELEM_F16 || (fp8 && cfg.metric == COLTT_COSINE) || shadow) || n_rows < 4096 || (size_t)k > n_rows) return COLTT_OK;
+  const uint8_t* f_rows = shadow ? d_shadow : d_rows;                 // the filter's operand
+  const uint32_t f_stride = shadow ? shadow_stride : row_stride, f_es = shadow ? 2u : elem_size(elem);
   GemmPlan gp;
-  if (plan_gemm_filter(dim * elem_size(elem), fp8, (uint32_t)nq, (uint32_t)k, n_sms, &gp) != COLTT_OK) return COLTT_OK;  // unsupported shape -> exact
+  if (plan_gemm_filter(dim * f_es, fp8, (uint32_t)nq, (uint32_t)k, n_sms, &gp) != COLTT_OK) return COLTT_OK;  // unsupported shape -> exact
   const uint32_t n_cols = gemm_filter_cols(gp, (uint32_t)n_rows);   // columns that see one query
   if (n_cols < gp.groups) return COLTT_OK;                           // too few columns for the bound scheme -> exact
   const uint32_t q_stride = (dim + 7) / 8 * 8;
@@ -537,13 +552,13 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
     }
   }
 #endif
-  rc = launch_gemm_filter(g, gp, d_rows, row_stride, st, &c.maps); if (rc) return rc;
+  rc = launch_gemm_filter(g, gp, f_rows, f_stride, st, &c.maps); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[2], st);
   RerankParams r{};
   r.nq = (uint32_t)nq; r.k = (uint32_t)k; r.dim = dim; r.q_stride = q_stride; r.row_stride = row_stride;
   r.grid_x = n_cols; r.cand_cap = gp.cand_out_cap;
   r.max_rows = gp.pub_kth ? 256u : 64u;
-  r.eps_rel = fast_eps_rel(dim);
+  r.eps_rel = shadow ? fast_eps_rel_f32_shadow(dim) : fast_eps_rel(dim);
   r.metric = cfg.metric; r.nearest = nearest; r.elem = elem;
   r.queries = (const float*)c.q_deq.p; r.q_norm2 = (const float*)c.q_n2.p; r.q_scale = fp8 ? (const float*)c.q_scale.p : nullptr;
   r.rows = d_rows; r.row_norm2 = d_norm2; r.row_scale = d_scale; r.ids = d_ids;

@@ -65,6 +65,8 @@ struct Store {
   uint8_t* d_rows = nullptr;
   float* d_norm2 = nullptr;
   float* d_scale = nullptr;                        // ELEM_F8E only: per-row power-of-two scale
+  uint8_t* d_shadow = nullptr;                     // fp32 cosine stores: fp16 copy of the rows, the tensor-core filter's operand
+  uint32_t shadow_stride = 0;                      // bytes per shadow row (0 = no shadow)
   uint64_t* d_ids = nullptr;
   unsigned long long* d_stat = nullptr;            // queries the FAST path re-ran exactly (counted on the device)
   std::atomic<bool> timing{false};                 // record per-phase CUDA events around searches (diagnostics)

@@ -117,6 +117,82 @@ def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, st
     return local_search, merge
 
 
+class Comm:
+    """One rank of a sharded collection behind the C-ABI (include/coltt_b200.h, csrc/comm.cu): the local search, the single
+    NCCL all-gather of per-shard top-k and the K5 merge all run inside libcoltt_b200.so on the rank's stream, with persistent
+    exchange buffers and pinned staging.  torch.distributed is used only to hand the 128-byte rendezvous blob to the ranks."""
+
+    def __init__(self, handle, rank: int, world: int, device: int):
+        self._h, self.rank, self.world, self.device = handle, rank, world, device
+
+    @classmethod
+    def from_torch_distributed(cls, device_index: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+        blob = (C.c_uint8 * 128)()
+        if rank == 0 and world > 1:
+            _lib.check(L.coltt_b200_comm_unique_id(blob, 128))
+        if world > 1:
+            t = torch.tensor(list(blob), dtype=torch.uint8)
+            t = t.cuda(device_index) if dist.get_backend(group) == "nccl" else t
+            dist.broadcast(t, src=0, group=group)
+            blob = (C.c_uint8 * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        if world > 1:
+            _lib.check(L.coltt_b200_comm_init_rank(blob, rank, world, device_index, C.byref(h)))
+        else:
+            dev = (C.c_int * 1)(device_index)
+            _lib.check(L.coltt_b200_init(dev, 1, C.byref(h)))
+        return cls(h, rank, world, device_index)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            from . import _lib
+            _lib.lib().coltt_b200_comm_destroy(self._h)
+            self._h = None
+
+    def search(self, space, queries, k: int, select_mode: int, math_mode: Optional[int] = None):
+        """Collective: every rank calls with the same queries.  Host buffers in, merged (ids, scores, counts) out."""
+        import ctypes as C
+        from . import _lib
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint64)
+        sc = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.int32)
+        mm = space.math_mode if math_mode is None else math_mode
+        _lib.check(_lib.lib().coltt_b200_sharded_search(self._h, space._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, select_mode, mm,
+                                                        ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                                        cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        return ids, sc, cnt
+
+    def search_dev(self, space, d_queries_ptr: int, nq: int, k: int, select_mode: int, math_mode: int, d_out_ptr: int, d_counts_ptr: int,
+                   stream_ptr: int = 0):
+        from . import _lib
+        _lib.check(_lib.lib().coltt_b200_sharded_search_dev(self._h, space._h, d_queries_ptr, nq, k, select_mode, math_mode, d_out_ptr,
+                                                            d_counts_ptr, stream_ptr))
+
+    def hnsw_search(self, sub_graph, queries, k: int, ef: int = 0):
+        """Collective Hnsw.Search over one sub-graph per GPU."""
+        import ctypes as C
+        from . import _lib
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint64)
+        sc = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.int32)
+        _lib.check(_lib.lib().coltt_b200_sharded_hnsw_search(self._h, sub_graph._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, ef,
+                                                             ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)),
+                                                             cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        return ids, sc, cnt
+
+
 def unpack_hits(hits, counts):
     """int32 [nq,k,4] coltt_hit tensor -> (ids u64 [nq,k], scores f32 [nq,k], counts)."""
     h = hits.detach().cpu().contiguous().numpy().view(HIT_DTYPE).reshape(hits.shape[0], hits.shape[1])

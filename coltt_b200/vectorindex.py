@@ -97,9 +97,16 @@ class Hnsw:
         _lib.check(_lib.lib().coltt_b200_hnsw_len(self._h, C.byref(n)))
         return int(n.value)
 
+    def Dim(self) -> int:
+        d = C.c_uint32(0)
+        _lib.check(_lib.lib().coltt_b200_hnsw_dim(self._h, C.byref(d)))
+        return int(d.value)
+
     def BatchSearch(self, queries, k: int, ef: int = 0):
         q = np.ascontiguousarray(queries, dtype=np.float32)
         q = q.reshape(1, -1) if q.ndim == 1 else q
+        if q.shape[1] != self.Dim():     # the C side reads nq * dim floats: never hand it a shorter buffer
+            raise ValueError("Dim Length UnmatchdError: expect dimension: [%d], but got [%d]" % (self.Dim(), q.shape[1]))
         nq = q.shape[0]
         ids = np.zeros((nq, max(k, 1)), dtype=np.uint64)
         sc = np.zeros((nq, max(k, 1)), dtype=np.float32)

@@ -192,6 +192,9 @@ COLTT_API int coltt_b200_multi_search(coltt_store* const* fields, const float* c
 COLTT_API int coltt_b200_hnsw_load(const void* commit_blob, size_t len, int device, coltt_hnsw** out);
 COLTT_API void coltt_b200_hnsw_destroy(coltt_hnsw* h);
 COLTT_API int coltt_b200_hnsw_len(coltt_hnsw* h, uint64_t* n);
+/* Vector dimension of the index (hnswVertex.vector length): callers validate query length against it, as
+ * Core.VectorSearch's callers do (core/core.go:633-695). */
+COLTT_API int coltt_b200_hnsw_dim(coltt_hnsw* h, uint32_t* dim);
 /* Hnsw.Search (hnsw.go:243-278), batched: normalize, greedy descent (hnsw.go:320-343),
  * searchLevel with ef = max(ef, k) (hnsw.go:345-389), trim to k, ascending.  ef <= 0 uses the
  * ef stored in the blob (hnsw_config.go:138).  Neighbour order = ascending id. */
@@ -226,6 +229,39 @@ COLTT_API int coltt_b200_hnsw_commit(coltt_hnsw* h, void* buf, size_t* len);
 COLTT_API int coltt_b200_hnsw_build_stats(coltt_hnsw* h, double* ms4, uint64_t* n_edges, int32_t* max_level);
 /* [0] construction searches served by the tensor-core filter, [1] of those re-run exactly (margin not certified). */
 COLTT_API int coltt_b200_hnsw_build_fast_stats(coltt_hnsw* h, uint64_t* out2);
+
+/* ---- sharded collections: one shard per GPU, ONE NCCL all-gather of per-shard top-k, merge ---------------
+ * Reference analogue: the 16 in-process shards of a vectorspace, each scanned into a shard-local queue and re-merged
+ * (edge/none_vectorstore.go:152-178); rows -> shard by ShardVertex(id, 16) mod n_gpus (pkg/sharding/shard.go:34-41; the
+ * host partitions the ids).  A coltt_comm is one rank: a GPU, its NCCL communicator, a stream and persistent exchange
+ * buffers.  NCCL is loaded at run time (libnccl.so.2); without it these calls return COLTT_ERR_UNSUPPORTED. */
+typedef struct coltt_comm coltt_comm;
+/* One process driving n GPUs (the Go host): ncclCommInitAll over device_ids; out_comms receives n rank handles
+ * (rank i = device_ids[i]).  n_dev = 1 needs no NCCL.  coltt_b200_shutdown destroys every handle created here. */
+COLTT_API int coltt_b200_init(const int* device_ids, int n_dev, coltt_comm** out_comms);
+COLTT_API void coltt_b200_shutdown(void);
+/* One process per GPU: rank 0 makes the 128-byte rendezvous blob, the host hands it to every rank, each joins. */
+COLTT_API int coltt_b200_comm_unique_id(void* out, size_t len);
+COLTT_API int coltt_b200_comm_init_rank(const void* unique_id, int rank, int world, int device, coltt_comm** out);
+COLTT_API void coltt_b200_comm_destroy(coltt_comm* c);
+COLTT_API int coltt_b200_comm_info(coltt_comm* c, int* rank, int* world, int* device);
+/* VertexSearch over the whole sharded collection, called by EVERY rank with the same queries / nq / k / modes (a
+ * collective): local search of `shard` (hits written straight into the send buffer), ncclAllGather, merge.  Every rank
+ * ends up with the merged answer; a rank may pass NULL outputs.  Host buffers; returns when the answer is in them. */
+COLTT_API int coltt_b200_sharded_search(coltt_comm* c, coltt_store* shard, const float* queries, size_t nq, int k, int select_mode,
+                                        int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts);
+/* Device-resident form (d_queries fp32 [nq][dim], d_out coltt_hit [nq][k], d_counts int32 [nq]); with a caller stream the
+ * call only enqueues (search, all-gather and merge are stream-ordered), with NULL it uses the rank's stream and waits. */
+COLTT_API int coltt_b200_sharded_search_dev(coltt_comm* c, coltt_store* shard, const void* d_queries, size_t nq, int k, int select_mode,
+                                            int math_mode, void* d_out, void* d_counts, void* stream);
+/* All n ranks of this process in one call (one library thread per rank); outputs come from rank 0. */
+COLTT_API int coltt_b200_sharded_search_all(coltt_comm* const* comms, coltt_store* const* shards, int n, const float* queries, size_t nq,
+                                            int k, int select_mode, int math_mode, uint64_t* out_ids, float* out_scores,
+                                            int32_t* out_counts);
+/* Hnsw.Search over one independent sub-graph per GPU (each built over its row shard): local walk, the same all-gather,
+ * merge nearest-first.  Collective like coltt_b200_sharded_search. */
+COLTT_API int coltt_b200_sharded_hnsw_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef,
+                                             uint64_t* out_ids, float* out_scores, int32_t* out_counts);
 
 /* ---- timing (replaces pprof for this path) ---------------------------------
  * Device time in milliseconds of the kernels of the last search on this handle, measured

@@ -21,3 +21,48 @@ def test_sharded_search_two_or_more_gpus():
            "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "DIST_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_single_process_multi_gpu_through_the_c_abi():
+    """coltt_b200_init(device_ids, n) + coltt_b200_sharded_search_all: ONE process drives every GPU (the Go host's shape,
+    INTEGRATION.md) — ncclCommInitAll, one library thread per rank, result == the oracle over the union of the shards."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import coltt_b200 as cb
+    from coltt_b200 import _lib
+    from coltt_b200.dist import gpu_of
+    from oracle import oracle as orc
+    from tests.util import QUERY_SEED, normal, sparse_ids
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    g = 2 if g < 4 else 4
+    L = _lib.lib()
+    n, d, k = 50_000, 256, 10
+    ids, vecs = sparse_ids(n), normal(n, d)
+    owner = gpu_of(ids, g)
+    shards = []
+    for r in range(g):
+        sp = cb.VectorSpace("s", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_BF16), device=r)
+        sp.ChangedVertices(ids[owner == r], vecs[owner == r])
+        shards.append(sp)
+    devs = (C.c_int * g)(*range(g))
+    comms = (C.c_void_p * g)()
+    _lib.check(L.coltt_b200_init(devs, g, comms))
+    sh = (C.c_void_p * g)(*[s._h for s in shards])
+    qs = normal(40, d, QUERY_SEED)
+    full = orc.FlatStore(d, orc.COSINE, orc.Q_BF16)
+    full.upsert(ids, vecs)
+    for mode in (cb.SELECT_NEAREST, cb.SELECT_COMPAT):
+        for mm in (cb.MATH_FAST, cb.MATH_EXACT):
+            oi, osc, oc = np.zeros((40, k), np.uint64), np.zeros((40, k), np.float32), np.zeros(40, np.int32)
+            _lib.check(L.coltt_b200_sharded_search_all(comms, sh, g, qs.ctypes.data_as(C.POINTER(C.c_float)), 40, k, mode, mm,
+                                                       oi.ctypes.data_as(C.POINTER(C.c_uint64)), osc.ctypes.data_as(C.POINTER(C.c_float)),
+                                                       oc.ctypes.data_as(C.POINTER(C.c_int32))))
+            for j in range(8):
+                wi, ws = full.search_total_order(qs[j], k, select_mode=mode)
+                assert np.array_equal(oi[j, : oc[j]], wi) and osc[j, : oc[j]].tobytes() == ws.tobytes(), (mode, mm, j)
+    L.coltt_b200_shutdown()
+    for s in shards:
+        s.close()

@@ -48,7 +48,10 @@ def _fast_stats(sp):
 @pytest.mark.parametrize("d,n,nq", [(768, 8192, 5), (768, 8200, 130), (128, 4096, 128), (100, 5000, 200), (64, 4100, 256)])
 def test_tensor_core_accumulators_match_fp64_reference(cb, oracle, d, n, nq):
     """The GEMM itself: acc[q][row] = sum_k fp16(q)[k] * fp16(row)[k] with fp32 accumulation.
-    Tolerance: 2e-4 absolute on unit-norm operands (768 exact products, fp32 accumulate)."""
+    Tolerance: the certificate margin the library derives from dim (coltt_b200_fast_eps_rel, relative to ||q|| ||row||,
+    which is 1 here up to fp16 rounding) — the bound the certificate relies on is the bound the test enforces."""
+    from coltt_b200 import _lib
+    tol = float(_lib.lib().coltt_b200_fast_eps_rel(d)) * 1.01
     ids = np.arange(1, n + 1, dtype=np.uint64)
     vecs = normal(n, d)
     qs = normal(nq, d, QUERY_SEED)
@@ -60,15 +63,16 @@ def test_tensor_core_accumulators_match_fp64_reference(cb, oracle, d, n, nq):
     want = q16 @ rows16.T
     # slots == insertion order for a fresh store, so acc column j is row j
     err = np.abs(acc.astype(np.float64) - want)
-    if not np.isfinite(acc).all() or err.max() >= 2e-4:   # leave evidence for the next debugging step
+    if not np.isfinite(acc).all() or err.max() >= tol:   # leave evidence for the next debugging step
         import os
         os.makedirs("gpurun_out", exist_ok=True)
         np.savez(f"gpurun_out/fast_dbg_d{d}_n{n}_q{nq}.npz", got=acc[:, :512], want=want[:, :512].astype(np.float32))
-        bad = ~np.isfinite(acc) | (err >= 2e-4)
+        bad = ~np.isfinite(acc) | (err >= tol)
         print("bad fraction", bad.mean(), "bad rows(q) sample", np.where(bad.any(1))[0][:10], "bad cols sample", np.where(bad.any(0))[0][:20])
         print("got[0,:8]", acc[0, :8], "want[0,:8]", want[0, :8])
     assert np.isfinite(acc).all(), "some accumulators were never written"
-    assert err.max() < 2e-4, f"max abs err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+    print(f"fp16 d={d}: max abs accumulator error {err.max():.3e} (margin {tol:.3e})")
+    assert err.max() < tol, f"max abs err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
     # and the FAST answer equals the EXACT answer
     ei, es, ec = sp.BatchVertexSearch(qs, 10, select_mode=cb.SELECT_NEAREST, math_mode=cb.MATH_EXACT)
     for j in range(nq):
@@ -117,9 +121,10 @@ def test_fast_with_heavy_ties_falls_back_and_stays_exact(cb):
 
 
 def test_fast_unsupported_shapes_silently_use_exact(cb, oracle):
-    """dim > 768 (query tile exceeds tensor memory), k > 32, fp32 stores and tiny stores are served by the
-    exact kernel under COLTT_MATH_FAST — same answer, no error."""
-    for d, n, k, quant in [(1536, 5000, 10, 3), (128, 5000, 64, 3), (128, 5000, 10, 0), (128, 300, 10, 3)]:
+    """Rows wider than 1536 bytes (the resident query tile would not fit shared memory), k > 200, L2 on fp32 / f8 stores and
+    tiny stores are served by the exact kernel under COLTT_MATH_FAST — same answer, no error; k = 64 and fp32 cosine
+    (served by FAST since round 2) give the same answer too."""
+    for d, n, k, quant in [(1536, 5000, 10, 3), (128, 5000, 64, 3), (128, 5000, 10, 0), (128, 300, 10, 3), (128, 5000, 300, 3), (1024, 5000, 10, 0)]:
         ids, vecs = sparse_ids(n), normal(n, d)
         sp = cb.VectorSpace("u", cb.Metadata(d, 0, quant))
         sp.ChangedVertices(ids, vecs)
@@ -127,4 +132,78 @@ def test_fast_unsupported_shapes_silently_use_exact(cb, oracle):
         fi, fs, fc = sp.BatchVertexSearch(qs, k, select_mode=1, math_mode=cb.MATH_FAST)
         ei, es, ec = sp.BatchVertexSearch(qs, k, select_mode=1, math_mode=cb.MATH_EXACT)
         assert np.array_equal(fi, ei) and fs.tobytes() == es.tobytes()
+        sp.close()
+
+
+@pytest.mark.parametrize("data", ["normal", "uniform"])
+def test_fp32_store_fast_through_fp16_shadow_equals_exact(cb, oracle, data):
+    """fp32 ("none") cosine stores: COLTT_MATH_FAST filters through an fp16 shadow of the rows on the tensor cores and
+    re-ranks on the fp32 rows — ids and score bits equal EXACT (and the oracle), top-10 and top-100, and the FAST path
+    must actually serve the queries (few certificate fallbacks) despite the wider margin."""
+    n, d = 100_000, 768
+    ids = sparse_ids(n)
+    vecs = normal(n, d) if data == "normal" else uniform(n, d)
+    sp = cb.VectorSpace("f32", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_None))
+    sp.ChangedVertices(ids, vecs)
+    st = oracle.FlatStore(d, oracle.COSINE, oracle.Q_NONE)
+    st.upsert(ids, vecs)
+    for k in (10, 100):
+        for nq in (1, 256):
+            qs = (normal if data == "normal" else uniform)(nq, d, QUERY_SEED + nq + k)
+            for mode in (cb.SELECT_NEAREST, cb.SELECT_COMPAT):
+                fi, fs, fc = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=cb.MATH_FAST)
+                sel = np.arange(nq) if nq <= 16 else np.linspace(0, nq - 1, 16).astype(int)
+                ei, es, ec = sp.BatchVertexSearch(qs[sel], k, select_mode=mode, math_mode=cb.MATH_EXACT)
+                for a, j in enumerate(sel):
+                    assert_same_hits(fi[j, :fc[j]], fs[j, :fc[j]], ei[a, :ec[a]], es[a, :ec[a]], f"f32 {data} k={k} nq={nq} mode={mode} q{j}")
+                wi, ws = st.search_total_order(qs[0], k, select_mode=mode)
+                assert_same_hits(fi[0, :fc[0]], fs[0, :fc[0]], wi, ws, f"f32 vs oracle {data} k={k} nq={nq} mode={mode}")
+    served, fell_back = _fast_stats(sp)
+    assert served > 0, "FAST path was never taken for the fp32 store"
+    assert fell_back <= served * 0.1, f"too many uncertified queries: {fell_back}/{served}"
+    # upsert-overwrite / remove keep the shadow in step with the rows
+    sp.ChangedVertices(ids[:100], vecs[500:600])
+    st.upsert(ids[:100], vecs[500:600])
+    sp.RemoveVertex(ids[2000:2500])
+    st.remove(ids[2000:2500])
+    qs = (normal if data == "normal" else uniform)(8, d, QUERY_SEED + 99)
+    fi, fs, fc = sp.BatchVertexSearch(qs, 10, select_mode=cb.SELECT_NEAREST, math_mode=cb.MATH_FAST)
+    for j in range(8):
+        wi, ws = st.search_total_order(qs[j], 10, select_mode=oracle.NEAREST)
+        assert_same_hits(fi[j, :fc[j]], fs[j, :fc[j]], wi, ws, f"f32 after mutation q{j}")
+    sp.close()
+
+
+def test_certificate_margin_covers_the_filter_error_and_near_ties(cb, oracle):
+    """The margin is a function of dim (coltt_b200_fast_eps_rel).  (1) The raw tensor-core scores stay
+    within it at dim 64 and 768 on adversarial all-positive data (every product has the same sign, so truncation errors
+    add up instead of cancelling).  (2) Rows that differ from a top-10 row by one fp16 ulp in one element — exact scores
+    closer than any margin — still come back in the exact order: the certificate either proves the order or sends the
+    query to the exact kernel."""
+    from coltt_b200 import _lib
+    for d in (64, 768):
+        n, nq = 8192, 64
+        vecs = uniform(n, d) + np.float32(0.5)
+        qs = uniform(nq, d, QUERY_SEED) + np.float32(0.5)
+        # near-ties: copies of the first rows with one element nudged by ~1 fp16 ulp
+        for j in range(40):
+            vecs[4000 + j] = vecs[j]
+            vecs[4000 + j, j % d] *= np.float32(1.0 + 2.0 ** -10)
+        ids = np.arange(1, n + 1, dtype=np.uint64)
+        sp = cb.VectorSpace("m", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_BF16))
+        sp.ChangedVertices(ids, vecs)
+        acc, gi, gs, gc = _fast_scores(cb, sp, qs, 10, cb.SELECT_NEAREST)
+        rows16 = np.stack([oracle.f16_to_f32(oracle.f32_to_f16(oracle.normalize(v))) for v in vecs]).astype(np.float64)
+        q16 = np.stack([oracle.f16_to_f32(oracle.f32_to_f16(oracle.normalize(q))) for q in qs]).astype(np.float64)
+        want = q16 @ rows16.T
+        rel = np.abs(acc.astype(np.float64) - want) / (np.linalg.norm(q16, axis=1)[:, None] * np.linalg.norm(rows16, axis=1)[None, :])
+        eps = float(_lib.lib().coltt_b200_fast_eps_rel(d))
+        print(f"fp16 d={d}: max relative accumulator error {rel.max():.3e} (certificate margin {eps:.3e})")
+        assert rel.max() < eps, f"d={d}: filter error {rel.max()} exceeds the certificate margin {eps}"
+        qs2 = np.concatenate([vecs[:20] + uniform(20, d, 5) * np.float32(1e-3), qs[:12]])      # queries next to the near-tied rows
+        for mode in (cb.SELECT_NEAREST, cb.SELECT_COMPAT):
+            fi, fs, fc = sp.BatchVertexSearch(qs2, 10, select_mode=mode, math_mode=cb.MATH_FAST)
+            ei, es, ec = sp.BatchVertexSearch(qs2, 10, select_mode=mode, math_mode=cb.MATH_EXACT)
+            for j in range(len(qs2)):
+                assert_same_hits(fi[j, :fc[j]], fs[j, :fc[j]], ei[j, :ec[j]], es[j, :ec[j]], f"near ties d={d} mode={mode} q{j}")
         sp.close()
