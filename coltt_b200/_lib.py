@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "coltt_b200_store_append_dev", "coltt_b200_store_fast_stats", "coltt_b200_fast_eps_rel", "coltt_b200_hnsw_dim",
     "coltt_b200_init", "coltt_b200_shutdown", "coltt_b200_comm_unique_id", "coltt_b200_comm_init_rank", "coltt_b200_comm_destroy",
     "coltt_b200_comm_info", "coltt_b200_sharded_search", "coltt_b200_sharded_search_dev", "coltt_b200_sharded_search_all",
-    "coltt_b200_sharded_hnsw_search",
+    "coltt_b200_sharded_hnsw_search", "coltt_b200_hnsw_pq_train", "coltt_b200_hnsw_pq_search",
 ]
 
 
@@ -41,6 +41,10 @@ class StoreCfg(C.Structure):
 class HnswBuildCfg(C.Structure):
     _fields_ = [("dim", C.c_uint32), ("metric", C.c_int32), ("m", C.c_int32), ("ef", C.c_int32), ("ef_construction", C.c_int32),
                 ("device", C.c_int32), ("seed", C.c_uint64)]
+
+
+class PqParams(C.Structure):
+    _fields_ = [("num_centroids", C.c_int32), ("num_sub_vectors", C.c_int32), ("trigger_threshold", C.c_int32)]
 
 
 class Hit(C.Structure):
@@ -105,6 +109,8 @@ def lib() -> C.CDLL:
     L.coltt_b200_fast_eps_rel.argtypes = [C.c_uint32]
     L.coltt_b200_fast_eps_rel.restype = C.c_float
     L.coltt_b200_hnsw_dim.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.coltt_b200_hnsw_pq_train.argtypes = [vp, C.POINTER(PqParams), C.c_int]
+    L.coltt_b200_hnsw_pq_search.argtypes = [vp, f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, u64p, f32p, i32p]
     ip = C.POINTER(C.c_int)
     L.coltt_b200_init.argtypes = [ip, C.c_int, C.POINTER(vp)]
     L.coltt_b200_shutdown.restype = None

@@ -35,11 +35,13 @@ namespace coltt {
 static constexpr int kScanWarps = 8;
 static constexpr int kRowsPerWarp = 16;
 static constexpr uint32_t kRowPad = 16;
+static constexpr uint32_t kF8LutFloats = 0x84 * 32;   // (code & 0x83) x 32 lane-private copies = 16.5 KB
 
 template <int ELEM, int METRIC, int QT>
 __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ float lut_s[ELEM == ELEM_F8C ? 256 : 1];
+  __shared__ float lut_tab[ELEM == ELEM_F8C ? kF8LutFloats : 1];   // F8C: per-lane copies of the decode table (exact_math.cuh)
+  const float* lut_s = lut_tab + (threadIdx.x & 31);
   __shared__ int warp_cnt_s[kScanWarps][QT];
   __shared__ uint32_t cta_kth_s[QT];   // best K-th bound any warp of this CTA has reached, order-encoded
 
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) flat_scan_kernel(ScanParam
   uint8_t* stages = smem + stages_off;                                // [W][S][16][RS]
 
   if (ELEM == ELEM_F8C)
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = __uint_as_float(f8_compat_decode_bits((uint8_t)i));
+    for (uint32_t i = threadIdx.x; i < kF8LutFloats; i += blockDim.x) lut_tab[i] = __uint_as_float(f8_compat_decode_bits((uint8_t)(i >> 5)));
   // Query groups of QT: grid.y groups run side by side, each CTA loops over the rest.  With `n_active`
   // the number of queries lives on the device (the FAST path's exact re-run of uncertified queries is
   // enqueued unconditionally and costs one empty wave when there is nothing to do); `q_map` then says
@@ -290,7 +292,9 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
   const size_t half = (227 * 1024) / 2 - 1024 - 256;
   const size_t merge_need = ((size_t)kScanWarps * k + k) * sizeof(Hit) + kScanWarps * sizeof(int);
   const int ctas_per_sm = (env_ctas == 2 && fixed + 32 * 1024 <= half && merge_need <= half) ? 2 : 1;
-  const size_t budget = ctas_per_sm == 2 ? half : 227 * 1024 - 256;  // static smem (lut, counts) is small; keep a margin
+  // static shared memory: counts (small) and, for the reference's f8 codec, the lane-private decode table
+  const size_t static_smem = 256 + (elem == ELEM_F8C ? (size_t)kF8LutFloats * 4 : 0);
+  const size_t budget = ctas_per_sm == 2 ? half : 227 * 1024 - static_smem;
   const size_t per_warp = (budget - fixed) / kScanWarps;
   const uint32_t row_up = (row_stride + 127) / 128 * 128;
   uint32_t cb = 0, stages = 0;
@@ -307,7 +311,7 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
   const size_t merge_bytes = ((size_t)kScanWarps * k + k) * sizeof(Hit) + kScanWarps * sizeof(int);
   size_t smem = fixed + (size_t)kScanWarps * stages * kRowsPerWarp * (cb + kRowPad);
   if (smem < merge_bytes) smem = merge_bytes;
-  if (smem > 227 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "shared memory budget exceeded");
+  if (smem + static_smem - 256 > 227 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "shared memory budget exceeded");
   const uint32_t n_groups = (n_items + kRowsPerWarp - 1) / kRowsPerWarp;
   uint32_t gx = (n_groups + kScanWarps - 1) / kScanWarps;
   if (gx > (uint32_t)(n_sms * ctas_per_sm)) gx = (uint32_t)(n_sms * ctas_per_sm);

@@ -27,6 +27,9 @@ struct Hnsw {
   float last_kernel_ms = 0.0f;
   std::mutex mu;
   DeviceBuf q_in, q_deq, q_n2, visited, out, counts, q_map, qlog;
+  // product quantizer (pq.cu): codebooks [m][c][dsub] fp32, codes [n][m] u8, per-search survivor scratch
+  DeviceBuf pq_cent, pq_codes, pq_slots, pq_d2, pq_cnt;
+  uint32_t pq_m = 0, pq_c = 0, pq_dsub = 0;
   uint64_t last_evals = 0, last_exp = 0, last_ties = 0;   // last search: distance evaluations, expansions, queries that met a tie
   uint64_t build_fast_queries = 0, build_fast_fallbacks = 0;   // bulk build: searches served by the FAST path / re-run exactly
   double build_ms[4] = {0, 0, 0, 0};            // bulk build: ingest, kNN search, exact edge distances, host graph assembly

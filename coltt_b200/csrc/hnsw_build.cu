@@ -313,6 +313,9 @@ static int hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids_in, c
   }
   const double t1 = now_ms();
   double ms_knn = 0, ms_dist = 0, ms_host = 0;
+  float max_abs = 0.0f;                        // Euclidean only: does the data fit the fp16 candidate shard?
+  if (cfg->metric != COLTT_COSINE)
+    for (size_t i = 0; i < n * (size_t)dim; i++) { const float a = std::fabs(vecs[i]); if (!(a <= max_abs)) max_abs = a == a ? a : INFINITY; }
 
   // ---- per level, top down
   const uint32_t q_stride = (dim + 7) / 8 * 8;
@@ -337,26 +340,34 @@ static int hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids_in, c
       COLTT_CUDA(cudaGetLastError());
       contig = (const float*)d_contig.p;
     }
-    // the members inserted so far, as a temporary fp16 FLAT shard (ids = member indices = insertion order)
+    // The members inserted so far, as a temporary FLAT shard (ids = member indices = insertion order) holding the SAME fp32
+    // rows as the index (appended raw, not re-normalized).  Cosine: an fp32 shard, which COLTT_MATH_FAST serves through its
+    // fp16 shadow with results bit-identical to the exact fp32 scan — the M hits ARE the true fp32 top-M, nothing is lost
+    // to a coarser ranking.  Euclidean rows are not unit-norm: the fp32 shard has no tensor-core path, so an fp16 shard
+    // ranks the candidates, over-fetched (M + 8, at most 24) so that the fp32 re-scoring below picks the true M nearest
+    // unless more than 8 rows swap ranks at the cut; values outside the fp16 range fall back to the exact fp32 shard.
+    const bool f16_shard = cfg->metric != COLTT_COSINE && max_abs <= 60000.0f;
     coltt_store_cfg scfg{};
-    scfg.dim = dim; scfg.metric = cfg->metric; scfg.quant = COLTT_QUANT_F16; scfg.device = cfg->device; scfg.capacity_hint = m;
+    scfg.dim = dim; scfg.metric = cfg->metric; scfg.quant = f16_shard ? COLTT_QUANT_F16 : COLTT_QUANT_NONE; scfg.device = cfg->device; scfg.capacity_hint = m;
     Store* shard_raw = nullptr;
     rc = Store::create(&scfg, &shard_raw);
     if (rc) return rc;
     std::unique_ptr<Store> shard(shard_raw);
+    shard->raw_queries = !f16_shard;          // queries are the index's own (already normalized) rows: score them as they are
     COLTT_CUDA(cudaStreamSynchronize(st));    // `contig` and the member list are complete before other streams read them
     {
       auto ctx = shard->acquire_ctx(nullptr);
       if (!ctx) return fail(COLTT_ERR_CUDA, "could not create a search context");
       cudaStream_t ss = ctx->stream;
       const size_t B = kSelBatch;
-      if ((rc = d_hits.ensure(B * (size_t)M * sizeof(Hit))) || (rc = d_counts.ensure(B * 4))) return rc;
+      if ((rc = d_hits.ensure(B * (size_t)(M + 8) * sizeof(Hit))) || (rc = d_counts.ensure(B * 4))) return rc;
       const size_t smem = ((size_t)q_stride + 2 * kSelMaxCand) * 4;
       if (smem > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "dim too large for the neighbour-selection kernel");
       const uint32_t* mem_arg = identity ? nullptr : (const uint32_t*)d_members.p;
       for (size_t q0 = 0; q0 < m && !rc; q0 += B) {
         const size_t nq = std::min(B, m - q0);
-        const uint32_t k = (uint32_t)std::min<size_t>((size_t)M, q0);     // hits wanted from the members before the batch
+        const size_t want = f16_shard ? std::min<size_t>(24, (size_t)M + 8) : (size_t)M;
+        const uint32_t k = (uint32_t)std::min<size_t>(want, q0);           // hits wanted from the members before the batch
         if (k) {
           rc = shard->search_enqueue(*ctx, ss, contig + q0 * dim, nq, (int)k, COLTT_SELECT_NEAREST, COLTT_MATH_FAST, nullptr, 0, (Hit*)d_hits.p,
                                      (int*)d_counts.p, false);
@@ -376,7 +387,7 @@ static int hnsw_build(const coltt_hnsw_build_cfg* cfg, const uint64_t* ids_in, c
         }
         count_launch();
         // the batch joins the shard (disjoint rows: the search above keeps reading the prefix while this writes)
-        rc = shard->append_dev(contig + q0 * dim, nq, dim);
+        rc = shard->append_dev(contig + q0 * dim, nq, dim, 0, /*raw=*/true);
       }
       cudaError_t e = cudaStreamSynchronize(ss);
       shard->release_ctx(std::move(ctx));

@@ -68,8 +68,12 @@ int require_device(int device) {
   return COLTT_OK;
 }
 
+static std::atomic<uint64_t> g_alloc_epoch{1};
+uint64_t alloc_epoch() { return g_alloc_epoch.load(std::memory_order_relaxed); }
+
 int DeviceBuf::ensure(size_t bytes) {
   if (bytes <= cap) return COLTT_OK;
+  g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);   // captured graphs hold the old pointer
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
@@ -108,7 +112,7 @@ PinnedBuf::~PinnedBuf() {
 
 thread_local bool Store::in_fallback = false;
 static std::atomic<uint64_t> g_launches{0};
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)(int64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int kernel_attrs(const void* fn, size_t dyn_smem_bytes) {
@@ -133,6 +137,8 @@ int kernel_attrs(const void* fn, size_t dyn_smem_bytes) {
 }
 
 SearchCtx::~SearchCtx() {
+  for (auto& g : graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
   if (done) cudaEventDestroy(done);
@@ -311,7 +317,7 @@ __global__ void iota_ids_kernel(uint64_t* ids, size_t base, size_t n, uint64_t i
 // Bulk ingest of rows that already live on the device (the HNSW builder's temporary per-level shards; shards too large
 // to stage through host memory): Normalize + Lower + ||row||^2 exactly as upsert does, ids = id_base + slot number.
 // The host id map is not maintained, so the store is search-only afterwards.
-int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base) {
+int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uint64_t id_base, bool raw) {
   if (n == 0) return COLTT_OK;
   if (!d_vecs || stride_floats < dim) return fail(COLTT_ERR_INVALID, "append_dev: bad argument");
   std::unique_lock<std::shared_mutex> lk(mu);
@@ -322,7 +328,7 @@ int Store::append_dev(const float* d_vecs, size_t n, uint32_t stride_floats, uin
   if (rc) return rc;
   PrepParams pp{};
   pp.in = d_vecs; pp.n = n; pp.in_stride = stride_floats; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
-  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.normalize = cfg.metric == COLTT_COSINE && !raw;
   pp.rows_out = d_rows; pp.row_stride = row_stride; pp.slot_base = (uint32_t)n_rows;
   pp.norm2_out = d_norm2; pp.norm2_by_slot = 1; pp.scale_out = d_scale; pp.shadow_out = d_shadow; pp.shadow_stride = shadow_stride;
   rc = launch_prep_rows(pp, elem, stream);
@@ -404,6 +410,78 @@ void Store::release_ctx(std::unique_ptr<SearchCtx> c) {
   pool.push_back(std::move(c));
 }
 
+template <class Pre, class Post>
+int Store::enqueue_cached(SearchCtx& c, cudaStream_t st, const GraphKey& key, bool timed, Pre pre, Post post) {
+  static const bool graphs_on = [] { const char* e = getenv("COLTT_GRAPHS"); return !e || atoi(e) != 0; }();
+  auto plain = [&]() -> int {
+    int rc = pre();
+    if (rc) return rc;
+    rc = search_enqueue(c, st, (const float*)key.q, key.nq, key.k, key.sel, key.math, nullptr, 0, (Hit*)key.out, (int*)key.counts, timed);
+    if (rc) return rc;
+    return post();
+  };
+  if (!graphs_on || timed || key.n_rows == 0) return plain();
+  GraphEntry* e = nullptr;
+  for (auto& g : c.graphs)
+    if (g.key == key) { e = &g; break; }
+  if (!e) {
+    if (c.graphs.size() >= 8) {
+      if (c.graphs.front().exec) cudaGraphExecDestroy(c.graphs.front().exec);
+      c.graphs.erase(c.graphs.begin());
+    }
+    c.graphs.emplace_back();
+    e = &c.graphs.back();
+    e->key = key;
+  }
+  if (e->exec && e->epoch != alloc_epoch()) {   // some scratch buffer moved since the capture
+    cudaGraphExecDestroy(e->exec);
+    e->exec = nullptr;
+    e->seen = 1;
+  }
+  if (e->exec) {
+    COLTT_CUDA(cudaGraphLaunch(e->exec, st));
+    count_launch((int)e->launches);
+    fast_queries += e->fast_q;
+    return COLTT_OK;
+  }
+  if (e->seen <= 0) {            // first sight of this key (or capture is off for it): plain enqueue, which also sizes the scratch
+    if (e->seen == 0) e->seen = 1;
+    return plain();
+  }
+  // second call with the same key: capture it
+  const uint64_t l0 = launch_count(), f0 = fast_queries, ep0 = alloc_epoch();
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    e->seen = -1;
+    return plain();
+  }
+  int rc = plain();
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &g);
+  const uint64_t nl = launch_count() - l0, nf = fast_queries - f0;
+  count_launch(-(int)nl);        // nothing ran yet
+  fast_queries = f0;
+  if (rc || ce != cudaSuccess || !g || ep0 != alloc_epoch()) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    e->seen = -1;
+    return plain();              // whatever went wrong under capture is reported (or not) by the plain path
+  }
+  cudaGraphExec_t ex = nullptr;
+  if (cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+    cudaGraphDestroy(g);
+    cudaGetLastError();
+    e->seen = -1;
+    return plain();
+  }
+  cudaGraphDestroy(g);
+  e->exec = ex; e->epoch = ep0; e->launches = nl; e->fast_q = nf;
+  COLTT_CUDA(cudaGraphLaunch(ex, st));
+  count_launch((int)nl);
+  fast_queries += nf;
+  return COLTT_OK;
+}
+
 // The device part of a search: everything enqueued on `st`; queries and outputs on the device.
 // Caller holds the shared lock.
 int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, size_t nq, int k, int select_mode,
@@ -447,7 +525,7 @@ int Store::search_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries,
   // Normalize(target) + Lower(target): *_vectorstore.go:131-139
   PrepParams pp{};
   pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
-  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.normalize = cfg.metric == COLTT_COSINE && !raw_queries;
   pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
   pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
   rc = launch_prep_rows(pp, elem, st);
@@ -523,7 +601,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   if (timed) cudaEventRecord(c.ev[0], st);
   PrepParams pp{};
   pp.in = d_queries; pp.n = nq; pp.in_stride = dim; pp.dim = dim; pp.smem_stride = (dim + 3) / 4 * 4;
-  pp.normalize = cfg.metric == COLTT_COSINE;
+  pp.normalize = cfg.metric == COLTT_COSINE && !raw_queries;
   pp.norm2_out = (float*)c.q_n2.p; pp.norm2_by_slot = 0;
   pp.deq_out = (float*)c.q_deq.p; pp.deq_stride = q_stride;
   if (fp8) { pp.code_out = (uint8_t*)c.q_f16.p; pp.code_stride = gp.q_stride; pp.scale_out = (float*)c.q_scale.p; }
@@ -663,14 +741,29 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
   rc = c.h_q.ensure(nq * dim * 4); if (rc) return rc;
   rc = c.h_out.ensure(nq * (size_t)k * sizeof(Hit) + nq * 4); if (rc) return rc;
   std::memcpy(c.h_q.p, queries, nq * (size_t)dim * 4);
-  COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, c.h_q.p, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
-  rc = search_enqueue(c, st, (const float*)c.q_in.p, nq, k, select_mode, math_mode, use_subset ? (const uint32_t*)c.subset.p : nullptr,
-                      n_sub, (Hit*)c.out.p, (int*)c.counts.p, timed);
-  if (rc) return rc;
   Hit* h_hits = (Hit*)c.h_out.p;
   int* h_counts = (int*)((uint8_t*)c.h_out.p + nq * (size_t)k * sizeof(Hit));
-  COLTT_CUDA(cudaMemcpyAsync(h_counts, c.counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
-  COLTT_CUDA(cudaMemcpyAsync(h_hits, c.out.p, nq * (size_t)k * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+  auto h2d = [&]() -> int {
+    COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, c.h_q.p, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+    return COLTT_OK;
+  };
+  auto d2h = [&]() -> int {
+    COLTT_CUDA(cudaMemcpyAsync(h_counts, c.counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    COLTT_CUDA(cudaMemcpyAsync(h_hits, c.out.p, nq * (size_t)k * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+    return COLTT_OK;
+  };
+  if (use_subset) {
+    if ((rc = h2d())) return rc;
+    rc = search_enqueue(c, st, (const float*)c.q_in.p, nq, k, select_mode, math_mode, (const uint32_t*)c.subset.p, n_sub, (Hit*)c.out.p,
+                        (int*)c.counts.p, timed);
+    if (rc) return rc;
+    if ((rc = d2h())) return rc;
+  } else {
+    // H2D + search + D2H as one (cached) graph: every pointer involved is this scratch's own
+    const GraphKey key{c.q_in.p, nq, k, select_mode, math_mode, c.out.p, c.counts.p, st, n_rows, d_rows, true};
+    rc = enqueue_cached(c, st, key, timed, h2d, d2h);
+    if (rc) return rc;
+  }
   COLTT_CUDA(cudaStreamSynchronize(st));
   c.used = true;
   c.last_stream = st;
@@ -714,7 +807,14 @@ int Store::search_dev(const void* d_queries, size_t nq, int k, int select_mode, 
     ctx->have_times = true;
   }
   cudaGetLastError();
-  int rc = search_enqueue(*ctx, st, (const float*)d_queries, nq, k, select_mode, math_mode, nullptr, 0, (Hit*)d_out, (int*)d_counts, timed);
+  int rc;
+  if (stream_) {
+    const GraphKey key{d_queries, nq, k, select_mode, math_mode, d_out, d_counts, st, n_rows, d_rows, false};
+    auto nop = []() -> int { return COLTT_OK; };
+    rc = enqueue_cached(*ctx, st, key, timed, nop, nop);
+  } else {
+    rc = search_enqueue(*ctx, st, (const float*)d_queries, nq, k, select_mode, math_mode, nullptr, 0, (Hit*)d_out, (int*)d_counts, timed);
+  }
   ctx->timed_last = timed;
   ctx->used = true;
   ctx->last_stream = st;

@@ -115,6 +115,26 @@ class Hnsw:
                                                       sc.ctypes.data_as(_f32p), cnt.ctypes.data_as(_i32p)))
         return ids, sc, cnt
 
+    def TrainPQ(self, num_centroids: int = 256, num_sub_vectors: int = 64, trigger_threshold: int = 65536, iterations: int = 0) -> None:
+        """Attach a product quantizer (ProductQuantizerParameters, pkg/models/hnsw_common.go:20-32; builder-defined
+        arithmetic, parity unpinned): k-means codebooks on the GPU, then every vertex encoded."""
+        pr = _lib.PqParams(int(num_centroids), int(num_sub_vectors), int(trigger_threshold))
+        _lib.check(_lib.lib().coltt_b200_hnsw_pq_train(self._h, C.byref(pr), int(iterations)))
+
+    def BatchSearchPQ(self, queries, k: int, ef: int = 0, rerank: bool = True):
+        """Hnsw.Search with asymmetric distances over the PQ codes (+ exact re-scoring of the ef survivors)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        if q.shape[1] != self.Dim():
+            raise ValueError("Dim Length UnmatchdError: expect dimension: [%d], but got [%d]" % (self.Dim(), q.shape[1]))
+        nq = q.shape[0]
+        ids = np.zeros((nq, max(k, 1)), dtype=np.uint64)
+        sc = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.int32)
+        _lib.check(_lib.lib().coltt_b200_hnsw_pq_search(self._h, q.ctypes.data_as(_f32p), nq, int(k), int(ef), 1 if rerank else 0,
+                                                         ids.ctypes.data_as(_u64p), sc.ctypes.data_as(_f32p), cnt.ctypes.data_as(_i32p)))
+        return ids, sc, cnt
+
     def Search(self, query, k: int, ef: int = 0) -> List[SearchResultItem]:
         """Hnsw.Search(ctx, query, k): nearest first, ascending Score (hnsw.go:268-275)."""
         ids, sc, cnt = self.BatchSearch(np.asarray(query, dtype=np.float32).reshape(1, -1), k, ef)

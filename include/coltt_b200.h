@@ -230,6 +230,24 @@ COLTT_API int coltt_b200_hnsw_build_stats(coltt_hnsw* h, double* ms4, uint64_t* 
 /* [0] construction searches served by the tensor-core filter, [1] of those re-run exactly (margin not certified). */
 COLTT_API int coltt_b200_hnsw_build_fast_stats(coltt_hnsw* h, uint64_t* out2);
 
+/* ---- product quantization for the HNSW walk (BASELINE config 5) ------------------------------------------------------------
+ * PARITY UNPINNED: the reference holds no PQ arithmetic (pkg/distancepq is dead code without any quantizer, pkg/hnswpq is
+ * absent — SURVEY F5).  The parameters are the reference's ProductQuantizerParameters (pkg/models/hnsw_common.go:20-32):
+ * NumCentroids in [2, 256], NumSubVectors >= 2 dividing the dimension, TriggerThreshold = rows the quantizer trains on
+ * (sampled at a fixed stride; any value >= NumCentroids is accepted here).  Training is a Lloyd k-means per sub-vector on
+ * the GPU; every vertex is then encoded as NumSubVectors code bytes. */
+typedef struct coltt_pq_params {
+  int32_t num_centroids;
+  int32_t num_sub_vectors;
+  int32_t trigger_threshold;
+} coltt_pq_params;
+COLTT_API int coltt_b200_hnsw_pq_train(coltt_hnsw* h, const coltt_pq_params* p, int iterations /* <= 0: 12 */);
+/* Hnsw.Search with asymmetric distance computation over the codes (64 B per neighbour at dim 768 / 64 sub-vectors instead
+ * of a 3 KB row).  rerank != 0: the ef survivors are re-scored with the reference's exact fp32 arithmetic, so returned
+ * scores are true distances; rerank == 0: scores are the quantized estimates.  Judged on recall, not on bit parity. */
+COLTT_API int coltt_b200_hnsw_pq_search(coltt_hnsw* h, const float* queries, size_t nq, int k, int ef, int rerank, uint64_t* out_ids,
+                                        float* out_scores, int32_t* out_counts);
+
 /* ---- sharded collections: one shard per GPU, ONE NCCL all-gather of per-shard top-k, merge ---------------
  * Reference analogue: the 16 in-process shards of a vectorspace, each scanned into a shard-local queue and re-merged
  * (edge/none_vectorstore.go:152-178); rows -> shard by ShardVertex(id, 16) mod n_gpus (pkg/sharding/shard.go:34-41; the
