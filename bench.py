@@ -39,9 +39,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "c4"],
+    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "c4", "c5"],
                     help="flat = BASELINE configs[1] (the headline, default); hnsw = configs[2] (core/vectorindex HNSW, one GPU); "
-                         "c4 = configs[3] (edge FLAT fp8 cosine dim=1536 N=10M/shard batch=1024 top-100, E4M3 store)")
+                         "c4 = configs[3] (edge FLAT fp8 cosine dim=1536 N=10M/shard batch=1024 top-100, E4M3 store); "
+                         "c5 = configs[4] (HNSW + PQ dim=768 N=10M efSearch=256 sharded 4 GPUs: 2.5M vertices per GPU)")
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--dim", type=int, default=None)
@@ -57,6 +58,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / recall legs (profiling runs)")
     a = ap.parse_args()
     wl = WORKLOADS["flat" if a.workload == "hnsw" else a.workload]
+    if a.workload == "c5" and a.ef == 128:
+        a.ef = 256
     for key in ("rows", "dim", "batch", "k", "steps", "warmup", "quant"):
         if getattr(a, key) is None:
             setattr(a, key, wl[key])
@@ -71,6 +74,9 @@ WORKLOADS = {
     "c4": dict(rows=10_000_000, dim=1536, batch=1024, k=100, steps=20, warmup=3, quant="f8_e4m3", es=1, device_gen=True,
                name="edge FLAT f8 (E4M3 store) cosine dim=1536 N=10M/GPU batch=1024 top-100 (BASELINE configs[3])",
                dtype="e4m3 rows/queries, f32 accumulate", metric="QPS @ recall@100, dim=1536, 10M vecs/shard"),
+    "c5": dict(rows=2_500_000, dim=768, batch=1024, k=10, steps=10, warmup=3, quant="pq", es=1, device_gen=False,
+               name="HNSW + PQ (64 sub-vectors x 256 centroids) cosine dim=768 N=10M over 4 GPUs (2.5M/GPU) efSearch=256 top-10 (BASELINE configs[4])",
+               dtype="u8 PQ codes (ADC, f32 tables) + f32 exact re-rank", metric="QPS @ recall@10, dim=768, HNSW+PQ, 2.5M vecs/shard"),
 }
 
 
@@ -622,6 +628,110 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
     return line
 
 
+def c5_arm(args, wl, torch, dist, world, rank, local):
+    """BASELINE configs[4]: HNSW + PQ, dim 768, efSearch 256, one independent sub-graph per GPU over its row shard,
+    product-quantized walk (csrc/pq.cu) + exact re-rank of the ef survivors, ONE all-gather of per-shard top-k + merge through
+    the C-ABI communicator.  PARITY UNPINNED (the reference has no PQ arithmetic): judged on recall@10 against exact search
+    over the union of the shards.  A step = one batch through coltt_b200_sharded_hnsw_pq_search (host buffers)."""
+    import coltt_b200 as cb
+    from coltt_b200 import _lib
+    from coltt_b200.dist import Comm
+    L = _lib.lib()
+    dev = torch.device("cuda", local)
+    n, d, k, ef, nq = args.rows, args.dim, args.k, args.ef, args.batch
+    t0 = time.perf_counter()
+    rows = latent_rows(n, d, BASE_SEED + rank)
+    ids = (np.arange(n, dtype=np.uint64) + np.uint64(1)) + (np.uint64(rank) << np.uint64(40))
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    h = cb.Hnsw.Build(ids, rows, metric=cb.Distance_Cosine, m=16, ef=ef, device=local)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    h.TrainPQ(num_centroids=256, num_sub_vectors=64, trigger_threshold=65536)
+    t_pq = time.perf_counter() - t0
+    comm = Comm.from_torch_distributed(local)
+    qsets = [latent_rows(nq, d, QUERY_SEED + i) for i in range(4)]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+
+    for i in range(args.warmup):
+        comm.hnsw_search(h, qsets[i % 4], k, ef, pq=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.coltt_b200_kernel_launches()
+    kern, evals, exps = [], 0, 0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        gi, gs, gc = comm.hnsw_search(h, qsets[i % 4], k, ef, pq=True)
+        st = h.last_stats()
+        kern.append(st["kernel_ms"]); evals += st["dist_evals"]; exps += st["expansions"]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = L.coltt_b200_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([wall], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    # ---- recall@10 against exact search over the union: per-shard exact fp32 top-k, merged on the host of rank 0
+    rq = min(64, nq)
+    gi, gs, gc = comm.hnsw_search(h, qsets[0], k, ef, pq=True)
+    fi, _, _ = comm.hnsw_search(h, qsets[0], k, ef, pq=False)            # the fp32 walk over the same sub-graphs, for comparison
+    sp = cb.VectorSpace("gt", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_None), device=local, capacity_hint=n, select_mode=cb.SELECT_NEAREST)
+    sp.ChangedVertices(ids, rows)
+    wi, ws, _ = sp.BatchVertexSearch(qsets[0][:rq], k, math_mode=cb.MATH_EXACT)
+    sp.close()
+    loc = torch.from_numpy(np.concatenate([wi.view(np.int64).astype(np.float64), ws.astype(np.float64)], axis=1)).to(dev)
+    if dist is not None:
+        allp = [torch.zeros_like(loc) for _ in range(world)] if rank == 0 else None
+        dist.gather(loc, allp, dst=0)
+    else:
+        allp = [loc]
+    if comm is not None:
+        comm.close()
+    if rank != 0:
+        h.close()
+        return None
+    rec_pq, rec_f32 = [], []
+    for j in range(rq):
+        cid = np.concatenate([a[j, :k].cpu().numpy().astype(np.int64).view(np.uint64) for a in allp])
+        csc = np.concatenate([a[j, k:].cpu().numpy() for a in allp])
+        truth = cid[np.lexsort((cid, csc))[:k]]
+        rec_pq.append(len(np.intersect1d(truth, gi[j, :k])) / k)
+        rec_f32.append(len(np.intersect1d(truth, fi[j, :k])) / k)
+    kern_ms = float(np.mean(kern))
+    peaks = measured_peaks()
+    M = 64
+    alg = (evals * M + exps * 32 * 4 + args.steps * nq * ef * (d * 4 + 8)) / args.steps        # codes + lists + re-ranked rows, per batch (this rank)
+    roof = {"bound": "hbm", "achieved": alg / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+            "kernel": "pq_search_kernel + pq_finish_kernel", "algorithmic_bytes": alg, "kernel_ms": kern_ms, "peak_source": peaks["src"],
+            "note": "latency-bound graph walk: E x 64 B code gathers + X x 128 B lists + ef x 3 KB re-ranked rows per query (SURVEY 8d: bytes = E x M)"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    qps = nq * args.steps / wall
+    unit = "queries/s" if world == 1 else "shard-queries/s"
+    line = {"metric": wl["metric"], "value": world * qps, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"],
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "rows_per_gpu": n, "dim": d, "batch": nq, "k": k, "ef": ef, "pq": "64 sub-vectors x 256 centroids, 65536 training rows",
+                       "data_model": "32-d latent + 10% noise", "gen_s": round(t_gen, 1), "build_s": round(t_build, 1), "pq_train_encode_s": round(t_pq, 2),
+                       "parallelism": f"shard{world}", "code_evals_per_query": evals / (args.steps * nq), "expansions_per_query": exps / (args.steps * nq),
+                       "unit_note": "weak scaling (rows_per_gpu per rank); value counts (query x shard) units, global_qps is queries/s over the union"},
+            "global_qps": qps, "global_rows": world * n,
+            "e2e": {"value": world * qps, "unit": unit, "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 16 + nq * 4,
+                    "note": "value is already end to end (host buffers through the C-ABI)", "global_qps": qps},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+            "recall_at_10": float(np.mean(rec_pq)), "recall_at_10_fp32_walk": float(np.mean(rec_f32)),
+            "recall_note": f"{rq} queries vs exact fp32 search over the union of the {world} shards; parity unpinned (builder-defined PQ, SURVEY F5)"}
+    h.close()
+    return line
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -647,6 +757,13 @@ def main():
     assert _lib.lib().coltt_b200_device_count() >= 1, "no sm_100 GPU: coltt_b200 has no CPU fallback"
 
     wl = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        line = c5_arm(args, wl, torch, dist, world, rank, local)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     line = flat_arm(args, wl, torch, dist, world, rank, local)
     # The default line also carries compact records of configs[2] (HNSW) and configs[3] (fp8, top-100, batch 1024) on this
     # GPU, so that they are driver-run numbers; time-boxed, N=1 only.

@@ -32,6 +32,8 @@ namespace coltt {
 
 int hnsw_search_keep_device(Hnsw* h, const float* queries, size_t nq, int k, int ef, const Hit** d_hits, const int** d_counts,
                             cudaStream_t* st);   // hnsw.cu
+int hnsw_pq_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_in, int rerank, uint64_t* out_ids, float* out_scores,
+                   int32_t* out_counts);         // pq.cu
 
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -176,7 +178,8 @@ static int sharded_search_host(Comm& cm, Store* shard, const float* queries, siz
 }
 
 // HNSW shards: one independent sub-graph per GPU over its row shard; the same all-gather + merge (nearest first).
-static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq, int k, int ef, uint64_t* out_ids, float* out_scores,
+// pq: 0 = fp32 walk (hnsw.cu), 1 = PQ walk + exact re-rank, 2 = PQ walk, quantized scores (pq.cu)
+static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq, int k, int ef, int pq, uint64_t* out_ids, float* out_scores,
                              int32_t* out_counts) {
   if (nq == 0) return COLTT_OK;
   if (!queries || k <= 0) return fail(COLTT_ERR_INVALID, "bad argument");
@@ -187,8 +190,18 @@ static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq,
   int rc;
   if ((rc = ensure_bufs(cm, nq, k)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_out.ensure(hb + nq * 4))) return rc;
   const Hit* d_hits = nullptr; const int* d_cnt = nullptr; cudaStream_t hst = nullptr;
-  rc = hnsw_search_keep_device(h, queries, nq, k, ef, &d_hits, &d_cnt, &hst);     // returns after the walk finished
-  if (rc) return rc;
+  if (pq) {
+    std::vector<uint64_t> ti(nq * (size_t)k);
+    std::vector<float> ts(nq * (size_t)k);
+    std::vector<int32_t> tc(nq);
+    rc = hnsw_pq_search(h, queries, nq, k, ef, pq == 1, ti.data(), ts.data(), tc.data());   // the hits also stay in the handle's scratch
+    if (rc) return rc;
+    if (h->n == 0) return fail(COLTT_ERR_UNSUPPORTED, "empty sub-graph in a sharded PQ search");
+    d_hits = (const Hit*)h->out.p; d_cnt = (const int*)h->counts.p;
+  } else {
+    rc = hnsw_search_keep_device(h, queries, nq, k, ef, &d_hits, &d_cnt, &hst);     // returns after the walk finished
+    if (rc) return rc;
+  }
   COLTT_CUDA(cudaMemcpyAsync(cm.send.p, d_hits, hb, cudaMemcpyDeviceToDevice, cm.stream));
   COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.send.p + hb, d_cnt, nq * 4, cudaMemcpyDeviceToDevice, cm.stream));
   rc = exchange_and_merge(cm, nq, k, 1, (Hit*)cm.out.p, (int*)cm.counts.p, cm.stream);
@@ -329,8 +342,15 @@ COLTT_API int coltt_b200_sharded_search_all(coltt_comm* const* comms, coltt_stor
 COLTT_API int coltt_b200_sharded_hnsw_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef, uint64_t* out_ids,
                                              float* out_scores, int32_t* out_counts) {
   if (!c || !sub) return fail(COLTT_ERR_INVALID, "null handle");
-  return coltt::sharded_hnsw_host(*reinterpret_cast<Comm*>(c), reinterpret_cast<coltt::Hnsw*>(sub), queries, nq, k, ef, out_ids, out_scores,
+  return coltt::sharded_hnsw_host(*reinterpret_cast<Comm*>(c), reinterpret_cast<coltt::Hnsw*>(sub), queries, nq, k, ef, 0, out_ids, out_scores,
                                   out_counts);
+}
+
+COLTT_API int coltt_b200_sharded_hnsw_pq_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef, int rerank,
+                                                uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
+  if (!c || !sub) return fail(COLTT_ERR_INVALID, "null handle");
+  return coltt::sharded_hnsw_host(*reinterpret_cast<Comm*>(c), reinterpret_cast<coltt::Hnsw*>(sub), queries, nq, k, ef, rerank ? 1 : 2, out_ids,
+                                  out_scores, out_counts);
 }
 
 }  // extern "C"

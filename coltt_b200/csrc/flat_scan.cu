@@ -282,9 +282,10 @@ int plan_flat_scan(int elem, uint32_t dim, uint32_t row_stride, uint32_t n_items
   if (nq == 0) return fail(COLTT_ERR_INVALID, "no queries");
   const uint32_t q_stride = (dim + 7) / 8 * 8;
   int qt = nq == 1 ? 1 : (nq <= 4 ? 4 : 8);
-  // experimental (COLTT_SCAN_CTAS=2, default 1): two resident CTAs per SM with half-depth rings — the fp16 scan is
-  // issue-bound at 2 warps per scheduler (profiles/r1_flat_scan_rerank_summary.md); not validated on a GPU yet
-  static const int env_ctas = [] { const char* e = getenv("COLTT_SCAN_CTAS"); const int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();
+  // Two resident CTAs per SM with half-depth rings: measured on B200 (profiles/r2_k1_shapes.md) it lifts the one-query fp16
+  // scan from 0.62 to 0.70 of the HBM roofline (the kernel is latency-bound at 2 warps per scheduler) but slows every other
+  // shape (fp32 / f8 rows, 8-query groups: more per-CTA lists to merge, shallower rings), so it is used for that shape only.
+  const int env_ctas = (elem == ELEM_F16 && nq == 1) ? 2 : 1;
   auto q_bytes = [&](int q) { return (size_t)q * q_stride * 4 + 32; };
   while (qt > 1 && q_bytes(qt) > 96 * 1024) qt = qt == 8 ? 4 : 1;
   if (q_bytes(qt) > 160 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "dim too large for the scan kernel");

@@ -177,8 +177,8 @@ class Comm:
         _lib.check(_lib.lib().coltt_b200_sharded_search_dev(self._h, space._h, d_queries_ptr, nq, k, select_mode, math_mode, d_out_ptr,
                                                             d_counts_ptr, stream_ptr))
 
-    def hnsw_search(self, sub_graph, queries, k: int, ef: int = 0):
-        """Collective Hnsw.Search over one sub-graph per GPU."""
+    def hnsw_search(self, sub_graph, queries, k: int, ef: int = 0, pq: bool = False, rerank: bool = True):
+        """Collective Hnsw.Search over one sub-graph per GPU; pq = the product-quantized walk (config 5)."""
         import ctypes as C
         from . import _lib
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -187,9 +187,12 @@ class Comm:
         ids = np.zeros((nq, k), np.uint64)
         sc = np.zeros((nq, k), np.float32)
         cnt = np.zeros(nq, np.int32)
-        _lib.check(_lib.lib().coltt_b200_sharded_hnsw_search(self._h, sub_graph._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, ef,
-                                                             ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)),
-                                                             cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        L = _lib.lib()
+        outs = (ids.ctypes.data_as(C.POINTER(C.c_uint64)), sc.ctypes.data_as(C.POINTER(C.c_float)), cnt.ctypes.data_as(C.POINTER(C.c_int32)))
+        if pq:
+            _lib.check(L.coltt_b200_sharded_hnsw_pq_search(self._h, sub_graph._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, ef, 1 if rerank else 0, *outs))
+        else:
+            _lib.check(L.coltt_b200_sharded_hnsw_search(self._h, sub_graph._h, q.ctypes.data_as(C.POINTER(C.c_float)), nq, k, ef, *outs))
         return ids, sc, cnt
 
 

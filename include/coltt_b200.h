@@ -280,6 +280,9 @@ COLTT_API int coltt_b200_sharded_search_all(coltt_comm* const* comms, coltt_stor
  * merge nearest-first.  Collective like coltt_b200_sharded_search. */
 COLTT_API int coltt_b200_sharded_hnsw_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef,
                                              uint64_t* out_ids, float* out_scores, int32_t* out_counts);
+/* The same with the product-quantized walk of every sub-graph (coltt_b200_hnsw_pq_search): BASELINE config 5. */
+COLTT_API int coltt_b200_sharded_hnsw_pq_search(coltt_comm* c, coltt_hnsw* sub, const float* queries, size_t nq, int k, int ef, int rerank,
+                                                uint64_t* out_ids, float* out_scores, int32_t* out_counts);
 
 /* ---- timing (replaces pprof for this path) ---------------------------------
  * Device time in milliseconds of the kernels of the last search on this handle, measured
