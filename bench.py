@@ -144,11 +144,14 @@ class ClockSampler:
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        return json.load(open(p)).get(kernel)
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+        except Exception:
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 def measured_peaks():
