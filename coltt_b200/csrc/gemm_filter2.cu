@@ -93,6 +93,9 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     if (do_pf && pair < n_tiles && elect_one())
       for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)((st * SB) >> p.tma_shift), (int)(pair * kBN) + row_off);
     __syncwarp();
+#if COLTT_K2_PROF
+    if (p.dbg_flags & 4u) goto producer_done;               // probe: MMA cadence without any TMA traffic (operands = whatever is in smem)
+#endif
     for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
       const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
       const bool pf = do_pf && t + n_pairs < n_tiles;
@@ -108,6 +111,9 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
+#if COLTT_K2_PROF
+  producer_done:;
+#endif
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     // This loop is the single-thread critical path of the kernel: ring position, phase and both operand
@@ -131,14 +137,23 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         uint64_t a_desc = a_desc0;                           // (start address >> 4) lives in the low 14 bits
         for (uint32_t st = 0; st < NSTEP; st++) {
           const long long c1 = K2_NOW();
+#if COLTT_K2_PROF
+          if (!(p.dbg_flags & 4u))
+#endif
           mbar_wait(full0 + s * 8, ph);
           w_full += K2_NOW() - c1;
           tc_fence_after();
           const uint64_t b_desc = b_desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
           if (elect_one()) {
+#if COLTT_K2_PROF
+            if (!(p.dbg_flags & 8u)) {                         // probe bit 3: TMA streaming speed without any MMA
+#endif
             umma_ss_pair<FP8>(d_tmem, a_desc, b_desc, idesc, st != 0 ? 1u : 0u);
 #pragma unroll
             for (uint32_t m = 1; m < MPS; m++) umma_ss_pair<FP8>(d_tmem, a_desc + 2 * m, b_desc + 2 * m, idesc, 1u);   // +32 B of K each
+#if COLTT_K2_PROF
+            }
+#endif
             umma_commit_pair(empty0 + s * 8, 3);             // stage free in both CTAs
           }
           __syncwarp();

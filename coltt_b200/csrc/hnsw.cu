@@ -874,15 +874,16 @@ int hnsw_load(const void* blob, size_t len, int device, Hnsw** out) {
 
 
 static int launch_hnsw_search(int metric, int R, const HnswParams& p, unsigned n_ctas, size_t smem, cudaStream_t st) {
-  if (p.ring_cb) {   // experimental dim-chunk ring (COLTT_HNSW_RING), register result set only
+  if (p.ring_cb) {   // dim-chunk ring staging (the default for wide rows), register result set only
 #define COLTT_HNSW_RING_CASE(M, RR)                                                          \
   if (metric == M && R == RR) {                                                              \
     int arc = kernel_attrs(hnsw_search_kernel<M, RR, true>, smem);                           \
     if (arc) return arc;                                                                     \
     hnsw_search_kernel<M, RR, true><<<n_ctas, kHnswThreads, smem, st>>>(p);                  \
   } else
-    COLTT_HNSW_RING_CASE(COLTT_COSINE, 4) COLTT_HNSW_RING_CASE(COLTT_EUCLIDEAN, 4)
-    return fail(COLTT_ERR_UNSUPPORTED, "COLTT_HNSW_RING serves 64 < ef <= 128 only");
+    COLTT_HNSW_RING_CASE(COLTT_COSINE, 2) COLTT_HNSW_RING_CASE(COLTT_COSINE, 4) COLTT_HNSW_RING_CASE(COLTT_COSINE, 8)
+    COLTT_HNSW_RING_CASE(COLTT_EUCLIDEAN, 2) COLTT_HNSW_RING_CASE(COLTT_EUCLIDEAN, 4) COLTT_HNSW_RING_CASE(COLTT_EUCLIDEAN, 8)
+    return fail(COLTT_ERR_UNSUPPORTED, "ring staging needs the register result set (ef <= 256)");
 #undef COLTT_HNSW_RING_CASE
     count_launch();
     COLTT_CUDA(cudaGetLastError());
@@ -924,8 +925,11 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   static const int env_chunk = getenv("COLTT_HNSW_CHUNK") ? atoi(getenv("COLTT_HNSW_CHUNK")) : 0;
   static const int env_ctas = getenv("COLTT_HNSW_CTAS") ? atoi(getenv("COLTT_HNSW_CTAS")) : 0;
   static const int env_literal = getenv("COLTT_HNSW_LITERAL") ? atoi(getenv("COLTT_HNSW_LITERAL")) : 0;
-  // experimental: COLTT_HNSW_RING="<chunk bytes>,<stages>" (e.g. "512,2") stages rows through per-warp dim-chunk rings
-  static const char* env_ring = getenv("COLTT_HNSW_RING");
+  // Rows are staged through per-warp rings of dim-chunks ("<chunk bytes>,<stages>", default 512,2 for rows of 1 KB and more;
+  // COLTT_HNSW_RING=0 selects whole-row staging): a CTA then needs ~50 KB of shared memory instead of ~100 KB at dim 768, four
+  // queries are resident per SM instead of two, and the walk — latency bound — gains 23 % (profiles/r2_hnsw_summary.md).
+  static const char* env_ring_raw = getenv("COLTT_HNSW_RING");
+  const char* env_ring = env_ring_raw ? env_ring_raw : (h->row_stride >= 1024 ? "512,2" : nullptr);
   int R = env_literal ? 0 : ef <= 64 ? 2 : ef <= 128 ? 4 : ef <= 256 ? 8 : 0;
   uint32_t cand_cap = kCandCapMin;
   while (cand_cap < 8 * ef && cand_cap < kCandCapMax) cand_cap *= 2;
@@ -949,16 +953,18 @@ static int hnsw_search(Hnsw* h, const float* queries, size_t nq, int k, int ef_i
   };
   if (!plan(cand_cap, nq)) return fail(COLTT_ERR_UNSUPPORTED, "ef/dim too large for the HNSW kernel's shared memory");
   uint32_t ring_cb = 0, ring_cs = 0, ring_stages = 0;
-  if (env_ring && R == 4) {
+  if (env_ring && R > 0) {
     unsigned cb = 0, stg = 0;
     if (sscanf(env_ring, "%u,%u", &cb, &stg) == 2 && cb >= 32 && cb % 32 == 0 && stg >= 2 && stg <= kRingMaxStages) {
-      ring_cb = std::min<uint32_t>(cb, (h->row_stride + 31) / 32 * 32);
-      ring_cs = (ring_cb + 127) / 128 * 128 + 32;
-      ring_stages = stg;
+      const uint32_t r_cb = std::min<uint32_t>(cb, (h->row_stride + 31) / 32 * 32);
+      const uint32_t r_cs = (r_cb + 127) / 128 * 128 + 32;
       const size_t fixed = (size_t)q_stride * 4 + (size_t)cand_cap * 8 + (size_t)(ef + 1) * 8 + kHnswChunkMax * 8;
-      chunk_rows = kHnswChunkMax;                 // the rows region is chunk_rows * rs bytes: 32 rows x stages x ring_cs
-      smem = fixed + (size_t)kHnswChunkMax * ring_stages * ring_cs;
-      if (smem > 200 * 1024) ring_cb = 0;
+      const size_t r_smem = fixed + (size_t)kHnswChunkMax * stg * r_cs;
+      if (r_smem <= 200 * 1024) {
+        ring_cb = r_cb; ring_cs = r_cs; ring_stages = stg;
+        chunk_rows = kHnswChunkMax;               // the rows region is chunk_rows * rs bytes: 32 rows x stages x ring_cs
+        smem = r_smem;
+      }
     }
   }
   const uint32_t words = (h->n + 31) / 32;
