@@ -93,10 +93,29 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     if (do_pf && pair < n_tiles && elect_one())
       for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)((st * SB) >> p.tma_shift), (int)(pair * kBN) + row_off);
     __syncwarp();
+    // Batches of more than 256 queries run gridDim.y query-tile groups side by side; pair p of every group walks the SAME
+    // tiles in the same order, so a tile fetched from HBM by one group is an L2 hit for the others — as long as the groups
+    // stay within L2's retention of one another (a few tens of tile steps).  Left alone they drift (SMs differ in their
+    // distance to the L2 slices) and ncu showed 1.9 HBM passes per batch; so the leaders keep a window: a group does not
+    // start tile step i before every group has started step i - kLockWindow.
+    constexpr uint32_t kLockWindow = 4;
+    const bool lockstep = gridDim.y > 1 && rank == 0;
+    uint32_t ti_p = 0;
 #if COLTT_K2_PROF
-    if (p.dbg_flags & 4u) goto producer_done;               // probe: MMA cadence without any TMA traffic (operands = whatever is in smem)
+    const uint32_t t_first = (p.dbg_flags & 4u) ? n_tiles : pair;   // probe bit 2: MMA cadence without any TMA traffic (operands = whatever is in smem)
+#else
+    const uint32_t t_first = pair;
 #endif
-    for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+    for (uint32_t t = t_first; t < n_tiles; t += n_pairs, ti_p++) {
+      if (lockstep) {
+        if (lane == 0) {
+          *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.y * n_pairs + pair) = ti_p + 1;
+          if (ti_p >= kLockWindow)
+            for (uint32_t g = 0; g < gridDim.y; g++)
+              while (*reinterpret_cast<volatile uint32_t*>(p.progress + g * n_pairs + pair) + kLockWindow < ti_p + 1) __nanosleep(100);
+        }
+        __syncwarp();
+      }
       const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
       const bool pf = do_pf && t + n_pairs < n_tiles;
       for (uint32_t st = 0; st < NSTEP; st++) {
@@ -111,9 +130,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
-#if COLTT_K2_PROF
-  producer_done:;
-#endif
+    if (lockstep && lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.y * n_pairs + pair) = 0xfffffff0u;   // finished: nobody waits for us
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     // This loop is the single-thread critical path of the kernel: ring position, phase and both operand
@@ -135,6 +152,37 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kBN;
         uint64_t a_desc = a_desc0;                           // (start address >> 4) lives in the low 14 bits
+        if (SB == 64 && NS == 4 && (NSTEP & 3u) == 0) {
+          // Fast issue loop (the configuration every wide-row shape runs: 4 x 8 KB stages).  The probes of round 2
+          // (profiles/r2_k2_probes.md) showed that THIS loop, not the tensor pipe or the TMA stream, set the kernel's pace:
+          // ~145 busy cycles per MMA on the issuing thread against the 128-cycle math floor.  So: the ring position is a
+          // compile-time constant inside a 4-stage group (barrier addresses and B descriptors become immediates, one phase
+          // flip per group), and the "stage full?" answer for stage u+1 is REQUESTED (mbarrier.test_wait, non-blocking)
+          // before the MMAs of stage u are issued and only consumed after them, which takes the ~90-cycle probe latency
+          // off the critical path; the blocking wait remains as the fallback when the answer is "not yet".
+          constexpr uint64_t ABLK16 = ABLK_BYTES >> 4;
+          bool ready = mbar_test_wait(full0, ph);
+          for (uint32_t st = 0; st < NSTEP; st += 4) {
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+              if (!ready) mbar_wait(full0 + u * 8, ph);
+              // probe the next stage now (next group's first stage has the flipped phase)
+              const bool last_of_tile = st + 4 >= NSTEP && u == 3;
+              ready = last_of_tile ? mbar_test_wait(full0, ph ^ 1) : mbar_test_wait(full0 + ((u + 1) & 3) * 8, u == 3 ? ph ^ 1 : ph);
+              tc_fence_after();
+              const uint64_t ad = a_desc + (u >> 1) * ABLK16 + (u & 1) * 4;       // K blocks of 128 B, two 64-byte stages each
+              const uint64_t bd = b_desc0 + (uint64_t)(u * (STAGE_BYTES >> 4));
+              if (elect_one()) {
+                umma_ss_pair<FP8>(d_tmem, ad, bd, idesc, (st | u) != 0 ? 1u : 0u);
+                umma_ss_pair<FP8>(d_tmem, ad + 2, bd + 2, idesc, 1u);             // +32 B of K
+                umma_commit_pair(empty0 + u * 8, 3);                               // stage free in both CTAs
+              }
+              __syncwarp();
+            }
+            a_desc += 2 * ABLK16;
+            ph ^= 1;
+          }
+        } else {
         for (uint32_t st = 0; st < NSTEP; st++) {
           const long long c1 = K2_NOW();
 #if COLTT_K2_PROF
@@ -160,6 +208,7 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
           if (SB == 128) a_desc += (uint64_t)(ABLK_BYTES >> 4);              // one whole K block per stage
           else a_desc += (st & 1) ? (uint64_t)((ABLK_BYTES - 64) >> 4) : 4ull;    // +64 B inside a K block, then the next block
           if (++s == NS) { s = 0; ph ^= 1; }
+        }
         }
         if (elect_one()) umma_commit_pair(smem_u32(tfull_bar + buf), 3);   // accumulator ready in both CTAs
         __syncwarp();

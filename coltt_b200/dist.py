@@ -86,32 +86,42 @@ def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, st
     dev = torch.device("cuda", device_index)
     mm = space.math_mode if math_mode is None else math_mode
 
-    def _stream_ptr():
-        return (stream or torch.cuda.current_stream(dev)).cuda_stream
+    # The library must be handed a REAL stream: pointer 0 means "use your own private stream", which is not ordered with
+    # torch's legacy default stream — the copies that produce `q` (and any fill of the outputs) could still be in flight when
+    # the library's kernels start.  So the calls run on a side stream that is made to wait for torch's current stream, and
+    # torch's current stream waits for it afterwards.
+    side = stream or torch.cuda.Stream(device=dev)
+
+    def _ordered(fn):
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)
+        fn(side.cuda_stream)
+        cur.wait_stream(side)
 
     def local_search(queries, k, select_mode):
         q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries, np.float32))
         q = q.to(dev, dtype=torch.float32).contiguous()
         nq = q.shape[0]
-        hits = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
-        counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
-        _lib.check(L.coltt_b200_store_search_dev(space._h, q.data_ptr(), nq, k, select_mode, mm, hits.data_ptr(), counts.data_ptr(),
-                                                  _stream_ptr()))
+        hits = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
+        counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+        _ordered(lambda sp: _lib.check(L.coltt_b200_store_search_dev(space._h, q.data_ptr(), nq, k, select_mode, mm, hits.data_ptr(),
+                                                                     counts.data_ptr(), sp)))
+        q.record_stream(side)
         return hits, counts
 
     def merge(gathered, gcounts, k, select_mode):
         world, nq = gathered.shape[0], gathered.shape[1]
-        out = torch.zeros((nq, k, 4), dtype=torch.int32, device=dev)
-        cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        out = torch.empty((nq, k, 4), dtype=torch.int32, device=dev)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
         if gathered.is_contiguous() and gcounts.is_contiguous():
-            _lib.check(L.coltt_b200_merge_topk_dev(device_index, gathered.data_ptr(), gcounts.data_ptr(), world, nq, gathered.shape[2], k,
-                                                    select_mode, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
+            _ordered(lambda sp: _lib.check(L.coltt_b200_merge_topk_dev(device_index, gathered.data_ptr(), gcounts.data_ptr(), world, nq,
+                                                                       gathered.shape[2], k, select_mode, out.data_ptr(), cnt.data_ptr(), sp)))
         else:   # strided views of the packed all-gather buffer: one block per shard, hits then counts
             stride_b = gathered.stride(0) * 4
             off_b = gcounts.data_ptr() - gathered.data_ptr()
             assert gcounts.stride(0) * 4 == stride_b and off_b > 0
-            _lib.check(L.coltt_b200_merge_topk_dev2(device_index, gathered.data_ptr(), world, nq, gathered.shape[2], k, select_mode,
-                                                     stride_b, off_b, out.data_ptr(), cnt.data_ptr(), _stream_ptr()))
+            _ordered(lambda sp: _lib.check(L.coltt_b200_merge_topk_dev2(device_index, gathered.data_ptr(), world, nq, gathered.shape[2], k,
+                                                                        select_mode, stride_b, off_b, out.data_ptr(), cnt.data_ptr(), sp)))
         return out, cnt
 
     return local_search, merge

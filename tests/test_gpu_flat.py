@@ -293,3 +293,38 @@ def test_config4_shape_f8_dim1536_top100_batched_and_sharded(cb, oracle):
             assert_same_hits(mi[order], ms[order], wi, ws, f"c4 sharded mode={mode} q{j}")
     for p in parts + [sp]:
         p.close()
+
+
+def test_mutations_wait_for_an_asynchronous_search(cb, oracle):
+    """coltt_b200_store_search_dev with a caller stream only enqueues and returns.  An upsert / remove issued right after it
+    edits rows, norms and ids in place on the store's own stream, so it must first wait for the outstanding search
+    (Store::wait_for_searches): the search has to see the collection as it was when it was called."""
+    import ctypes as C
+    import torch
+    from coltt_b200 import _lib
+    L = _lib.lib()
+    n, d, k, nq = 200_000, 256, 10, 64
+    ids, vecs = sparse_ids(n), normal(n, d)
+    sp = cb.VectorSpace("race", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_None))
+    sp.ChangedVertices(ids, vecs)
+    st = oracle.FlatStore(d, oracle.COSINE, oracle.Q_NONE)
+    st.upsert(ids, vecs)
+    qs = normal(nq, d, QUERY_SEED)
+    q = torch.from_numpy(qs).cuda()
+    out = torch.empty((nq, k, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for trial in range(3):
+        _lib.check(L.coltt_b200_store_search_dev(sp._h, q.data_ptr(), nq, k, cb.SELECT_NEAREST, cb.MATH_EXACT, out.data_ptr(), cnt.data_ptr(),
+                                                  stream.cuda_stream))          # 8 exact passes over 200 MB: still running when we return
+        sp.ChangedVertices(ids[:60_000], normal(60_000, d, 100 + trial))        # overwrite in place
+        sp.RemoveVertex(ids[100_000:160_000])                                   # move tail rows into the holes
+        stream.synchronize()
+        h = out.cpu().numpy().view(np.uint8).reshape(nq, k, 16)
+        gi, gs = h[..., :8].copy().view(np.uint64)[..., 0], h[..., 8:12].copy().view(np.float32)[..., 0]
+        for j in range(0, nq, 7):
+            wi, ws = st.search_total_order(qs[j], k, select_mode=oracle.NEAREST)
+            assert_same_hits(gi[j], gs[j], wi, ws, f"trial {trial} q{j}: the search saw a half-mutated store")
+        sp.ChangedVertices(ids, vecs)                                            # restore for the next trial
+    sp.close()
