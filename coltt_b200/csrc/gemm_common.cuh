@@ -154,23 +154,32 @@ __device__ __forceinline__ float pick32(const float (&k)[32], uint32_t c) {
   return (c & 1u) ? e[1] : e[0];
 }
 
-// Cross-column bound G of filter_epilogue (see its header comment): reads the n_cols published values of query q.  The loads of
-// one pass (one per class) are issued together BEFORE any of them is consumed: each is an L2 round trip, and a sweep that
-// serialises them (load, max, load, max ...) costs ~100 K cycles — measured: it doubled the kernel time.  Out of line: the
-// epilogue calls it from three places and its body is cold code next to the per-tile hot loop.
+// Cross-column bound G of filter_epilogue (see its header comment): reads published values of query q.  ANY subset of the
+// columns gives a valid bound (fewer vouching columns only make it looser), so a sweep reads at most kSweepCols of them —
+// a window that rotates from sweep to sweep — instead of all n_cols: the epilogue warps do not drain accumulators while
+// they sweep, and the role timers showed the MMA issuer waiting on exactly that (7 sweeps x ~10 K cycles of 148 dependent-
+// latency loads = the whole "waiting for the epilogue" share, 13 % of the kernel).  The loads of one pass (one per class) are
+// issued together BEFORE any of them is consumed: each is an L2 round trip, and a sweep that serialises them (load, max,
+// load, max ...) costs ~100 K cycles — measured: it doubled the kernel time.  Out of line: cold code next to the hot loop.
+static constexpr uint32_t kSweepCols = 32;
 template <int KP>
-__device__ __noinline__ float cross_column_bound(const float* pub, uint32_t nq, uint32_t q, uint32_t col, uint32_t n_cols, uint32_t groups) {
+__device__ __noinline__ float cross_column_bound(const float* pub, uint32_t nq, uint32_t q, uint32_t col, uint32_t n_cols, uint32_t groups,
+                                                 uint32_t first) {
   const float NEG_INF = __int_as_float(0xff800000);
   float gmax[KP];
 #pragma unroll
   for (int i = 0; i < KP; i++) gmax[i] = NEG_INF;
+  // window of columns [first, first + span) modulo n_cols; span is a multiple of `groups` so every class gets the same share
+  uint32_t span = n_cols < kSweepCols ? n_cols : kSweepCols;
+  if (span > groups) span -= span % groups;
 #pragma unroll 2
-  for (uint32_t c0 = 0; c0 < n_cols; c0 += groups) {
+  for (uint32_t c0 = 0; c0 < span; c0 += groups) {
     float pv[KP];
 #pragma unroll
     for (int i = 0; i < KP; i++) {
-      const uint32_t c = c0 + i;
-      const bool ok = (uint32_t)i < groups && c < n_cols;
+      uint32_t c = first + c0 + i;
+      if (c >= n_cols) c -= n_cols;
+      const bool ok = (uint32_t)i < groups && c0 + i < span;
       pv[i] = __ldcg(pub + (size_t)(ok ? c : col) * nq + q);   // own column when masked: a valid address, value unused
       if (!ok) pv[i] = NEG_INF;
     }
@@ -255,7 +264,12 @@ __device__ __forceinline__ void filter_epilogue(const GemmParams& p, uint32_t tm
     coef_a[idx] = a;
     coef_b[idx] = b;
   };
-  auto sweep = [&]() { thr = fmaxf(thr, cross_column_bound<KP>(p.pub, p.nq, q, col, n_cols, groups)); };
+  uint32_t sweep_first = col % n_cols;     // rotating window start: different columns vouch in different sweeps
+  auto sweep = [&]() {
+    thr = fmaxf(thr, cross_column_bound<KP>(p.pub, p.nq, q, col, n_cols, groups, sweep_first));
+    sweep_first += kSweepCols;
+    if (sweep_first >= n_cols) sweep_first %= n_cols;
+  };
   // ||row||^2 (and the E4M3 row scale) of the next tile are fetched while the current one is processed (one row per epilogue thread)
   float n2_a = 0.0f, sc_a = 1.0f;
   {

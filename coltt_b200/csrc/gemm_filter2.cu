@@ -98,8 +98,8 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     // stay within L2's retention of one another (a few tens of tile steps).  Left alone they drift (SMs differ in their
     // distance to the L2 slices) and ncu showed 1.9 HBM passes per batch; so the leaders keep a window: a group does not
     // start tile step i before every group has started step i - kLockWindow.
-    constexpr uint32_t kLockWindow = 4;
-    const bool lockstep = gridDim.y > 1 && rank == 0;
+    const uint32_t kLockWindow = p.lock_window;
+    const bool lockstep = gridDim.y > 1 && rank == 0 && kLockWindow != 0;
     uint32_t ti_p = 0;
 #if COLTT_K2_PROF
     const uint32_t t_first = (p.dbg_flags & 4u) ? n_tiles : pair;   // probe bit 2: MMA cadence without any TMA traffic (operands = whatever is in smem)
