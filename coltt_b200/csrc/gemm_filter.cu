@@ -319,8 +319,6 @@ int launch_gemm_filter(const GemmParams& p_in, const GemmPlan& plan_in, const vo
   p.rows = static_cast<const uint8_t*>(d_rows);
   p.row_stride = row_stride;
   p.pf_inner = pf_inner;
-  static const uint32_t env_lock = [] { const char* e = getenv("COLTT_LOCK_WINDOW"); return e ? (uint32_t)atoi(e) : 0u; }();
-  p.lock_window = env_lock;
   p.tma_shift = tma_shift;
   p.kblocks = plan.kblocks; p.kprime = plan.kprime; p.cand_cap = plan.cand_cap; p.cand_out_cap = plan.cand_out_cap; p.n_stages = plan.n_stages;
   p.pub_kth = plan.pub_kth; p.groups = plan.groups;

@@ -94,28 +94,16 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
       for (uint32_t st = 0; st < NSTEP; st += pf_mask + 1) tma_prefetch_2d(&tmap_pf, (int)((st * SB) >> p.tma_shift), (int)(pair * kBN) + row_off);
     __syncwarp();
     // Batches of more than 256 queries run gridDim.y query-tile groups side by side; pair p of every group walks the SAME
-    // tiles in the same order, so a tile fetched from HBM by one group is an L2 hit for the others — as long as the groups
-    // stay within L2's retention of one another (a few tens of tile steps).  Left alone they drift (SMs differ in their
-    // distance to the L2 slices) and ncu showed 1.9 HBM passes per batch; so the leaders keep a window: a group does not
-    // start tile step i before every group has started step i - kLockWindow.
-    const uint32_t kLockWindow = p.lock_window;
-    const bool lockstep = gridDim.y > 1 && rank == 0 && kLockWindow != 0;
-    uint32_t ti_p = 0;
+    // tiles in the same order, so a tile fetched from HBM by one group is usually an L2 hit for the others: ncu measures 1.9 HBM
+    // passes per 1024-query batch instead of 4.  Forcing the groups into lock-step (a window of 4 or 8 tile steps on a progress
+    // counter per pair) brought that to 1.13 passes but cost 24 % of the kernel time on the power-capped, tensor-bound config 4
+    // (profiles/r2_gemm_filter_pair_summary.md), so the groups run free.
 #if COLTT_K2_PROF
     const uint32_t t_first = (p.dbg_flags & 4u) ? n_tiles : pair;   // probe bit 2: MMA cadence without any TMA traffic (operands = whatever is in smem)
 #else
     const uint32_t t_first = pair;
 #endif
-    for (uint32_t t = t_first; t < n_tiles; t += n_pairs, ti_p++) {
-      if (lockstep) {
-        if (lane == 0) {
-          *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.y * n_pairs + pair) = ti_p + 1;
-          if (ti_p >= kLockWindow)
-            for (uint32_t g = 0; g < gridDim.y; g++)
-              while (*reinterpret_cast<volatile uint32_t*>(p.progress + g * n_pairs + pair) + kLockWindow < ti_p + 1) __nanosleep(100);
-        }
-        __syncwarp();
-      }
+    for (uint32_t t = t_first; t < n_tiles; t += n_pairs) {
       const int row = (int)(t * kBN) + row_off, row_pf = row + (int)(n_pairs * kBN);
       const bool pf = do_pf && t + n_pairs < n_tiles;
       for (uint32_t st = 0; st < NSTEP; st++) {
@@ -130,7 +118,6 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         if (++s == NS) { s = 0; ph ^= 1; }
       }
     }
-    if (lockstep && lane == 0) *reinterpret_cast<volatile uint32_t*>(p.progress + blockIdx.y * n_pairs + pair) = 0xfffffff0u;   // finished: nobody waits for us
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     // This loop is the single-thread critical path of the kernel: ring position, phase and both operand
@@ -165,6 +152,9 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
           for (uint32_t st = 0; st < NSTEP; st += 4) {
 #pragma unroll
             for (uint32_t u = 0; u < 4; u++) {
+#if COLTT_K2_PROF
+              if (p.dbg_flags & 4u) ready = true;                                  // probe bit 2: no TMA traffic, nothing to wait for
+#endif
               if (!ready) mbar_wait(full0 + u * 8, ph);
               // probe the next stage now (next group's first stage has the flipped phase)
               const bool last_of_tile = st + 4 >= NSTEP && u == 3;
@@ -173,8 +163,14 @@ gemm_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
               const uint64_t ad = a_desc + (u >> 1) * ABLK16 + (u & 1) * 4;       // K blocks of 128 B, two 64-byte stages each
               const uint64_t bd = b_desc0 + (uint64_t)(u * (STAGE_BYTES >> 4));
               if (elect_one()) {
+#if COLTT_K2_PROF
+                if (!(p.dbg_flags & 8u)) {                                         // probe bit 3: the TMA stream without any MMA
+#endif
                 umma_ss_pair<FP8>(d_tmem, ad, bd, idesc, (st | u) != 0 ? 1u : 0u);
                 umma_ss_pair<FP8>(d_tmem, ad + 2, bd + 2, idesc, 1u);             // +32 B of K
+#if COLTT_K2_PROF
+                }
+#endif
                 umma_commit_pair(empty0 + u * 8, 3);                               // stage free in both CTAs
               }
               __syncwarp();

@@ -95,8 +95,6 @@ struct GemmParams {
   uint32_t row_stride;       // bytes
   int metric, nearest;
   uint32_t* g_thr;           // [nq] order-encoded bound the survivors were cut at (max over columns), zero-initialised
-  uint32_t lock_window;      // tile steps a query-tile group may run ahead of the slowest one (0 = no lock-step)
-  uint32_t* progress;        // [grid_y][pairs] tiles each (query group, pair) has issued, zero-initialised (lock-step window, gemm_filter2.cu)
   float* pub;                // [n_cols][nq] the order statistic each column publishes per query, initialised to NaN
   GemmCand* cand_buf;        // scratch [grid_y*grid_x*2][cand_cap][128]: per-(column,query) candidate buffers
   GemmCand* cand_out;        // [nq][n_cols][cand_out_cap]

@@ -588,8 +588,7 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   rc = c.q_f16.ensure(nq * (size_t)gp.q_stride); if (rc) return rc;   // lowered queries: fp16 or E4M3 codes, gp.q_stride bytes each
   rc = c.q_scale.ensure(nq * 4); if (rc) return rc;
   rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
-  const size_t n_prog = (size_t)gp.grid_x * gp.grid_y;             // lock-step counters of the query-tile groups, zeroed with g_thr
-  rc = c.g_thr.ensure((nq + n_prog) * 4); if (rc) return rc;
+  rc = c.g_thr.ensure(nq * 4); if (rc) return rc;
   rc = c.cand.ensure(nq * (size_t)n_cols * gp.cand_out_cap * sizeof(GemmCand)); if (rc) return rc;
   rc = c.cand_cnt.ensure(nq * (size_t)n_cols * 4); if (rc) return rc;
   rc = c.flags.ensure(nq * 4); if (rc) return rc;
@@ -610,14 +609,14 @@ int Store::fast_enqueue(SearchCtx& c, cudaStream_t st, const float* d_queries, s
   else { pp.f16_out = (__half*)c.q_f16.p; pp.f16_stride = gp.q_stride / 2; }
   // scratch initialisation rides in the prep launch: bound = 0, counts = 0, published values = -NaN ("nothing yet":
   // never greater than anything)
-  pp.fill_ptr[0] = (uint32_t*)c.g_thr.p;    pp.fill_words[0] = nq + n_prog;           pp.fill_value[0] = 0u;
+  pp.fill_ptr[0] = (uint32_t*)c.g_thr.p;    pp.fill_words[0] = nq;                    pp.fill_value[0] = 0u;
   pp.fill_ptr[1] = (uint32_t*)c.cand_cnt.p; pp.fill_words[1] = nq * (size_t)n_cols;  pp.fill_value[1] = 0u;
   pp.fill_ptr[2] = (uint32_t*)c.pub.p;      pp.fill_words[2] = nq * (size_t)n_cols;  pp.fill_value[2] = 0xffffffffu;
   rc = launch_prep_rows(pp, elem, st); if (rc) return rc;
   if (timed) cudaEventRecord(c.ev[1], st);
   GemmParams g{};
   g.n_rows = (uint32_t)n_rows; g.dim = dim; g.nq = (uint32_t)nq; g.q_lowered = c.q_f16.p; g.q_stride = gp.q_stride;
-  g.row_norm2 = d_norm2; g.row_scale = fp8 ? d_scale : nullptr; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p; g.progress = (uint32_t*)c.g_thr.p + nq;
+  g.row_norm2 = d_norm2; g.row_scale = fp8 ? d_scale : nullptr; g.metric = cfg.metric; g.nearest = nearest; g.g_thr = (uint32_t*)c.g_thr.p;
   g.cand_out = (GemmCand*)c.cand.p; g.cand_cnt = (uint32_t*)c.cand_cnt.p; g.dbg_acc = dbg_acc; g.pub = (float*)c.pub.p; g.cand_buf = (GemmCand*)c.cand_buf.p;
 #if COLTT_K2_PROF
   {   // role timers of the filter kernel: profiling builds only (make EXTRA=-DCOLTT_K2_PROF=1)
