@@ -15,10 +15,20 @@
 //   * one process driving all GPUs (the Go host): coltt_b200_init(device_ids, n) = ncclCommInitAll, and
 //     either n threads (goroutines) calling coltt_b200_sharded_search with their rank's handle, or one call of
 //     coltt_b200_sharded_search_all, which runs the ranks on n library threads.
+// The exchange itself does not have to be an NCCL call.  When every pair of ranks can map the other's memory (NVLink /
+// NVSwitch peers: cudaIpc handles between processes, cudaDeviceEnablePeerAccess inside one) the all-gather is FUSED INTO
+// THE MERGE: each rank's local search writes its hits into its own exchange buffer and raises a flag (system-scope
+// release); a one-CTA kernel on every rank waits for the peers' flags; then K5 reads the peers' lists straight out of
+// their memory over NVLink while it merges — no gather kernel, no receive buffer, no second pass.  Exchange buffers are
+// double-buffered by the parity of a per-communicator sequence number (a rank can only reach step s+2 after every peer
+// has finished merging step s).  NCCL then only bootstraps (it carries the IPC handles once) and stays as the fallback
+// (COLTT_P2P=0, more than 8 ranks, no peer access).  The wait has a timeout: a peer that never arrives is an error code,
+// not a hung GPU.
 // NCCL is loaded at run time (dlopen of libnccl.so.2, preferring the copy already mapped into the process), so
 // libcoltt_b200.so has no link-time dependency on it and single-GPU hosts never touch it.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <mutex>
 #include <thread>
@@ -86,8 +96,19 @@ struct Comm {
   std::mutex mu;                       // one collective at a time per rank
   DeviceBuf send, recv, q_in, out, counts;
   PinnedBuf h_q, h_out;
+  // peer-memory exchange (see the header comment)
+  int p2p = 0;                         // 0 = not set up yet, 1 = active, -1 = unavailable: NCCL path
+  uint8_t* xbuf = nullptr;             // [2][xcap] this rank's messages of even / odd steps
+  size_t xcap = 0;
+  uint32_t* flags = nullptr;           // [0..1] sequence number last published per slot, [2] timeout marker
+  std::vector<void*> peer_x, peer_f, ipc_opened;
+  DeviceBuf d_bases[2], d_peer_flags;  // device tables: list base addresses per slot; peers' flag words
+  uint32_t seq = 0;
   ~Comm() {
     cudaSetDevice(device);
+    for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
+    if (xbuf) cudaFree(xbuf);
+    if (flags) cudaFree(flags);
     if (comm && nccl().ok) nccl().CommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -107,9 +128,157 @@ static int make_comm(int device, int rank, int world, ncclComm_t c, Comm** out) 
   return COLTT_OK;
 }
 
+static int ensure_bufs(Comm& cm, size_t nq, int k) {
+  const size_t mb = msg_bytes(nq, k);
+  int rc;
+  if ((rc = cm.send.ensure(mb))) return rc;
+  if (cm.world > 1 && (rc = cm.recv.ensure(mb * cm.world))) return rc;
+  return COLTT_OK;
+}
+// ---- peer-memory exchange ------------------------------------------------------------------------------------------
+__global__ void xchg_signal_kernel(uint32_t* flag, uint32_t seq) {
+  // everything earlier in the stream (the local search's writes into the exchange buffer) is complete; publish it to the peers
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
+__global__ void xchg_wait_kernel(const unsigned long long* peer_flags, int world, uint32_t slot, uint32_t seq, uint32_t* timeout_marker,
+                                 long long timeout_cycles) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const uint32_t* f = reinterpret_cast<const uint32_t*>(peer_flags[r]) + slot;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if ((int32_t)(v - seq) >= 0) break;                  // sequence numbers only grow
+    if (clock64() - t0 > timeout_cycles) { atomicExch(timeout_marker, seq ? seq : 1u); break; }
+    __nanosleep(200);
+  }
+}
+
+struct XchgInfo {                      // what the ranks tell each other once, through NCCL
+  unsigned long long pid, x_ptr, f_ptr, xcap;
+  cudaIpcMemHandle_t hx, hf;
+  unsigned long long ok;
+};
+
+// Collective: (re)creates the exchange buffers for messages of `need` bytes and maps every peer's.  All ranks call it at the
+// same step (the message size is a function of nq and k, which the collective contract makes equal everywhere).
+static int p2p_setup(Comm& cm, size_t need) {
+  static const bool enabled = [] { const char* e = getenv("COLTT_P2P"); return !e || atoi(e) != 0; }();
+  if (!enabled || cm.world < 2 || cm.world > 8) { cm.p2p = -1; return COLTT_OK; }
+  cudaStream_t st = cm.stream;
+  int rc;
+  // Barrier first: a peer may still be merging the previous step out of THIS rank's buffer.  Every rank synchronises its own
+  // stream and then joins a tiny all-gather, which completes only when all of them have — after that nobody reads anybody.
+  COLTT_CUDA(cudaDeviceSynchronize());
+  if ((rc = cm.send.ensure(sizeof(XchgInfo))) || (rc = cm.recv.ensure(sizeof(XchgInfo) * cm.world))) return rc;
+  COLTT_NCCL(nccl().AllGather(cm.send.p, cm.recv.p, 8, ncclChar, cm.comm, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  for (void* q : cm.ipc_opened) cudaIpcCloseMemHandle(q);
+  cm.ipc_opened.clear(); cm.peer_x.assign(cm.world, nullptr); cm.peer_f.assign(cm.world, nullptr);
+  if (cm.xbuf) { cudaFree(cm.xbuf); cm.xbuf = nullptr; }
+  if (!cm.flags) { COLTT_CUDA(cudaMalloc(&cm.flags, 64)); COLTT_CUDA(cudaMemset(cm.flags, 0, 64)); cm.seq = 0; }
+  const size_t cap = std::max<size_t>((need + 255) / 256 * 256, 1u << 20);
+  XchgInfo mine{};
+  mine.ok = 1;
+  if (cudaMalloc(&cm.xbuf, 2 * cap) != cudaSuccess) { cudaGetLastError(); cm.xbuf = nullptr; mine.ok = 0; }
+  cm.xcap = cap;
+  mine.pid = (unsigned long long)getpid(); mine.x_ptr = (unsigned long long)cm.xbuf; mine.f_ptr = (unsigned long long)cm.flags; mine.xcap = cap;
+  if (mine.ok && (cudaIpcGetMemHandle(&mine.hx, cm.xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine.hf, cm.flags) != cudaSuccess)) {
+    cudaGetLastError();
+    mine.ok = 0;
+  }
+  // one NCCL all-gather of the descriptors (the sequence number simply continues: it is the same on every rank)
+  const size_t ib = sizeof(XchgInfo);
+  std::vector<XchgInfo> all(cm.world);
+  COLTT_CUDA(cudaMemcpyAsync(cm.send.p, &mine, ib, cudaMemcpyHostToDevice, st));
+  COLTT_NCCL(nccl().AllGather(cm.send.p, cm.recv.p, ib, ncclChar, cm.comm, st));
+  COLTT_CUDA(cudaMemcpyAsync(all.data(), cm.recv.p, ib * cm.world, cudaMemcpyDeviceToHost, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  bool ok = true;
+  for (int r = 0; r < cm.world; r++) ok = ok && all[r].ok && all[r].xcap == cap;
+  if (ok) {
+    for (int r = 0; r < cm.world && ok; r++) {
+      if (r == cm.rank) { cm.peer_x[r] = cm.xbuf; cm.peer_f[r] = cm.flags; continue; }
+      if (all[r].pid == mine.pid) {           // same process (coltt_b200_init): plain peer access
+        int peer_dev = -1;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, (void*)all[r].x_ptr) == cudaSuccess) peer_dev = at.device;
+        int can = 0;
+        if (peer_dev < 0 || cudaDeviceCanAccessPeer(&can, cm.device, peer_dev) != cudaSuccess || !can) { ok = false; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+        cudaGetLastError();
+        cm.peer_x[r] = (void*)all[r].x_ptr; cm.peer_f[r] = (void*)all[r].f_ptr;
+      } else {
+        void *px = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&px, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        cm.ipc_opened.push_back(px);
+        if (cudaIpcOpenMemHandle(&pf, all[r].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        cm.ipc_opened.push_back(pf);
+        cm.peer_x[r] = px; cm.peer_f[r] = pf;
+      }
+    }
+    cudaGetLastError();
+  }
+  // consensus: the peer path is used only if EVERY rank mapped every peer (a mixed decision would deadlock)
+  unsigned long long vote = ok ? 1 : 0;
+  std::vector<unsigned long long> votes(cm.world);
+  COLTT_CUDA(cudaMemcpyAsync(cm.send.p, &vote, 8, cudaMemcpyHostToDevice, st));
+  COLTT_NCCL(nccl().AllGather(cm.send.p, cm.recv.p, 8, ncclChar, cm.comm, st));
+  COLTT_CUDA(cudaMemcpyAsync(votes.data(), cm.recv.p, 8 * cm.world, cudaMemcpyDeviceToHost, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < cm.world; r++) ok = ok && votes[r] == 1;
+  if (!ok) { cm.p2p = -1; return COLTT_OK; }
+  // device tables: list bases per slot, peers' flag words
+  std::vector<unsigned long long> b0(cm.world), b1(cm.world), pf(cm.world);
+  for (int r = 0; r < cm.world; r++) { b0[r] = (unsigned long long)cm.peer_x[r]; b1[r] = b0[r] + cap; pf[r] = (unsigned long long)cm.peer_f[r]; }
+  if ((rc = cm.d_bases[0].ensure(8 * cm.world)) || (rc = cm.d_bases[1].ensure(8 * cm.world)) || (rc = cm.d_peer_flags.ensure(8 * cm.world))) return rc;
+  COLTT_CUDA(cudaMemcpyAsync(cm.d_bases[0].p, b0.data(), 8 * cm.world, cudaMemcpyHostToDevice, st));
+  COLTT_CUDA(cudaMemcpyAsync(cm.d_bases[1].p, b1.data(), 8 * cm.world, cudaMemcpyHostToDevice, st));
+  COLTT_CUDA(cudaMemcpyAsync(cm.d_peer_flags.p, pf.data(), 8 * cm.world, cudaMemcpyHostToDevice, st));
+  COLTT_CUDA(cudaStreamSynchronize(st));
+  cm.p2p = 1;
+  return COLTT_OK;
+}
+
+// Where this step's local search must write its hits (+ counts): the rank's exchange slot, or the NCCL send buffer.
+static int exchange_begin(Comm& cm, size_t nq, int k, uint8_t** msg) {
+  const size_t mb = msg_bytes(nq, k);
+  if (cm.world > 1 && nccl().ok && (cm.p2p == 0 || (cm.p2p == 1 && mb > cm.xcap))) {
+    int rc = p2p_setup(cm, mb);
+    if (rc) return rc;
+  }
+  if (cm.p2p == 1) {
+    cm.seq++;
+    *msg = cm.xbuf + (size_t)(cm.seq & 1u) * cm.xcap;
+    return COLTT_OK;
+  }
+  int rc = ensure_bufs(cm, nq, k);
+  if (rc) return rc;
+  *msg = (uint8_t*)cm.send.p;
+  return COLTT_OK;
+}
+
 // The exchange: this rank's message is already in cm.send; all-gather, then merge the `world` lists per query.
 static int exchange_and_merge(Comm& cm, size_t nq, int k, int nearest, Hit* d_out, int* d_counts, cudaStream_t st) {
   const size_t mb = msg_bytes(nq, k);
+  if (cm.p2p == 1) {
+    // fused exchange: publish, wait for the peers' flags (one small CTA), merge straight out of the peers' memory
+    const uint32_t slot = cm.seq & 1u;
+    xchg_signal_kernel<<<1, 1, 0, st>>>(cm.flags + slot, cm.seq);
+    static const long long timeout_cycles = [] { const char* e = getenv("COLTT_P2P_TIMEOUT_MS"); return (long long)(e ? atoi(e) : 20000) * 1500000ll; }();
+    xchg_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long*)cm.d_peer_flags.p, cm.world, slot, cm.seq, cm.flags + 2, timeout_cycles);
+    count_launch(2);
+    COLTT_CUDA(cudaGetLastError());
+    MergeParams mp{};
+    mp.list_bases = (const unsigned long long*)cm.d_bases[slot].p; mp.counts_off = nq * (size_t)k * sizeof(Hit);
+    mp.lists = (const Hit*)cm.xbuf; mp.counts = (const int*)cm.xbuf;     // unused with list_bases
+    mp.n_lists = cm.world; mp.nq = (uint32_t)nq; mp.k_in = (uint32_t)k; mp.k = (uint32_t)k; mp.nearest = nearest; mp.in_best_first = 0;
+    mp.out = d_out; mp.out_counts = d_counts;
+    return launch_merge_topk(mp, st);
+  }
   if (cm.world > 1) COLTT_NCCL(nccl().AllGather(cm.send.p, cm.recv.p, mb, ncclChar, cm.comm, st));
   MergeParams mp{};
   const uint8_t* base = (const uint8_t*)(cm.world > 1 ? cm.recv.p : cm.send.p);
@@ -120,26 +289,29 @@ static int exchange_and_merge(Comm& cm, size_t nq, int k, int nearest, Hit* d_ou
   return launch_merge_topk(mp, st);
 }
 
-static int ensure_bufs(Comm& cm, size_t nq, int k) {
-  const size_t mb = msg_bytes(nq, k);
-  int rc;
-  if ((rc = cm.send.ensure(mb))) return rc;
-  if (cm.world > 1 && (rc = cm.recv.ensure(mb * cm.world))) return rc;
-  return COLTT_OK;
-}
 
 // Enqueue-only: local search into the send buffer, all-gather, merge into d_out / d_counts, all on `st`.
 static int sharded_search_enqueue(Comm& cm, Store* shard, const void* d_queries, size_t nq, int k, int select_mode, int math_mode,
                                   Hit* d_out, int* d_counts, cudaStream_t st) {
   if (select_mode != COLTT_SELECT_COMPAT && select_mode != COLTT_SELECT_NEAREST) return fail(COLTT_ERR_INVALID, "bad select mode");
   if (shard->device != cm.device) return fail(COLTT_ERR_INVALID, "shard and communicator live on different devices");
-  int rc = ensure_bufs(cm, nq, k);
+  uint8_t* msg = nullptr;
+  int rc = exchange_begin(cm, nq, k, &msg);
   if (rc) return rc;
-  Hit* s_hits = (Hit*)cm.send.p;
-  int* s_cnt = (int*)((uint8_t*)cm.send.p + nq * (size_t)k * sizeof(Hit));
+  Hit* s_hits = (Hit*)msg;
+  int* s_cnt = (int*)(msg + nq * (size_t)k * sizeof(Hit));
   rc = shard->search_dev(d_queries, nq, k, select_mode, math_mode, s_hits, s_cnt, st);   // caller stream: enqueue only
   if (rc) return rc;
   return exchange_and_merge(cm, nq, k, select_mode == COLTT_SELECT_NEAREST, d_out, d_counts, st);
+}
+
+// after a synchronised host call: did the wait kernel give up on a peer?
+static int check_exchange_timeout(Comm& cm) {
+  if (cm.p2p != 1) return COLTT_OK;
+  uint32_t marker = 0;
+  COLTT_CUDA(cudaMemcpy(&marker, cm.flags + 2, 4, cudaMemcpyDeviceToHost));
+  if (marker) return fail(COLTT_ERR_CUDA, "sharded search: a peer rank did not publish its results within the exchange timeout (step " + std::to_string(marker) + ")");
+  return COLTT_OK;
 }
 
 static void unpack(const Hit* h, const int* c, size_t nq, int k, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
@@ -173,6 +345,7 @@ static int sharded_search_host(Comm& cm, Store* shard, const float* queries, siz
     COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.h_out.p + hb, cm.counts.p, nq * 4, cudaMemcpyDeviceToHost, cm.stream));
   }
   COLTT_CUDA(cudaStreamSynchronize(cm.stream));
+  if ((rc = check_exchange_timeout(cm))) return rc;
   if (want) unpack((const Hit*)cm.h_out.p, (const int*)((uint8_t*)cm.h_out.p + hb), nq, k, out_ids, out_scores, out_counts);
   return COLTT_OK;
 }
@@ -188,7 +361,8 @@ static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq,
   COLTT_CUDA(cudaSetDevice(cm.device));
   const size_t hb = nq * (size_t)k * sizeof(Hit);
   int rc;
-  if ((rc = ensure_bufs(cm, nq, k)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_out.ensure(hb + nq * 4))) return rc;
+  uint8_t* msg = nullptr;
+  if ((rc = exchange_begin(cm, nq, k, &msg)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_out.ensure(hb + nq * 4))) return rc;
   const Hit* d_hits = nullptr; const int* d_cnt = nullptr; cudaStream_t hst = nullptr;
   if (pq) {
     std::vector<uint64_t> ti(nq * (size_t)k);
@@ -202,8 +376,8 @@ static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq,
     rc = hnsw_search_keep_device(h, queries, nq, k, ef, &d_hits, &d_cnt, &hst);     // returns after the walk finished
     if (rc) return rc;
   }
-  COLTT_CUDA(cudaMemcpyAsync(cm.send.p, d_hits, hb, cudaMemcpyDeviceToDevice, cm.stream));
-  COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.send.p + hb, d_cnt, nq * 4, cudaMemcpyDeviceToDevice, cm.stream));
+  COLTT_CUDA(cudaMemcpyAsync(msg, d_hits, hb, cudaMemcpyDeviceToDevice, cm.stream));
+  COLTT_CUDA(cudaMemcpyAsync(msg + hb, d_cnt, nq * 4, cudaMemcpyDeviceToDevice, cm.stream));
   rc = exchange_and_merge(cm, nq, k, 1, (Hit*)cm.out.p, (int*)cm.counts.p, cm.stream);
   if (rc) return rc;
   const bool want = out_ids && out_scores && out_counts;
@@ -212,6 +386,7 @@ static int sharded_hnsw_host(Comm& cm, Hnsw* h, const float* queries, size_t nq,
     COLTT_CUDA(cudaMemcpyAsync((uint8_t*)cm.h_out.p + hb, cm.counts.p, nq * 4, cudaMemcpyDeviceToHost, cm.stream));
   }
   COLTT_CUDA(cudaStreamSynchronize(cm.stream));
+  if ((rc = check_exchange_timeout(cm))) return rc;
   if (want) unpack((const Hit*)cm.h_out.p, (const int*)((uint8_t*)cm.h_out.p + hb), nq, k, out_ids, out_scores, out_counts);
   return COLTT_OK;
 }

@@ -186,6 +186,10 @@ struct MergeParams {
   uint32_t out_stride;       // hits per output row (0 = k)
   size_t list_stride_hits;   // Hits between consecutive lists (0 = nq*k_in, the dense layout)
   size_t count_stride;       // ints between consecutive lists' counts (0 = nq)
+  // Peer-memory form (comm.cu): list j lives at its own base address — another GPU's exchange buffer, read over NVLink —
+  // as coltt_hit[nq][k_in] followed, counts_off bytes in, by int32 counts[nq].  Null = the lists / counts arrays above.
+  const unsigned long long* list_bases;   // device array [n_lists]
+  size_t counts_off;
   Hit* out;                  // [nq][out_stride] in T order (ascending score, NaN last, then id)
   int* out_counts;           // [nq]
 };

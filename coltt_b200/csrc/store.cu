@@ -425,7 +425,7 @@ int Store::enqueue_cached(SearchCtx& c, cudaStream_t st, const GraphKey& key, bo
   for (auto& g : c.graphs)
     if (g.key == key) { e = &g; break; }
   if (!e) {
-    if (c.graphs.size() >= 8) {
+    if (c.graphs.size() >= 16) {
       if (c.graphs.front().exec) cudaGraphExecDestroy(c.graphs.front().exec);
       c.graphs.erase(c.graphs.begin());
     }

@@ -72,7 +72,7 @@ struct SearchCtx {
   DeviceBuf q_in, q_deq, q_n2, q_f16, q_scale, warp_lists, cta_lists, cta_counts, out, counts, tmp_out, subset, cand, cand_cnt, g_thr, flags, fb_q, fb_out, fb_cnt, pub, prof, cand_buf, multi_acc;
   PinnedBuf h_q, h_out;
   GemmMapCache maps;                // TMA descriptors of the last FAST launch on this scratch
-  std::vector<GraphEntry> graphs;   // captured searches of this scratch (at most 8)
+  std::vector<GraphEntry> graphs;   // captured searches of this scratch (at most 16)
   ~SearchCtx();
 };
 

@@ -41,13 +41,14 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(MergeParams p
     Hit* Ls = surv + surv_cap;                         // [n_lists][k_in]
     int* cnt_s = reinterpret_cast<int*>(Ls + (size_t)p.n_lists * p.k_in);
     for (int j = tid; j < p.n_lists; j += blockDim.x) {
-      int c = p.counts[(size_t)j * cstr + q];
+      int c = p.list_bases ? reinterpret_cast<const int*>(p.list_bases[j] + p.counts_off)[q] : p.counts[(size_t)j * cstr + q];
       cnt_s[j] = c > (int)p.k_in ? (int)p.k_in : c;
     }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)p.n_lists * p.k_in; i += blockDim.x) {
       uint32_t j = i / p.k_in, e = i - j * p.k_in;
-      if ((int)e < cnt_s[j]) Ls[i] = p.lists[(size_t)j * lstr + (size_t)q * p.k_in + e];
+      if ((int)e < cnt_s[j])
+        Ls[i] = p.list_bases ? reinterpret_cast<const Hit*>(p.list_bases[j])[(size_t)q * p.k_in + e] : p.lists[(size_t)j * lstr + (size_t)q * p.k_in + e];
     }
     L = Ls; cnt = cnt_s; list_stride = p.k_in; cnt_stride = 1;
   } else {
@@ -142,6 +143,7 @@ int launch_merge_topk(const MergeParams& p, cudaStream_t stream) {
   uint32_t surv_cap = 4 * p.k > 1024 ? 4 * p.k : 1024;
   const size_t base = ((size_t)p.k + piv_cap + surv_cap) * sizeof(Hit);
   const size_t staged = base + (size_t)p.n_lists * p.k_in * sizeof(Hit) + (size_t)p.n_lists * sizeof(int);
+  if (p.list_bases && staged > 200 * 1024) return fail(COLTT_ERR_UNSUPPORTED, "merge: peer-memory lists need the staged variant");
   if (staged <= 200 * 1024) {
     { int arc = kernel_attrs(merge_topk_kernel<true>, staged); if (arc) return arc; }
     merge_topk_kernel<true><<<p.nq, kMergeThreads, staged, stream>>>(p, piv_per_list, piv_cap, surv_cap);

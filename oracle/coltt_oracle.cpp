@@ -194,7 +194,7 @@ ORC_API float orc_e4m3_decode(uint8_t c) {
 ORC_API uint8_t orc_e4m3_encode(float x) {
   const uint8_t sign = std::signbit(x) ? 0x80 : 0x00;
   const float a = std::fabs(x);
-  if (a != a) return (uint8_t)(sign | 0x7f);
+  if (a != a) return (uint8_t)0x7f;                      // one canonical NaN code (the sign of a NaN is not part of the contract)
   if (a > 448.0f) return (uint8_t)(sign | 0x7e);        // saturate (values in (448, 464) would round down to 448 anyway)
   if (a < 0.015625f) {                                   // below 2^-6: subnormal grid of 2^-9
     const int q = (int)std::nearbyint(std::ldexp(a, 9)); // exact scaling, RNE (default rounding mode)

@@ -61,3 +61,32 @@ def test_score_helper_matches_oracle(oracle):
         got = coltt_b200.score_helper(s, metric)
         want = np.array([oracle.lib().orc_score_helper(float(x), metric) for x in s], dtype=np.float32)
         assert got.tobytes() == want.tobytes()
+
+
+def test_certificate_margin_is_a_function_of_dim():
+    """coltt_b200_fast_eps_rel is pure host arithmetic: 1.25 (dim 2^-23 + (dim/8 + 3) 2^-24) + 2^-20."""
+    from coltt_b200 import _lib
+    L = _lib.lib()
+    for dim in (1, 64, 100, 768, 1536, 4096):
+        want = 1.25 * (dim * 2.0 ** -23 + (dim / 8.0 + 3.0) * 2.0 ** -24) + 2.0 ** -20
+        got = float(L.coltt_b200_fast_eps_rel(dim))
+        assert abs(got - want) <= 1e-6 * want, (dim, got, want)
+    assert L.coltt_b200_fast_eps_rel(64) < L.coltt_b200_fast_eps_rel(768) < L.coltt_b200_fast_eps_rel(1536)
+    assert 1.0e-4 < L.coltt_b200_fast_eps_rel(768) < 1.5e-4
+
+
+def test_multi_gpu_entry_points_fail_cleanly_without_a_gpu():
+    """No device: the communicator calls return codes (COLTT_ERR_NO_DEVICE), never abort; shutdown with nothing open is a no-op."""
+    from coltt_b200 import _lib
+    L = _lib.lib()
+    if L.coltt_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    devs = (C.c_int * 1)(0)
+    h = (C.c_void_p * 1)()
+    assert L.coltt_b200_init(devs, 1, h) == -8
+    assert b"no CPU fallback" in L.coltt_b200_last_error() or b"CUDA" in L.coltt_b200_last_error()
+    blob = (C.c_uint8 * 128)()
+    out = C.c_void_p()
+    assert L.coltt_b200_comm_init_rank(blob, 0, 1, 0, C.byref(out)) == -8
+    assert L.coltt_b200_comm_init_rank(blob, 3, 2, 0, C.byref(out)) == -1       # rank >= world: invalid before any device work
+    L.coltt_b200_shutdown()

@@ -181,3 +181,35 @@ def test_append_device_rows_equals_host_upsert(cb):
     with pytest.raises(cb.ColttError):
         a.ChangedVertices(np.array([1], np.uint64), vecs[:1])
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_e4m3_edge_cases(cb, oracle, metric):
+    """Tiny dims, k larger than the store, empty store, rows whose magnitudes hit the scale clamp (2^+-40), infinities
+    (scale 1, saturating encode) and all-zero rows: the exact kernel equals the oracle's restatement bit for bit."""
+    for d in (1, 3, 17):
+        n, k = 60, 100
+        vecs = normal(n, d)
+        vecs[3] *= np.float32(1e30)
+        vecs[4] *= np.float32(1e-30)
+        vecs[5] = 0.0
+        vecs[6, 0] = np.float32(np.inf)
+        vecs[7] = np.float32(3.0e38)
+        ids = sparse_ids(n)
+        sp = cb.VectorSpace("edge", cb.Metadata(d, metric, cb.Quantization_F8_E4M3))
+        st = oracle.FlatStore(d, metric, oracle.Q_F8_E4M3)
+        gi, gs, gc = sp.BatchVertexSearch(normal(2, d, QUERY_SEED), k)
+        assert gc.tolist() == [0, 0]                                       # empty store
+        sp.ChangedVertices(ids, vecs)
+        st.upsert(ids, vecs)
+        for j in (0, 3, 4, 5, 6, 7, n - 1):
+            assert np.array_equal(sp.stored_row(int(ids[j])), st.get_row(int(ids[j]))), f"d={d} stored codes of row {j}"
+        qs = np.concatenate([normal(3, d, QUERY_SEED), vecs[3:5], np.zeros((1, d), np.float32)])
+        for mode in (cb.SELECT_COMPAT, cb.SELECT_NEAREST):
+            for mm in (cb.MATH_EXACT, cb.MATH_FAST):                         # FAST: below 4096 rows -> served exactly
+                gi, gs, gc = sp.BatchVertexSearch(qs, k, select_mode=mode, math_mode=mm)
+                for j in range(len(qs)):
+                    wi, ws = st.search_total_order(qs[j], k, select_mode=mode)
+                    assert gc[j] == n
+                    assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], wi, ws, f"d={d} metric={metric} mode={mode} math={mm} q{j}")
+        sp.close()
