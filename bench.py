@@ -539,6 +539,7 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
         recall = float(np.mean([len(np.intersect1d(gt[j], gi[j, :k])) / k for j in range(rq)]))   # edge/resultset.go:55-65
         recall_note = f"{rq} queries vs fp32 exact ground truth (torch fp32 matmul over the regenerated rows) over all {n} rows"
 
+    exchange = comm.exchange if comm is not None else None
     if comm is not None:
         comm.close()
     if rank != 0:
@@ -575,7 +576,7 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
                        "weak scaling: every rank holds its own shard of rows_per_gpu rows and every query is answered over all "
                        "of them; value counts (query x shard) units = n_gpus x batch per step; global_qps is queries/s over the "
                        "whole n_gpus x rows_per_gpu collection",
-                       "parallelism": f"shard{world}", "ingest_s": round(t_ingest, 2)},
+                       "parallelism": f"shard{world}", "exchange": exchange, "ingest_s": round(t_ingest, 2)},
             "global_qps": nq * steps / (ms / 1000.0), "global_rows": world * n,
             "gpu_launches": int(launches), "kernel_ms": parts, "roofline": roof, "clocks": clocks}
     if e2e_value is not None:
@@ -696,6 +697,7 @@ def c5_arm(args, wl, torch, dist, world, rank, local):
         dist.gather(loc, allp, dst=0)
     else:
         allp = [loc]
+    exchange = comm.exchange if comm is not None else None
     if comm is not None:
         comm.close()
     if rank != 0:
@@ -723,7 +725,7 @@ def c5_arm(args, wl, torch, dist, world, rank, local):
             "data": "synthetic",
             "config": {"workload": wl["name"], "rows_per_gpu": n, "dim": d, "batch": nq, "k": k, "ef": ef, "pq": "64 sub-vectors x 256 centroids, 65536 training rows",
                        "data_model": "32-d latent + 10% noise", "gen_s": round(t_gen, 1), "build_s": round(t_build, 1), "pq_train_encode_s": round(t_pq, 2),
-                       "parallelism": f"shard{world}", "code_evals_per_query": evals / (args.steps * nq), "expansions_per_query": exps / (args.steps * nq),
+                       "parallelism": f"shard{world}", "exchange": exchange, "code_evals_per_query": evals / (args.steps * nq), "expansions_per_query": exps / (args.steps * nq),
                        "unit_note": "weak scaling (rows_per_gpu per rank); value counts (query x shard) units, global_qps is queries/s over the union"},
             "global_qps": qps, "global_rows": world * n,
             "e2e": {"value": world * qps, "unit": unit, "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 16 + nq * 4,

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_multi_search", "coltt_b200_hnsw_last_timing",
     "coltt_b200_store_append_dev", "coltt_b200_store_fast_stats", "coltt_b200_fast_eps_rel", "coltt_b200_hnsw_dim",
     "coltt_b200_init", "coltt_b200_shutdown", "coltt_b200_comm_unique_id", "coltt_b200_comm_init_rank", "coltt_b200_comm_destroy",
-    "coltt_b200_comm_info", "coltt_b200_sharded_search", "coltt_b200_sharded_search_dev", "coltt_b200_sharded_search_all",
+    "coltt_b200_comm_info", "coltt_b200_comm_exchange_mode", "coltt_b200_sharded_search", "coltt_b200_sharded_search_dev", "coltt_b200_sharded_search_all",
     "coltt_b200_sharded_hnsw_search", "coltt_b200_sharded_hnsw_pq_search", "coltt_b200_hnsw_pq_train", "coltt_b200_hnsw_pq_search",
 ]
 
@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
     L.coltt_b200_comm_destroy.argtypes = [vp]
     L.coltt_b200_comm_destroy.restype = None
     L.coltt_b200_comm_info.argtypes = [vp, ip, ip, ip]
+    L.coltt_b200_comm_exchange_mode.argtypes = [vp]
     L.coltt_b200_sharded_search.argtypes = [vp, vp, f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, u64p, f32p, i32p]
     L.coltt_b200_sharded_search_dev.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.coltt_b200_sharded_search_all.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int, f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, u64p, f32p, i32p]

@@ -473,6 +473,13 @@ COLTT_API int coltt_b200_comm_info(coltt_comm* c, int* rank, int* world, int* de
   return COLTT_OK;
 }
 
+COLTT_API int coltt_b200_comm_exchange_mode(coltt_comm* c) {
+  Comm* cm = reinterpret_cast<Comm*>(c);
+  if (!cm) return fail(COLTT_ERR_INVALID, "null communicator");
+  if (cm->world < 2) return COLTT_EXCHANGE_NCCL;
+  return cm->p2p == 1 ? COLTT_EXCHANGE_PEER : cm->p2p == 0 ? COLTT_EXCHANGE_UNDECIDED : COLTT_EXCHANGE_NCCL;
+}
+
 COLTT_API int coltt_b200_sharded_search(coltt_comm* c, coltt_store* shard, const float* queries, size_t nq, int k, int select_mode,
                                         int math_mode, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
   if (!c || !shard) return fail(COLTT_ERR_INVALID, "null handle");

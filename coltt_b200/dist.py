@@ -129,8 +129,9 @@ def cuda_callables(space, device_index: int, math_mode: Optional[int] = None, st
 
 class Comm:
     """One rank of a sharded collection behind the C-ABI (include/coltt_b200.h, csrc/comm.cu): the local search, the single
-    NCCL all-gather of per-shard top-k and the K5 merge all run inside libcoltt_b200.so on the rank's stream, with persistent
-    exchange buffers and pinned staging.  torch.distributed is used only to hand the 128-byte rendezvous blob to the ranks."""
+    exchange of per-shard top-k (fused into the merge over NVLink peer memory, else one NCCL all-gather) and the K5 merge all
+    run inside libcoltt_b200.so on the rank's stream, with persistent exchange buffers and pinned staging.  torch.distributed
+    is used only to hand the 128-byte rendezvous blob to the ranks."""
 
     def __init__(self, handle, rank: int, world: int, device: int):
         self._h, self.rank, self.world, self.device = handle, rank, world, device
@@ -164,6 +165,13 @@ class Comm:
             from . import _lib
             _lib.lib().coltt_b200_comm_destroy(self._h)
             self._h = None
+
+    @property
+    def exchange(self) -> str:
+        """"peer-memory" | "nccl" | "undecided" (before the first sharded search): coltt_b200_comm_exchange_mode."""
+        from . import _lib
+        m = _lib.lib().coltt_b200_comm_exchange_mode(self._h)
+        return {1: "peer-memory", 2: "nccl"}.get(m, "undecided")
 
     def search(self, space, queries, k: int, select_mode: int, math_mode: Optional[int] = None):
         """Collective: every rank calls with the same queries.  Host buffers in, merged (ids, scores, counts) out."""

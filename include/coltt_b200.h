@@ -248,7 +248,7 @@ COLTT_API int coltt_b200_hnsw_pq_train(coltt_hnsw* h, const coltt_pq_params* p, 
 COLTT_API int coltt_b200_hnsw_pq_search(coltt_hnsw* h, const float* queries, size_t nq, int k, int ef, int rerank, uint64_t* out_ids,
                                         float* out_scores, int32_t* out_counts);
 
-/* ---- sharded collections: one shard per GPU, ONE NCCL all-gather of per-shard top-k, merge ---------------
+/* ---- sharded collections: one shard per GPU, ONE exchange of per-shard top-k lists, merge ----------------
  * Reference analogue: the 16 in-process shards of a vectorspace, each scanned into a shard-local queue and re-merged
  * (edge/none_vectorstore.go:152-178); rows -> shard by ShardVertex(id, 16) mod n_gpus (pkg/sharding/shard.go:34-41; the
  * host partitions the ids).  A coltt_comm is one rank: a GPU, its NCCL communicator, a stream and persistent exchange
@@ -263,6 +263,12 @@ COLTT_API int coltt_b200_comm_unique_id(void* out, size_t len);
 COLTT_API int coltt_b200_comm_init_rank(const void* unique_id, int rank, int world, int device, coltt_comm** out);
 COLTT_API void coltt_b200_comm_destroy(coltt_comm* c);
 COLTT_API int coltt_b200_comm_info(coltt_comm* c, int* rank, int* world, int* device);
+/* How this rank exchanges the per-shard lists: COLTT_EXCHANGE_UNDECIDED before the first sharded search (the choice is a
+ * collective vote taken there), COLTT_EXCHANGE_PEER = the all-gather is fused into the merge kernel, which reads every
+ * peer's list out of the peer's HBM over NVLink (cudaIpc / peer access; every rank could map every peer),
+ * COLTT_EXCHANGE_NCCL = ncclAllGather then merge (COLTT_P2P=0, > 8 ranks, or some pair without peer access). */
+enum { COLTT_EXCHANGE_UNDECIDED = 0, COLTT_EXCHANGE_PEER = 1, COLTT_EXCHANGE_NCCL = 2 };
+COLTT_API int coltt_b200_comm_exchange_mode(coltt_comm* c);
 /* VertexSearch over the whole sharded collection, called by EVERY rank with the same queries / nq / k / modes (a
  * collective): local search of `shard` (hits written straight into the send buffer), ncclAllGather, merge.  Every rank
  * ends up with the merged answer; a rank may pass NULL outputs.  Host buffers; returns when the answer is in them. */

@@ -82,12 +82,13 @@ def main():
             if not good:
                 print("MISMATCH (sharded hnsw)", j, gi[j], allp[j, order, 0], flush=True)
             ok &= bool(good)
+    exchange = comm.exchange
     comm.close()
     sub.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_GPU_OK" if int(t.item()) == 1 else "DIST_GPU_FAIL", "world", world, flush=True)
+        print("DIST_GPU_OK" if int(t.item()) == 1 else "DIST_GPU_FAIL", "world", world, "exchange", exchange, flush=True)
     dist.destroy_process_group()
 
 

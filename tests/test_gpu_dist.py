@@ -11,7 +11,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_sharded_search_two_or_more_gpus():
+@pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
+def test_sharded_search_two_or_more_gpus(exchange):
+    """Both exchange steps of csrc/comm.cu — the merge kernel reading the peers' lists over NVLink (default where every pair of
+    ranks has peer access) and ncclAllGather + merge (COLTT_P2P=0) — against the oracle over the union of the shards."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -19,8 +22,14 @@ def test_sharded_search_two_or_more_gpus():
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, COLTT_P2P="1" if exchange == "peer-memory" else "0")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert "DIST_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    used = out.stdout.split("exchange", 1)[1].split()[0]
+    if exchange == "nccl":
+        assert used == "nccl", out.stdout[-500:]
+    elif used != "peer-memory":
+        pytest.skip("this box has no peer access between the GPUs: the ranks voted for the NCCL exchange")
 
 
 def test_single_process_multi_gpu_through_the_c_abi():
