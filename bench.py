@@ -113,9 +113,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Summary of the samples taken in [t_from, t_to] (perf_counter times; default: all of them)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -126,7 +127,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t_row, r in self.rows:
+            # a row printed at t_row describes the ~50 ms before it
+            if (t_from is not None and t_row < t_from) or (t_to is not None and t_row > t_to + 0.06):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -287,10 +291,11 @@ def hnsw_arm(args, light=False):
     h = cb.Hnsw.Build(ids, rows, metric=cb.Distance_Cosine, m=16, ef=ef)
     t_build = time.perf_counter() - t0
     qsets = [latent_rows(nq, d, QUERY_SEED + i) for i in range(4)]
+    sampler = ClockSampler(0)       # started before the warm-up, rows time-stamped: see flat_arm
+    sampler.start()
+    t_load0 = time.perf_counter()
     for i in range(warmup):
         h.BatchSearch(qsets[i % 4], k, ef)
-    sampler = ClockSampler(0)
-    sampler.start()
     launches0 = L.coltt_b200_kernel_launches()
     kern, evals, exps = [], 0, 0
     torch.cuda.synchronize()
@@ -302,7 +307,12 @@ def hnsw_arm(args, light=False):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     launches = L.coltt_b200_kernel_launches() - launches0
-    clocks = sampler.stop()
+    extra = 0
+    while time.perf_counter() - t_load0 < 0.45:      # the same searches, untimed, until nvidia-smi has seen the load
+        h.BatchSearch(qsets[extra % 4], k, ef)
+        extra += 1
+    clocks = sampler.stop(t_load0 + 0.05, time.perf_counter())
+    clocks["continued_steps_for_sampling"] = extra
     kern_ms = float(np.mean(kern))
     qps = nq * steps / wall
     peaks = measured_peaks()
@@ -436,12 +446,17 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
 
     steps, warmup = (min(args.steps, 10), 3) if light else (args.steps, args.warmup)
     # ---- device-resident throughput -------------------------------------------------------
-    for i in range(warmup):
-        step_dev(i)
-    barrier()
+    # nvidia-smi needs ~0.2 s to print its first row, longer than a 20-step timed region (8 ms at config 2): the sampler starts
+    # before the warm-up, and when warm-up + timed region lasted less than 0.45 s the SAME steps keep running, untimed, right
+    # behind the timed region until 0.45 s of load have passed.  Rows are time-stamped; only rows printed while the device was
+    # under this load (warm-up, timed region, continuation) are summarised.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_load0 = time.perf_counter()
+    for i in range(warmup):
+        step_dev(i)
+    barrier()
     launches0 = L.coltt_b200_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -452,11 +467,25 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
     barrier()
     launches = L.coltt_b200_kernel_launches() - launches0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # the continuation: every rank runs the same number of extra steps (the step is a collective at N > 1)
+    load_ms = (warmup + steps) * ms / steps
+    extra = int(min(5000, max(0.0, 450.0 - load_ms) / (ms / steps) + 0.999)) if load_ms < 450.0 else 0
+    for i in range(extra):
+        step_dev(i)
+        if i % 64 == 63:
+            torch.cuda.synchronize(dev)
+    barrier()
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop(t_load0 + 0.05, time.perf_counter())
+        clocks["continued_steps_for_sampling"] = extra
+        if extra:
+            clocks["note"] = (f"timed region {ms:.1f} ms is below nvidia-smi's resolution: rows cover warm-up + timed region + {extra} more "
+                              "untimed steps of the same load (0.45 s in all), long enough for the power cap to engage")
     ms_per_step = ms / steps
     value = world * nq * steps / (ms / 1000.0)   # (query x shard) units per second, whole job
 
@@ -495,28 +524,40 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
 
     # ---- end to end: host buffers in, host results out.  N=1: the host-pointer C-ABI call.  N>1: the sharded
     # C-ABI call coltt_b200_sharded_search: H2D of the queries, per-shard search, all-gather, merge, D2H.
-    e2e_value = e2e_steps = None
+    e2e_value = e2e_steps = e2e_pageable = None
     if not light:
-        if world > 1:
-            def e2e_step(i):     # coltt_b200_sharded_search: host queries in, merged host results out, on every rank
-                return comm.search(sp, q_host[i % n_qsets], k, cb.SELECT_NEAREST, math_mode)
-        else:
-            def e2e_step(i):
-                return sp.BatchVertexSearch(q_host[i % n_qsets], k)
-        for i in range(min(warmup, 3)):
-            e2e_step(i)
-        barrier()
-        t1 = time.perf_counter()
-        e2e_steps = max(3, min(steps // 3, 300))
-        for i in range(e2e_steps):
-            e2e_step(i)
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t1
-        if dist is not None:
-            t = torch.tensor([e2e_s], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e_value = world * nq * e2e_steps / e2e_s
+        # the caller's query batches live in page-locked buffers (coltt_b200_host_alloc), as the bench contract asks: the
+        # library DMAs them in place.  The same loop over ordinary (pageable) numpy arrays — staged through the handle's pinned
+        # buffer by one extra host memcpy — is reported beside it.
+        q_pin = []
+        for q in q_host:
+            b = cb.pinned_empty(q.shape, np.float32)
+            b[...] = q
+            q_pin.append(b)
+
+        def e2e_leg(qsets):
+            if world > 1:
+                def e2e_step(i):     # coltt_b200_sharded_search: host queries in, merged host results out, on every rank
+                    return comm.search(sp, qsets[i % n_qsets], k, cb.SELECT_NEAREST, math_mode)
+            else:
+                def e2e_step(i):
+                    return sp.BatchVertexSearch(qsets[i % n_qsets], k)
+            for i in range(max(3, min(warmup, 10))):
+                e2e_step(i)
+            barrier()
+            t1 = time.perf_counter()
+            n_e = max(50, min(steps // 3, 300)) if nq * d <= 256 * 768 else max(5, min(steps // 3, 300))
+            for i in range(n_e):
+                e2e_step(i)
+            torch.cuda.synchronize(dev)
+            e2e_s = time.perf_counter() - t1
+            if dist is not None:
+                t = torch.tensor([e2e_s], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            return world * nq * n_e / e2e_s, n_e
+        e2e_pageable, _ = e2e_leg(q_host)
+        e2e_value, e2e_steps = e2e_leg(q_pin)
 
     # ---- recall@k against fp32 ground truth.  Host-resident rows: the oracle.  Device-generated shards (config 4): the
     # rows are regenerated chunk by chunk and scored in fp32 by torch (CUDA-core matmul, TF32 off) — a checker independent
@@ -581,7 +622,8 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
             "gpu_launches": int(launches), "kernel_ms": parts, "roofline": roof, "clocks": clocks}
     if e2e_value is not None:
         line["e2e"] = {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 16 + nq * 4,
-                       "steps": e2e_steps, "global_qps": e2e_value / world}
+                       "steps": e2e_steps, "global_qps": e2e_value / world, "host_buffers": "page-locked (coltt_b200_host_alloc), DMA in place",
+                       "value_pageable_host_buffers": e2e_pageable}
     if merge_check is not None:
         line["merge_check"] = merge_check
         line["merge_check_note"] = "8 queries: device all-gather + K5 merge vs host merge of per-rank EXACT searches over the union, ids + score bits"

@@ -49,6 +49,7 @@ func (b *Batcher) VertexSearch(target []float32, topK int) ([]Hit, error) {
 
 func (b *Batcher) run() {
 	var held []batchReq // requests whose topK differs from the batch being formed
+	pinned, _ := HostAlloc(b.MaxBatch * b.dim) // nil on failure: ordinary slices still work, through the library's staging copy
 	for {
 		var first batchReq
 		if len(held) > 0 {
@@ -72,7 +73,11 @@ func (b *Batcher) run() {
 			}
 		}
 		timer.Stop()
-		flat := make([]float32, 0, len(batch)*b.dim)
+		// the batch is assembled in page-locked memory (one buffer for the life of the batcher): the library DMAs it in place
+		flat := make([]float32, 0)
+		if pinned != nil {
+			flat = pinned.Data[:0]
+		}
 		for _, r := range batch {
 			flat = append(flat, r.q...)
 		}

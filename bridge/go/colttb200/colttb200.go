@@ -190,6 +190,32 @@ func (s *Store) BatchVertexSearch(targets []float32, nq, topK int, selectMode, m
 	return ids, scores, counts, err
 }
 
+// PinnedFloats is a []float32 over page-locked host memory (coltt_b200_host_alloc).  A query batch assembled in it is
+// DMA'd to the GPU in place by BatchVertexSearch / Cluster.BatchVertexSearch; ordinary Go slices are first copied into the
+// handle's own pinned staging buffer by the library.  C memory: not moved or scanned by the Go GC; Free it explicitly.
+type PinnedFloats struct {
+	Data []float32
+	p    unsafe.Pointer
+}
+
+func HostAlloc(nFloats int) (*PinnedFloats, error) {
+	if nFloats <= 0 {
+		return nil, errors.New("colttb200: HostAlloc needs a positive size")
+	}
+	var p unsafe.Pointer
+	if err := call(func() C.int { return C.coltt_b200_host_alloc(C.size_t(nFloats)*4, &p) }); err != nil {
+		return nil, err
+	}
+	return &PinnedFloats{Data: unsafe.Slice((*float32)(p), nFloats), p: p}, nil
+}
+
+func (b *PinnedFloats) Free() {
+	if b.p != nil {
+		C.coltt_b200_host_free(b.p)
+		b.p, b.Data = nil, nil
+	}
+}
+
 // SaveVertex / LoadVertex: edge/none_vectorstore.go:308-516 (metaCount = 0; metadata is saved by the Go side).
 func (s *Store) SaveVertex() ([]byte, error) {
 	var n C.size_t

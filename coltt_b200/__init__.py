@@ -6,7 +6,7 @@ this package is the Python host-side mirror of the reference's Go interfaces use
 bench.py (the Go toolchain is absent from the build image; INTEGRATION.md holds the cgo shim).
 There is no CPU fallback: importing works anywhere, every compute call needs an sm_100 GPU.
 """
-from ._lib import ColttError, lib, build_library, LIB_PATH  # noqa: F401
+from ._lib import ColttError, lib, build_library, LIB_PATH, pinned_empty  # noqa: F401
 from .edge import (  # noqa: F401
     Vectorstore, VectorSpace, SearchResultItem, Metadata,
     Distance_Cosine, Distance_Euclidean,

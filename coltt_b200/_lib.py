@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "coltt_b200_store_export", "coltt_b200_store_import", "coltt_b200_store_get_row",
     "coltt_b200_hnsw_load", "coltt_b200_hnsw_destroy", "coltt_b200_hnsw_len", "coltt_b200_hnsw_search",
     "coltt_b200_hnsw_last_stats", "coltt_b200_hnsw_build", "coltt_b200_hnsw_commit", "coltt_b200_hnsw_build_stats", "coltt_b200_hnsw_build_fast_stats",
-    "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_multi_search", "coltt_b200_hnsw_last_timing",
+    "coltt_b200_store_last_timing", "coltt_b200_store_set_timing", "coltt_b200_kernel_launches", "coltt_b200_host_alloc", "coltt_b200_host_free", "coltt_b200_multi_search", "coltt_b200_hnsw_last_timing",
     "coltt_b200_store_append_dev", "coltt_b200_store_fast_stats", "coltt_b200_fast_eps_rel", "coltt_b200_hnsw_dim",
     "coltt_b200_init", "coltt_b200_shutdown", "coltt_b200_comm_unique_id", "coltt_b200_comm_init_rank", "coltt_b200_comm_destroy",
     "coltt_b200_comm_info", "coltt_b200_comm_exchange_mode", "coltt_b200_sharded_search", "coltt_b200_sharded_search_dev", "coltt_b200_sharded_search_all",
@@ -104,6 +104,9 @@ def lib() -> C.CDLL:
     L.coltt_b200_store_last_timing.argtypes = [vp, f32p, C.c_int]
     L.coltt_b200_store_set_timing.argtypes = [vp, C.c_int]
     L.coltt_b200_kernel_launches.restype = C.c_uint64
+    L.coltt_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.coltt_b200_host_free.argtypes = [vp]
+    L.coltt_b200_host_free.restype = None
     L.coltt_b200_store_append_dev.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint64]
     L.coltt_b200_store_fast_stats.argtypes = [vp, u64p]
     L.coltt_b200_fast_eps_rel.argtypes = [C.c_uint32]
@@ -137,3 +140,20 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != 0:
         raise ColttError(rc, (lib().coltt_b200_last_error() or b"").decode("utf-8", "replace"))
+
+
+def pinned_empty(shape, dtype="float32"):
+    """A numpy array over page-locked host memory from coltt_b200_host_alloc (freed with the array).  Query batches
+    assembled in such a buffer are DMA'd in place by the host-pointer search calls instead of being staged first."""
+    import weakref
+    import numpy as np
+    dt = np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = max(1, int(np.prod(shape)) * dt.itemsize)
+    L = lib()
+    p = C.c_void_p()
+    check(L.coltt_b200_host_alloc(nbytes, C.byref(p)))
+    raw = (C.c_uint8 * nbytes).from_address(p.value)
+    weakref.finalize(raw, L.coltt_b200_host_free, C.c_void_p(p.value))
+    arr = np.frombuffer(raw, dtype=dt, count=int(np.prod(shape))).reshape(shape)   # keeps `raw` alive through .base
+    return arr

@@ -335,8 +335,9 @@ static int sharded_search_host(Comm& cm, Store* shard, const float* queries, siz
   if ((rc = cm.q_in.ensure(qb)) || (rc = cm.out.ensure(hb)) || (rc = cm.counts.ensure(nq * 4)) || (rc = cm.h_q.ensure(qb)) ||
       (rc = cm.h_out.ensure(hb + nq * 4)))
     return rc;
-  std::memcpy(cm.h_q.p, queries, qb);
-  COLTT_CUDA(cudaMemcpyAsync(cm.q_in.p, cm.h_q.p, qb, cudaMemcpyHostToDevice, cm.stream));
+  const bool direct = host_ptr_is_pinned(queries);     // a page-locked caller buffer is the DMA source itself (store.cu)
+  if (!direct) std::memcpy(cm.h_q.p, queries, qb);
+  COLTT_CUDA(cudaMemcpyAsync(cm.q_in.p, direct ? (const void*)queries : (const void*)cm.h_q.p, qb, cudaMemcpyHostToDevice, cm.stream));
   rc = sharded_search_enqueue(cm, shard, cm.q_in.p, nq, k, select_mode, math_mode, (Hit*)cm.out.p, (int*)cm.counts.p, cm.stream);
   if (rc) return rc;
   const bool want = out_ids && out_scores && out_counts;     // ranks other than the caller's front rank may pass NULL outputs

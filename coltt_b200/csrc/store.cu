@@ -106,6 +106,13 @@ int PinnedBuf::ensure(size_t bytes) {
   cap = bytes;
   return COLTT_OK;
 }
+// cudaPointerGetAttributes on an ordinary malloc pointer succeeds with cudaMemoryTypeUnregistered (CUDA >= 11); ~1 us.
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 PinnedBuf::~PinnedBuf() {
   if (p) cudaFreeHost(p);
 }
@@ -741,11 +748,15 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
   rc = c.counts.ensure(nq * 4); if (rc) return rc;
   rc = c.h_q.ensure(nq * dim * 4); if (rc) return rc;
   rc = c.h_out.ensure(nq * (size_t)k * sizeof(Hit) + nq * 4); if (rc) return rc;
-  std::memcpy(c.h_q.p, queries, nq * (size_t)dim * 4);
+  // A caller buffer that is already page-locked (coltt_b200_host_alloc, cudaHostRegister, a pinned torch tensor) is the DMA
+  // source itself; anything else is staged through this scratch's pinned buffer first (one host memcpy of nq*dim*4 bytes).
+  const bool direct = host_ptr_is_pinned(queries);
+  if (!direct) std::memcpy(c.h_q.p, queries, nq * (size_t)dim * 4);
+  const void* h_src = direct ? (const void*)queries : (const void*)c.h_q.p;
   Hit* h_hits = (Hit*)c.h_out.p;
   int* h_counts = (int*)((uint8_t*)c.h_out.p + nq * (size_t)k * sizeof(Hit));
   auto h2d = [&]() -> int {
-    COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, c.h_q.p, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+    COLTT_CUDA(cudaMemcpyAsync(c.q_in.p, h_src, nq * (size_t)dim * 4, cudaMemcpyHostToDevice, st));
     return COLTT_OK;
   };
   auto d2h = [&]() -> int {
@@ -760,9 +771,17 @@ int Store::search_host(const float* queries, size_t nq, const uint64_t* cand_ids
     if (rc) return rc;
     if ((rc = d2h())) return rc;
   } else {
-    // H2D + search + D2H as one (cached) graph: every pointer involved is this scratch's own
-    const GraphKey key{c.q_in.p, nq, k, select_mode, math_mode, c.out.p, c.counts.p, st, n_rows, d_rows, true};
-    rc = enqueue_cached(c, st, key, timed, h2d, d2h);
+    // H2D + search + D2H as one (cached) graph: every pointer involved is this scratch's own.  With a pinned caller buffer
+    // the H2D stays outside the graph (its source changes from call to call) and the graph is search + D2H.
+    if (direct) {
+      if ((rc = h2d())) return rc;
+      auto nop = []() -> int { return COLTT_OK; };
+      const GraphKey key{c.q_in.p, nq, k, select_mode, math_mode, c.out.p, c.counts.p, st, n_rows, d_rows, 2};
+      rc = enqueue_cached(c, st, key, timed, nop, d2h);
+    } else {
+      const GraphKey key{c.q_in.p, nq, k, select_mode, math_mode, c.out.p, c.counts.p, st, n_rows, d_rows, 1};
+      rc = enqueue_cached(c, st, key, timed, h2d, d2h);
+    }
     if (rc) return rc;
   }
   COLTT_CUDA(cudaStreamSynchronize(st));
@@ -810,7 +829,7 @@ int Store::search_dev(const void* d_queries, size_t nq, int k, int select_mode, 
   cudaGetLastError();
   int rc;
   if (stream_) {
-    const GraphKey key{d_queries, nq, k, select_mode, math_mode, d_out, d_counts, st, n_rows, d_rows, false};
+    const GraphKey key{d_queries, nq, k, select_mode, math_mode, d_out, d_counts, st, n_rows, d_rows, 0};
     auto nop = []() -> int { return COLTT_OK; };
     rc = enqueue_cached(*ctx, st, key, timed, nop, nop);
   } else {
@@ -976,6 +995,25 @@ COLTT_API int coltt_b200_store_set_timing(coltt_store* s, int on) {
   return COLTT_OK;
 }
 COLTT_API uint64_t coltt_b200_kernel_launches(void) { return coltt::launch_count(); }
+
+COLTT_API int coltt_b200_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return fail(COLTT_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(COLTT_ERR_NO_DEVICE, "no CUDA device visible: libcoltt_b200 has no CPU fallback");
+  }
+  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return fail(COLTT_ERR_NOMEM, "cudaHostAlloc failed");
+  }
+  return COLTT_OK;
+}
+COLTT_API void coltt_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 
 // ---- test/diagnostic hooks (not part of include/coltt_b200.h) --------------------------------
 // Raw tcgen05 accumulators of the FAST filter for host queries: out_acc is a host [nq][n_rows] fp32.

@@ -41,12 +41,14 @@ struct PinnedBuf {
   int ensure(size_t bytes);
   ~PinnedBuf();
 };
+bool host_ptr_is_pinned(const void* p);   // page-locked host memory known to CUDA: usable as a DMA source in place
 
 // A search whose arguments repeat (same buffers, shapes and modes — a serving loop, bench.py) is captured once into a CUDA
 // graph and replayed: the five to seven dependent launches of a FAST search then cost one graph launch, which removes
 // ~40 us of launch gaps from a 0.45 ms step.  Entries are dropped when any scratch buffer was reallocated since capture.
 struct GraphKey {
-  const void* q; size_t nq; int k, sel, math; const void* out; const void* counts; cudaStream_t st; size_t n_rows; const void* rows; bool host;
+  const void* q; size_t nq; int k, sel, math; const void* out; const void* counts; cudaStream_t st; size_t n_rows; const void* rows;
+  int host;                         // 0 = device in/out, 1 = + H2D from the pinned staging buffer and D2H, 2 = + D2H only
   bool operator==(const GraphKey& o) const {
     return q == o.q && nq == o.nq && k == o.k && sel == o.sel && math == o.math && out == o.out && counts == o.counts && st == o.st &&
            n_rows == o.n_rows && rows == o.rows && host == o.host;

@@ -307,6 +307,15 @@ COLTT_API float coltt_b200_fast_eps_rel(uint32_t dim);
 /* Kernels this library has launched in this process so far (bench.py's gpu_launches). */
 COLTT_API uint64_t coltt_b200_kernel_launches(void);
 
+/* ---- page-locked host buffers ------------------------------------------------------------------------------------------
+ * Every host-pointer search entry point (coltt_b200_store_search, coltt_b200_sharded_search, ...) checks whether the
+ * caller's query buffer is page-locked memory known to CUDA: if so it is the DMA source itself; otherwise the queries are
+ * first copied into the handle's own pinned staging buffer (one host memcpy of nq * dim * 4 bytes: ~70 us of a 0.5 ms
+ * batch at config 2).  A host that assembles its batches in a buffer from coltt_b200_host_alloc (the micro-batcher,
+ * INTEGRATION.md) therefore skips that copy.  The library never keeps the pointer past the call.  Needs a GPU. */
+COLTT_API int coltt_b200_host_alloc(size_t bytes, void** out);
+COLTT_API void coltt_b200_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,9 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(coltt_b200.ColttError) as e:
         coltt_b200.VectorSpace("c", coltt_b200.Metadata(8))
     assert e.value.code == -8 and "no CPU fallback" in e.value.message
+    with pytest.raises(coltt_b200.ColttError) as e:          # page-locked buffers are a CUDA service too
+        coltt_b200.pinned_empty((4, 8))
+    assert e.value.code == -8
 
 
 def test_product_never_touches_the_oracle():

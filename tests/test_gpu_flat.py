@@ -328,3 +328,30 @@ def test_mutations_wait_for_an_asynchronous_search(cb, oracle):
             assert_same_hits(gi[j], gs[j], wi, ws, f"trial {trial} q{j}: the search saw a half-mutated store")
         sp.ChangedVertices(ids, vecs)                                            # restore for the next trial
     sp.close()
+
+
+def test_page_locked_caller_buffers_are_searched_in_place(cb, oracle):
+    """Host-pointer searches DMA straight out of a caller buffer that is page-locked (coltt_b200_host_alloc) and stage ordinary
+    memory through the handle's pinned buffer: same answer either way, repeated calls (the second and later ones replay the
+    cached graph, whose H2D node must not have captured the caller's pointer), and a buffer whose contents change between calls."""
+    n, d, k, nq = 30_000, 768, 10, 40
+    ids, vecs = sparse_ids(n), normal(n, d)
+    sp, st = _pair(cb, oracle, d, 0, 3, ids, vecs)
+    pin = cb.pinned_empty((nq, d), np.float32)
+    assert pin.shape == (nq, d) and pin.dtype == np.float32 and pin.flags["C_CONTIGUOUS"]
+    for mm in (cb.MATH_FAST, cb.MATH_EXACT):
+        for trial in range(4):
+            qs = normal(nq, d, QUERY_SEED + 50 + trial)
+            pin[...] = qs                                  # the same pinned buffer, new contents
+            gi, gs, gc = sp.BatchVertexSearch(pin, k, select_mode=cb.SELECT_NEAREST, math_mode=mm)
+            pi, ps, pc = sp.BatchVertexSearch(qs, k, select_mode=cb.SELECT_NEAREST, math_mode=mm)      # pageable twin
+            assert np.array_equal(gi, pi) and gs.tobytes() == ps.tobytes() and np.array_equal(gc, pc)
+            for j in range(0, nq, 9):
+                wi, ws = st.search_total_order(qs[j], k, select_mode=oracle.NEAREST)
+                assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], wi, ws, f"mm={mm} trial={trial} j={j}")
+    # a slice that does not start at the allocation's base is still inside the page-locked range
+    gi, gs, gc = sp.BatchVertexSearch(pin[8:24], k, select_mode=cb.SELECT_NEAREST)
+    for j in (0, 15):
+        wi, ws = st.search_total_order(np.array(pin[8 + j]), k, select_mode=oracle.NEAREST)
+        assert_same_hits(gi[j, :gc[j]], gs[j, :gc[j]], wi, ws, f"slice j={j}")
+    sp.close()
