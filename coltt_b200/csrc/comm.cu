@@ -100,7 +100,9 @@ struct Comm {
   int p2p = 0;                         // 0 = not set up yet, 1 = active, -1 = unavailable: NCCL path
   uint8_t* xbuf = nullptr;             // [2][xcap] this rank's messages of even / odd steps
   size_t xcap = 0;
-  uint32_t* flags = nullptr;           // [0..1] sequence number last published per slot, [2] timeout marker
+  uint32_t* flags = nullptr;           // [0..1] sequence number last published per slot
+  uint32_t* h_marker = nullptr;        // page-locked, device-mapped: the step at which the wait kernel gave up on a peer (0 = never).
+                                       // The host reads it without a copy or a synchronisation; once set the communicator is broken.
   std::vector<void*> peer_x, peer_f, ipc_opened;
   DeviceBuf d_bases[2], d_peer_flags;  // device tables: list base addresses per slot; peers' flag words
   uint32_t seq = 0;
@@ -109,6 +111,7 @@ struct Comm {
     for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     if (xbuf) cudaFree(xbuf);
     if (flags) cudaFree(flags);
+    if (h_marker) cudaFreeHost(h_marker);
     if (comm && nccl().ok) nccl().CommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -151,7 +154,11 @@ __global__ void xchg_wait_kernel(const unsigned long long* peer_flags, int world
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
     if ((int32_t)(v - seq) >= 0) break;                  // sequence numbers only grow
-    if (clock64() - t0 > timeout_cycles) { atomicExch(timeout_marker, seq ? seq : 1u); break; }
+    if (clock64() - t0 > timeout_cycles) {               // the marker lives in mapped host memory: plain store + system fence
+      *reinterpret_cast<volatile uint32_t*>(timeout_marker) = seq ? seq : 1u;
+      __threadfence_system();
+      break;
+    }
     __nanosleep(200);
   }
 }
@@ -179,6 +186,10 @@ static int p2p_setup(Comm& cm, size_t need) {
   cm.ipc_opened.clear(); cm.peer_x.assign(cm.world, nullptr); cm.peer_f.assign(cm.world, nullptr);
   if (cm.xbuf) { cudaFree(cm.xbuf); cm.xbuf = nullptr; }
   if (!cm.flags) { COLTT_CUDA(cudaMalloc(&cm.flags, 64)); COLTT_CUDA(cudaMemset(cm.flags, 0, 64)); cm.seq = 0; }
+  if (!cm.h_marker) {
+    COLTT_CUDA(cudaHostAlloc((void**)&cm.h_marker, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *cm.h_marker = 0;
+  }
   const size_t cap = std::max<size_t>((need + 255) / 256 * 256, 1u << 20);
   XchgInfo mine{};
   mine.ok = 1;
@@ -269,7 +280,7 @@ static int exchange_and_merge(Comm& cm, size_t nq, int k, int nearest, Hit* d_ou
     const uint32_t slot = cm.seq & 1u;
     xchg_signal_kernel<<<1, 1, 0, st>>>(cm.flags + slot, cm.seq);
     static const long long timeout_cycles = [] { const char* e = getenv("COLTT_P2P_TIMEOUT_MS"); return (long long)(e ? atoi(e) : 20000) * 1500000ll; }();
-    xchg_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long*)cm.d_peer_flags.p, cm.world, slot, cm.seq, cm.flags + 2, timeout_cycles);
+    xchg_wait_kernel<<<1, 32, 0, st>>>((const unsigned long long*)cm.d_peer_flags.p, cm.world, slot, cm.seq, cm.h_marker, timeout_cycles);
     count_launch(2);
     COLTT_CUDA(cudaGetLastError());
     MergeParams mp{};
@@ -290,28 +301,30 @@ static int exchange_and_merge(Comm& cm, size_t nq, int k, int nearest, Hit* d_ou
 }
 
 
+// Did the wait kernel give up on a peer?  Checked after every synchronised host call, and at the start of every call for
+// the enqueue-only entry points (whose failure can only surface at the next call).  Sticky: the ranks' sequence numbers no
+// longer agree after a timeout, so the communicator stays failed until it is destroyed.
+static int check_exchange_timeout(Comm& cm) {
+  if (cm.p2p != 1 || !cm.h_marker) return COLTT_OK;
+  const uint32_t marker = *reinterpret_cast<volatile uint32_t*>(cm.h_marker);
+  if (marker) return fail(COLTT_ERR_CUDA, "sharded search: a peer rank did not publish its results within the exchange timeout (step " + std::to_string(marker) + ")");
+  return COLTT_OK;
+}
+
 // Enqueue-only: local search into the send buffer, all-gather, merge into d_out / d_counts, all on `st`.
 static int sharded_search_enqueue(Comm& cm, Store* shard, const void* d_queries, size_t nq, int k, int select_mode, int math_mode,
                                   Hit* d_out, int* d_counts, cudaStream_t st) {
   if (select_mode != COLTT_SELECT_COMPAT && select_mode != COLTT_SELECT_NEAREST) return fail(COLTT_ERR_INVALID, "bad select mode");
   if (shard->device != cm.device) return fail(COLTT_ERR_INVALID, "shard and communicator live on different devices");
   uint8_t* msg = nullptr;
-  int rc = exchange_begin(cm, nq, k, &msg);
+  int rc = check_exchange_timeout(cm);
   if (rc) return rc;
+  if ((rc = exchange_begin(cm, nq, k, &msg))) return rc;
   Hit* s_hits = (Hit*)msg;
   int* s_cnt = (int*)(msg + nq * (size_t)k * sizeof(Hit));
   rc = shard->search_dev(d_queries, nq, k, select_mode, math_mode, s_hits, s_cnt, st);   // caller stream: enqueue only
   if (rc) return rc;
   return exchange_and_merge(cm, nq, k, select_mode == COLTT_SELECT_NEAREST, d_out, d_counts, st);
-}
-
-// after a synchronised host call: did the wait kernel give up on a peer?
-static int check_exchange_timeout(Comm& cm) {
-  if (cm.p2p != 1) return COLTT_OK;
-  uint32_t marker = 0;
-  COLTT_CUDA(cudaMemcpy(&marker, cm.flags + 2, 4, cudaMemcpyDeviceToHost));
-  if (marker) return fail(COLTT_ERR_CUDA, "sharded search: a peer rank did not publish its results within the exchange timeout (step " + std::to_string(marker) + ")");
-  return COLTT_OK;
 }
 
 static void unpack(const Hit* h, const int* c, size_t nq, int k, uint64_t* out_ids, float* out_scores, int32_t* out_counts) {
@@ -500,7 +513,10 @@ COLTT_API int coltt_b200_sharded_search_dev(coltt_comm* c, coltt_store* shard, c
   int rc = coltt::sharded_search_enqueue(cm, reinterpret_cast<coltt::Store*>(shard), d_queries, nq, k, select_mode, math_mode, (coltt::Hit*)d_out,
                                          (int*)d_counts, st);
   if (rc) return rc;
-  if (!stream) COLTT_CUDA(cudaStreamSynchronize(st));
+  if (!stream) {
+    COLTT_CUDA(cudaStreamSynchronize(st));
+    return coltt::check_exchange_timeout(cm);
+  }
   return COLTT_OK;
 }
 

@@ -75,3 +75,56 @@ def test_single_process_multi_gpu_through_the_c_abi():
     L.coltt_b200_shutdown()
     for s in shards:
         s.close()
+
+
+_TIMEOUT_SCRIPT = r"""
+import ctypes as C, sys
+import numpy as np
+import coltt_b200 as cb
+from coltt_b200 import _lib
+from tests.util import normal, sparse_ids
+L = _lib.lib()
+g, n, d, k, nq = 2, 4000, 64, 5, 8
+ids, vecs = sparse_ids(n), normal(n, d)
+shards = []
+for r in range(g):
+    sp = cb.VectorSpace("t", cb.Metadata(d, cb.Distance_Cosine, cb.Quantization_None), device=r)
+    sp.ChangedVertices(ids[r::g], vecs[r::g])
+    shards.append(sp)
+comms = (C.c_void_p * g)()
+_lib.check(L.coltt_b200_init((C.c_int * g)(0, 1), g, comms))
+sh = (C.c_void_p * g)(*[s._h for s in shards])
+qs = normal(nq, d, 9)
+oi, osc, oc = np.zeros((nq, k), np.uint64), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
+args = (qs.ctypes.data_as(C.POINTER(C.c_float)), nq, k, cb.SELECT_NEAREST, cb.MATH_EXACT, oi.ctypes.data_as(C.POINTER(C.c_uint64)),
+        osc.ctypes.data_as(C.POINTER(C.c_float)), oc.ctypes.data_as(C.POINTER(C.c_int32)))
+_lib.check(L.coltt_b200_sharded_search_all(comms, sh, g, *args))          # a proper collective: sets the exchange up
+if L.coltt_b200_comm_exchange_mode(comms[0]) != 1:
+    print("NO_PEER_ACCESS")
+    sys.exit(0)
+rc = L.coltt_b200_sharded_search(comms[0], sh[0], *args)                  # rank 1 never arrives
+msg = (L.coltt_b200_last_error() or b"").decode()
+rc2 = L.coltt_b200_sharded_search(comms[0], sh[0], *args)                 # the communicator stays failed
+print("RC", rc, rc2, "|", msg)
+L.coltt_b200_shutdown()
+"""
+
+
+def test_a_peer_that_never_arrives_is_an_error_not_a_hang():
+    """The peer-memory exchange waits for the peers' flags with a deadline (COLTT_P2P_TIMEOUT_MS): a rank whose peer does not
+    join the collective gets COLTT_ERR_CUDA with a message naming the step, within the deadline, and the communicator then
+    refuses further searches (the ranks' sequence numbers no longer agree)."""
+    import time
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    env = dict(os.environ, COLTT_P2P="1", COLTT_P2P_TIMEOUT_MS="400", PYTHONPATH=ROOT)
+    t0 = time.time()
+    out = subprocess.run([sys.executable, "-c", _TIMEOUT_SCRIPT], capture_output=True, text=True, timeout=180, cwd=ROOT, env=env)
+    if "NO_PEER_ACCESS" in out.stdout:
+        pytest.skip("no peer access between the GPUs of this box")
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RC")]
+    assert line, out.stdout[-1500:] + out.stderr[-1500:]
+    rc, rc2 = int(line[0].split()[1]), int(line[0].split()[2])
+    assert rc == -2 and rc2 == -2 and "did not publish its results within the exchange timeout" in line[0], line[0]
+    assert time.time() - t0 < 120
