@@ -84,3 +84,34 @@ def test_bench_roofline_picks_the_binding_floor():
     assert r4["bound"] == "tensor" and r4["peak"] == 2 * 1364.4
     for key in ("bound", "achieved", "peak", "unit", "traffic"):
         assert key in r and key in r1
+
+
+def test_bench_clock_sampler_summarises_only_rows_inside_the_load_window():
+    """bench.py's nvidia-smi sampler time-stamps its rows; stop(t_from, t_to) must ignore rows printed before the load began
+    (idle clocks) and keep throttle reasons of the rows inside the window."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    row = "0, {sm}, 1965, 700.0, 0x0, Not Active, Not Active, Not Active, {cap}"
+    s.rows = [(10.00, row.format(sm=345, cap="Not Active")),       # idle, before the load
+              (10.30, row.format(sm=1965, cap="Not Active")),
+              (10.35, row.format(sm=1500, cap="Active")),
+              (10.40, row.format(sm=1440, cap="Active")),
+              (11.00, row.format(sm=345, cap="Not Active")),       # long after
+              (10.36, "garbage line")]
+    c = s.stop(10.25, 10.40)
+    assert c["samples"] == 3 and c["sm_mhz"] == 1500.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]
