@@ -582,6 +582,7 @@ def flat_arm(args, wl, torch, dist, world, rank, local, light=False):
 
     exchange = comm.exchange if comm is not None else None
     if comm is not None:
+        barrier()           # no peer is still reading this rank's exchange buffer (coltt_b200_comm_destroy's contract)
         comm.close()
     if rank != 0:
         sp.close()
@@ -741,6 +742,7 @@ def c5_arm(args, wl, torch, dist, world, rank, local):
         allp = [loc]
     exchange = comm.exchange if comm is not None else None
     if comm is not None:
+        barrier()
         comm.close()
     if rank != 0:
         h.close()

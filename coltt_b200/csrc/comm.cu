@@ -475,6 +475,10 @@ COLTT_API void coltt_b200_shutdown(void) {
     std::lock_guard<std::mutex> g(coltt::g_all_mu);
     all.swap(coltt::g_all);
   }
+  // peers read each other's exchange buffers while they merge: every device is idle before any rank's buffers are freed
+  for (Comm* cm : all)
+    if (cudaSetDevice(cm->device) == cudaSuccess) cudaDeviceSynchronize();
+  cudaGetLastError();
   for (Comm* cm : all) delete cm;
 }
 

@@ -261,6 +261,9 @@ COLTT_API void coltt_b200_shutdown(void);
 /* One process per GPU: rank 0 makes the 128-byte rendezvous blob, the host hands it to every rank, each joins. */
 COLTT_API int coltt_b200_comm_unique_id(void* out, size_t len);
 COLTT_API int coltt_b200_comm_init_rank(const void* unique_id, int rank, int world, int device, coltt_comm** out);
+/* With the peer-memory exchange the peers read this rank's exchange buffer while they merge: destroy a rank only after every
+ * rank has returned from the last sharded search (a host-side barrier in a multi-process host; coltt_b200_shutdown and
+ * coltt_b200_sharded_search_all take care of it inside one process). */
 COLTT_API void coltt_b200_comm_destroy(coltt_comm* c);
 COLTT_API int coltt_b200_comm_info(coltt_comm* c, int* rank, int* world, int* device);
 /* How this rank exchanges the per-shard lists: COLTT_EXCHANGE_UNDECIDED before the first sharded search (the choice is a

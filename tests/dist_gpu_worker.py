@@ -52,6 +52,7 @@ def main():
                     if not good:
                         print("MISMATCH (C-ABI comm)", quant, mode, j, gi[j], wi, flush=True)
                     ok &= bool(good)
+        dist.barrier()      # a peer may still be merging this rank's last list out of its exchange buffer (see coltt_b200_comm_destroy)
         comm.close()
         sp.close()
     # HNSW shards: one independent sub-graph per GPU, same all-gather + merge; the merged answer must equal the
@@ -83,6 +84,7 @@ def main():
                 print("MISMATCH (sharded hnsw)", j, gi[j], allp[j, order, 0], flush=True)
             ok &= bool(good)
     exchange = comm.exchange
+    dist.barrier()
     comm.close()
     sub.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
